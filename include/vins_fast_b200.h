@@ -1,0 +1,183 @@
+/* vins_fast_b200 -- C ABI of the B200-native stereo visual front-end.
+ *
+ * This is the drop-in boundary for ONE hot path of weihaoysgs/vins-fast:
+ *     estimator::FeatureTracker::TrackImage(t, img0, img1)      vins/estimator/feature_tracker.cpp:27-217
+ * and the pieces it is made of.  Every entry point below cites the reference interface it replaces.
+ * Plain pointers and sizes only (no torch / OpenCV / Eigen types).  The C++ class with the
+ * reference's API (vins_fast_b200/csrc/feature_tracker.hpp) and the Python mirror
+ * (vins_fast_b200/tracker.py) are thin layers over these calls.
+ *
+ * Conventions: all functions return vf_status (0 = VF_OK); nothing aborts or throws.  The caller owns
+ * every host buffer; the library owns all device memory.  A handle is one sequence of frames (one
+ * camera rig); handles are independent and may be driven from different host threads, but one handle
+ * is not thread-safe (same as the reference: one caller thread, estimator.cpp:152).
+ * There is NO CPU fallback: without a CUDA device every compute call fails with VF_ERR_CUDA.
+ */
+#ifndef VINS_FAST_B200_H
+#define VINS_FAST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VF_VERSION 100   /* 0.1.0 */
+
+typedef enum {
+    VF_OK = 0,
+    VF_ERR_INVALID_ARG = 1,   /* null pointer, bad size/stride, unsupported parameter               */
+    VF_ERR_CUDA = 2,          /* CUDA runtime error (no device, OOM, launch failure): see last_error */
+    VF_ERR_IO = 3,            /* YAML file missing / unreadable                                      */
+    VF_ERR_PARSE = 4,         /* YAML key missing or malformed, unknown camera model                 */
+    VF_ERR_STATE = 5          /* call order violated (e.g. debug getter before the first frame)      */
+} vf_status;
+
+/* camodocal model types on the hot path (CameraFactory.cc:96-136: model_type, case-insensitive). */
+enum { VF_CAM_MEI = 0, VF_CAM_PINHOLE = 1 };
+
+/* One camera: what CataCamera::Parameters / PinholeCamera::Parameters::readFromYamlFile read
+ * (CataCamera.cc:161-202, PinholeCamera.cc:145-183).  For MEI fx,fy,cx,cy = gamma1,gamma2,u0,v0. */
+typedef struct {
+    int32_t model;
+    int32_t image_width, image_height;   /* informational (as in the YAML) */
+    double xi, k1, k2, p1, p2, fx, fy, cx, cy;
+} vf_camera;
+
+/* Tracker configuration.  max_cnt / min_dist / flow_back are the reference's YAML keys
+ * (feature_tracker.cpp:10-12, euroc_stero.yaml:44-51).  lk_max_level / lk_win / quality_level are the
+ * reference's hard-coded call arguments (feature_tracker.cpp:42,90: Size(21,21), 3, 0.01), exposed as
+ * optional keys whose defaults equal the hard-coded values. */
+typedef struct {
+    int32_t width, height;        /* image size (euroc_stero.yaml:18-19 image_width / image_height) */
+    int32_t max_cnt;              /* MAX_CNT_FEATURES_PER_FRAME                                      */
+    int32_t min_dist;             /* MIN_DIST                                                        */
+    int32_t flow_back;            /* OPTICAL_FLOW_BACK                                               */
+    int32_t lk_max_level;         /* default 3   (maxLevel of the forward and stereo LK calls)       */
+    int32_t lk_win;               /* 21 only (window is compiled into the kernel)                    */
+    double quality_level;         /* default 0.01                                                    */
+    vf_camera cam[2];             /* [0] left, [1] right  (ReadIntrinsicParameter order, :301-308)   */
+    int32_t device;               /* CUDA device ordinal, -1 = current device                        */
+    int32_t use_cuda_graph;       /* 1 = replay the frame as a captured CUDA graph (default), 0 = plain launches */
+    void* cuda_stream;            /* optional cudaStream_t the frame work is ordered on (0 = library-owned stream) */
+} vf_config;
+
+/* One tracked feature = one entry of the featureFrame map (feature_tracker.cpp:173-213):
+ *   map[id] = { (0,[x,y,1,u,v,vx,vy]) [, (1,[xr,yr,1,ur,vr,vxr,vyr])] }.
+ * Records come back in ids_ order; right observations exist only where has_right != 0 and appear in the
+ * same relative order as ids_right_. */
+typedef struct {
+    int32_t id;          /* ids_[i]                                  */
+    int32_t track_cnt;   /* track_count_[i]                          */
+    int32_t has_right;   /* 1 if the stereo match survived (:128-133) */
+    float x, y;          /* current_un_distortion_kps_[i]            */
+    float u, v;          /* current_kps_[i]                          */
+    float vx, vy;        /* pts_velocity[i]                          */
+    float xr, yr, ur, vr, vxr, vyr;   /* right camera counterparts    */
+} vf_feature;
+
+typedef struct vf_tracker vf_tracker;   /* one stream of stereo frames                         */
+typedef struct vf_batch vf_batch;       /* S independent streams advanced in lock-step on one GPU */
+
+/* ---- configuration (replaces common::Setting + camodocal YAML readers) --------------------------- */
+void vf_config_default(vf_config* cfg);
+/* Reads the tracker keys of the estimator YAML (OpenCV %YAML:1.0 dialect): max_cnt, min_dist, flow_back,
+ * image_width, image_height [, lk_max_level, lk_win, quality_level] -- parameter.hpp:36-53,
+ * feature_tracker.cpp:8-18.  Missing mandatory key -> VF_ERR_PARSE (the reference would LOG(FATAL)). */
+vf_status vf_config_load_yaml(const char* estimator_yaml, vf_config* cfg);
+/* CameraFactory::generateCameraFromYamlFile (CameraFactory.cc:96-189) for MEI and PINHOLE. */
+vf_status vf_camera_load_yaml(const char* calib_yaml, vf_camera* cam);
+const char* vf_last_global_error(void);   /* message of the last failing call that had no handle */
+
+/* ---- one stream: replaces FeatureTracker ctor/dtor and TrackImage --------------------------------- */
+vf_status vf_tracker_create(const vf_config* cfg, vf_tracker** out);          /* feature_tracker.cpp:8-18, 301-308 */
+void vf_tracker_destroy(vf_tracker* t);
+vf_status vf_tracker_reset(vf_tracker* t);                                    /* back to the state after create   */
+/* TrackImage(t, img0, img1) (feature_tracker.cpp:27-217).  img0/img1: CV_8UC1, `height` rows of `width`
+ * pixels, row strides in bytes (>= width).  out: capacity >= max_cnt.  Copies the images to the device
+ * inside the call and keeps nothing of the caller's memory. */
+vf_status vf_tracker_track(vf_tracker* t, double time_s, const uint8_t* img0, size_t stride0,
+                           const uint8_t* img1, size_t stride1, vf_feature* out, int32_t* n_out);
+/* Same, images already resident on the device (device pointers, same layout). */
+vf_status vf_tracker_track_device(vf_tracker* t, double time_s, const uint8_t* d_img0, size_t stride0,
+                                  const uint8_t* d_img1, size_t stride1, vf_feature* out, int32_t* n_out);
+const char* vf_last_error(const vf_tracker* t);
+
+/* ---- S independent streams on one GPU (multi-stream throughput, BASELINE config 4) ---------------- */
+vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** out);
+void vf_batch_destroy(vf_batch* b);
+vf_status vf_batch_reset(vf_batch* b);
+int32_t vf_batch_size(const vf_batch* b);
+/* One frame for every stream.  times[s]; img0[s]/img1[s] host pointers (strides shared); out is
+ * n_streams * max_cnt records (stream s at out + s*max_cnt); n_out[s]. */
+vf_status vf_batch_track(vf_batch* b, const double* times, const uint8_t* const* img0, size_t stride0,
+                         const uint8_t* const* img1, size_t stride1, vf_feature* out, int32_t* n_out);
+/* Device-resident variant: d_img0/d_img1 each hold n_streams images back to back
+ * (image s at base + s*image_stride_bytes). */
+vf_status vf_batch_track_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
+                                size_t row_stride, size_t image_stride_bytes, vf_feature* out, int32_t* n_out);
+/* Asynchronous halves of vf_batch_track_device: enqueue the frame, then wait for / fetch its result. */
+vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
+                                  size_t row_stride, size_t image_stride_bytes);
+vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out);
+const char* vf_batch_last_error(const vf_batch* b);
+void* vf_batch_cuda_stream(const vf_batch* b);        /* cudaStream_t the frame work is ordered on      */
+int32_t vf_batch_launches_per_frame(const vf_batch* b); /* kernels launched by the last frame            */
+vf_tracker* vf_batch_stream(vf_batch* b, int32_t s);  /* borrowed view of stream s (for debug getters)  */
+
+/* ---- stage-level debug getters (parity tests only; valid after a frame) --------------------------- */
+enum {
+    VF_DBG_PYR_LEFT = 0,     /* arg = level;  uint8  w_l*h_l       current left pyramid level            */
+    VF_DBG_PYR_RIGHT = 1,    /* arg = level;  uint8                current right pyramid level           */
+    VF_DBG_EIG = 2,          /* float w*h     cornerMinEigenVal map of the current left image            */
+    VF_DBG_MASK = 3,         /* uint8 w*h     SetFeatureExtractorMask result (255 / 0)                   */
+    VF_DBG_FWD_PTS = 4,      /* float 2*n_prev  forward LK result                                        */
+    VF_DBG_FWD_STATUS = 5,   /* uint8 n_prev                                                             */
+    VF_DBG_REV_PTS = 6,      /* float 2*n_prev  reverse LK result                                        */
+    VF_DBG_REV_STATUS = 7,   /* uint8 n_prev                                                             */
+    VF_DBG_TEMPORAL_STATUS = 8, /* uint8 n_prev  after flow-back + InBorder                              */
+    VF_DBG_SORT_PERM = 9,    /* int32 n_tracked  std::sort permutation used by the mask                  */
+    VF_DBG_LR_PTS = 10,      /* float 2*n     left->right LK result                                      */
+    VF_DBG_LR_STATUS = 11,   /* uint8 n                                                                  */
+    VF_DBG_RL_PTS = 12,      /* float 2*n     right->left LK result                                      */
+    VF_DBG_RL_STATUS = 13,   /* uint8 n                                                                  */
+    VF_DBG_COUNTS = 14       /* int32[8]: n_prev, n_tracked, n_kept, n_new, n_total, n_right, n_local_max, landmark_id */
+};
+/* Copies the item into `buf` (capacity `cap_bytes`), writes the byte size to *size_out. */
+vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* buf, size_t cap_bytes, size_t* size_out);
+
+/* ---- stand-alone stage operators on HOST buffers (parity tests against the OpenCV routines) ------- */
+/* buildOpticalFlowPyramid + pyrDown (lkpyramid.cpp / pyramids.cpp; feature_tracker.cpp:41).
+ * levels_out: concatenated unpadded levels 0..n-1 (capacity >= 2*w*h); ws/hs: per-level sizes (cap 8). */
+vf_status vf_op_build_pyramid(const uint8_t* img, int32_t w, int32_t h, int32_t max_level, int32_t device,
+                              uint8_t* levels_out, int32_t* ws, int32_t* hs, int32_t* n_levels);
+/* calcScharrDeriv: out int16 interleaved (Ix,Iy), w*h*2. */
+vf_status vf_op_scharr(const uint8_t* img, int32_t w, int32_t h, int32_t device, int16_t* out);
+/* calcOpticalFlowPyrLK(prev, next, prev_pts, next_pts(in/out), status, winSize 21, max_level, criteria 30/0.01,
+ * flags = use_initial_flow ? OPTFLOW_USE_INITIAL_FLOW : 0, minEigThreshold 1e-4). */
+vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t h, const float* prev_pts,
+                   float* next_pts, uint8_t* status, int32_t n, int32_t max_level, int32_t use_initial_flow,
+                   int32_t device, int32_t* iters_out);
+/* cornerMinEigenVal(img, 3, ksize 3): out float w*h. */
+vf_status vf_op_min_eigen(const uint8_t* img, int32_t w, int32_t h, int32_t device, float* out);
+/* goodFeaturesToTrack(img, max_corners, quality, min_dist, mask): out_xy capacity 2*max_corners floats. */
+vf_status vf_op_good_features(const uint8_t* img, int32_t w, int32_t h, int32_t max_corners, double quality,
+                              int32_t min_dist, const uint8_t* mask, int32_t device, float* out_xy, int32_t* n_out);
+/* SetFeatureExtractorMask (feature_tracker.cpp:219-246) on given points/track counts: perm_out = std::sort
+ * order (n), keep_out = indices kept in order (cap n), mask_out optional w*h. */
+vf_status vf_op_set_mask(const float* pts, const int32_t* track_cnt, int32_t n, int32_t w, int32_t h,
+                         int32_t min_dist, int32_t device, int32_t* perm_out, int32_t* keep_out, int32_t* n_keep,
+                         uint8_t* mask_out);
+/* RemoveDistortion (feature_tracker.cpp:310-321): out_xy float 2*n. */
+vf_status vf_op_undistort(const vf_camera* cam, const float* uv, int32_t n, int32_t device, float* out_xy);
+
+/* Pinned host memory helpers (so callers can hand page-locked images to vf_tracker_track). */
+vf_status vf_host_alloc(size_t bytes, void** out);
+void vf_host_free(void* p);
+int32_t vf_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VINS_FAST_B200_H */

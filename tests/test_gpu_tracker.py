@@ -1,0 +1,160 @@
+"""Whole-path parity: vf_tracker_track (C ABI) against the CPU oracle on identical synthetic stereo sequences.
+The oracle's TrackImage (oracle/vf_oracle.c) is bit-identical to the cv2-based restatement of the reference
+(tests/test_oracle_golden.py), and the GPU path must be bit-identical to the oracle: ids, track counts, pixel
+coordinates, undistorted coordinates and velocities, frame after frame (north_star tolerances -- 0.01 px,
+99.5 % status agreement, 1e-6 undistorted -- are therefore met with zero slack)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import assert_frames_equal
+from oracle.camera import EUROC_CAM0, EUROC_CAM1, pinhole_for
+
+pytestmark = pytest.mark.gpu
+
+
+def _tracker(w, h, max_cnt, min_dist, flow_back, cam0, cam1, level=3, graph=True):
+    import vins_fast_b200 as v
+    cfg = v.make_config(w, h, max_cnt, min_dist, flow_back, cam0.__dict__, cam1.__dict__, lk_max_level=level,
+                        use_cuda_graph=graph)
+    return v.FeatureTracker(cfg)
+
+
+def _run_pair(oracle, frames, w, h, max_cnt, min_dist, flow_back, cam0, cam1, level=3, graph=True, check_debug=False):
+    from vins_fast_b200 import _lib
+    gpu = _tracker(w, h, max_cnt, min_dist, flow_back, cam0, cam1, level, graph)
+    ref = oracle.CFeatureTracker(cam0, cam1, w, h, max_cnt, min_dist, flow_back, level, 21, 0.01, 0)
+    total = 0
+    for k, (t, l, r) in enumerate(frames):
+        g = oracle.records_to_frame(gpu.track(t, l, r))
+        o = ref.track_image(t, l, r)
+        assert_frames_equal(g, o, f"frame {k}")
+        total += len(g["ids"])
+        if check_debug:
+            cnts = gpu.debug(_lib.DBG_COUNTS, dtype=np.int32)
+            assert cnts[4] == len(g["ids"]) and cnts[5] == len(g["ids_right"])
+            for lvl in range(4):
+                assert np.array_equal(gpu.debug(_lib.DBG_PYR_LEFT, lvl), oracle.Pyramid(l).level(lvl).ravel())
+                assert np.array_equal(gpu.debug(_lib.DBG_PYR_RIGHT, lvl), oracle.Pyramid(r).level(lvl).ravel())
+            eig = gpu.debug(_lib.DBG_EIG, dtype=np.float32).reshape(h, w)
+            assert np.array_equal(eig.view(np.uint32), oracle.min_eigen_val(l).view(np.uint32))
+    return total
+
+
+def test_euroc_sequence_bit_exact(lib, oracle, euroc_frames):
+    n = _run_pair(oracle, euroc_frames, 752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1)
+    assert n > 20 * 140
+
+
+def test_euroc_reference_defaults_200_15(lib, oracle, euroc_frames):
+    _run_pair(oracle, euroc_frames[:12], 752, 480, 200, 15, 1, EUROC_CAM0, EUROC_CAM1)
+
+
+def test_euroc_no_graph_and_debug_getters(lib, oracle, euroc_frames):
+    _run_pair(oracle, euroc_frames[:4], 752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1, graph=False, check_debug=True)
+
+
+def test_flow_back_off(lib, oracle, euroc_frames):
+    _run_pair(oracle, euroc_frames[:8], 752, 480, 150, 30, 0, EUROC_CAM0, EUROC_CAM1)
+
+
+def test_pinhole_720p_level4(lib, oracle):
+    from vins_fast_b200.synth import StereoSequence
+    seq = StereoSequence(2, 1280, 720)
+    cam = pinhole_for(1280, 720)
+    _run_pair(oracle, [seq.frame(k) for k in range(5)], 1280, 720, 400, 30, 1, cam, cam, level=4)
+
+
+def test_odd_size_and_small_max_cnt(lib, oracle, euroc_seq):
+    frames = [(t, np.ascontiguousarray(l[:301, :433]), np.ascontiguousarray(r[:301, :433]))
+              for t, l, r in (euroc_seq.frame(k) for k in range(6))]
+    cam = pinhole_for(433, 301, distorted=False)
+    _run_pair(oracle, frames, 433, 301, 20, 25, 1, cam, cam)
+
+
+def test_featureframe_contract_and_strides(lib, oracle, euroc_frames):
+    """featureFrame invariants the consumer asserts (feature_manager.cpp:36-43) + strided (non-contiguous) input."""
+    import vins_fast_b200 as v
+    tr = _tracker(752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1)
+    pad = np.zeros((480, 800), np.uint8)
+    ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
+    for t, l, r in euroc_frames[:3]:
+        pl, pr = pad.copy(), pad.copy()
+        pl[:, :752], pr[:, :752] = l, r
+        ff = tr.TrackImage(t, pl[:, :752], pr[:, :752])          # row stride 800
+        o = ref.track_image(t, l, r)
+        assert sorted(ff.keys()) == sorted(int(i) for i in o["ids"])
+        for fid, obs in ff.items():
+            assert 1 <= len(obs) <= 2 and obs[0][0] == 0 and obs[0][1][2] == 1.0
+            if len(obs) == 2:
+                assert obs[1][0] == 1 and obs[1][1][2] == 1.0
+        assert sum(len(o_) == 2 for o_ in ff.values()) == len(o["ids_right"])
+
+
+def test_reset_restarts_ids(lib, oracle, euroc_frames):
+    tr = _tracker(752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1)
+    a = [tr.track(t, l, r) for t, l, r in euroc_frames[:3]]
+    tr.reset()
+    b = [tr.track(t, l, r) for t, l, r in euroc_frames[:3]]
+    for x, y in zip(a, b):
+        assert x.tobytes() == y.tobytes()
+    assert a[0]["id"].min() == 0 and np.all(a[0]["vx"] == 0)
+
+
+def test_batch_streams_independent_and_deterministic(lib, oracle):
+    """BASELINE config 4 in small: S streams in one batch == S single-stream runs == oracle."""
+    import vins_fast_b200 as v
+    from vins_fast_b200.synth import StereoSequence
+    S, nfr = 3, 5
+    seqs = [StereoSequence(10 + s, 752, 480) for s in range(S)]
+    cfg = v.make_config(752, 480, 150, 30, 1, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__)
+    batch = v.Batch(cfg, S)
+    refs = [oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1) for _ in range(S)]
+    for k in range(nfr):
+        fr = [q.frame(k) for q in seqs]
+        res = batch.track([f[0] for f in fr], [f[1] for f in fr], [f[2] for f in fr])
+        for s in range(S):
+            assert_frames_equal(oracle.records_to_frame(res[s]), refs[s].track_image(*fr[s]), f"stream {s} frame {k}")
+    assert batch.launches_per_frame >= 10
+    batch.close()
+
+
+def test_device_resident_input(lib, oracle, euroc_frames):
+    torch = pytest.importorskip("torch")
+    tr = _tracker(752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1)
+    ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
+    for t, l, r in euroc_frames[:4]:
+        dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+        torch.cuda.synchronize()
+        g = oracle.records_to_frame(tr.track_device(t, dl.data_ptr(), dr.data_ptr(), 752))
+        assert_frames_equal(g, ref.track_image(t, l, r))
+
+
+def test_error_codes(lib):
+    import vins_fast_b200 as v
+    from vins_fast_b200 import _lib
+    cfg = v.make_config(752, 480, 150, 30)
+    cfg.lk_win = 15
+    with pytest.raises(v.VfError) as e:
+        v.FeatureTracker(cfg)._ensure()
+    assert e.value.status == _lib.VF_ERR_INVALID_ARG
+    cfg = v.make_config(32, 32, 150, 30)
+    with pytest.raises(v.VfError):
+        v.FeatureTracker(cfg)._ensure()
+    tr = v.FeatureTracker(v.make_config(752, 480, 150, 30))
+    with pytest.raises(v.VfError):
+        tr.track(0.0, np.zeros((480, 752), np.uint8), None)              # stereo is mandatory (feature_tracker.cpp:30)
+    with pytest.raises(v.VfError):
+        tr.track(0.0, np.zeros((100, 100), np.uint8), np.zeros((100, 100), np.uint8))
+    tr._ensure()
+    out = np.zeros(150, v.FEATURE_DTYPE)
+    n = C.c_int32(0)
+    img = np.zeros((480, 752), np.uint8)
+    st = lib.vf_tracker_track(tr._h, 0.0, img.ctypes.data, 100, img.ctypes.data, 752, out.ctypes.data, C.byref(n))
+    assert st == _lib.VF_ERR_INVALID_ARG and b"stride" in lib.vf_last_error(tr._h)
+    st = lib.vf_tracker_track(tr._h, 0.0, None, 752, img.ctypes.data, 752, out.ctypes.data, C.byref(n))
+    assert st == _lib.VF_ERR_INVALID_ARG
+    size = C.c_size_t(0)
+    st = lib.vf_tracker_debug_get(tr._h, _lib.DBG_EIG, 0, None, 0, C.byref(size))
+    assert st == _lib.VF_ERR_STATE                                        # no frame yet

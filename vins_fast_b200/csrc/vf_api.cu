@@ -1,0 +1,812 @@
+// C ABI of the B200-native stereo front-end (include/vins_fast_b200.h): handle management, HBM layout,
+// per-frame orchestration (streams, events, CUDA graph), debug getters and the stand-alone stage operators.
+//
+// One frame (= FeatureTracker::TrackImage, vins/estimator/feature_tracker.cpp:27-217) on the device:
+//
+//   main stream                                   side A                         side B
+//   ----------------------------------------     ---------------------------    ------------------------
+//   H2D times, H2D/D2D left image                                                H2D/D2D right image
+//   [graph: left chain]                                                          pyrdown right L1..Ln
+//     clear_frame, pyrdown left L1..Ln
+//     lk_temporal  (fwd + rev LK, status)         response_nms (eig + local max)
+//     select_tracked (compaction, std::sort        bucket_scan
+//        order, min_dist keep)                     bucket_scatter
+//     mask_and_max   <- joins side A
+//     gftt_select    (top-up corners, new ids)
+//   lk_stereo (L->R, R->L, undistort, velocity,   <- joins side B
+//              packed featureFrame records)
+//   D2H records + counters
+//
+// Only `parity` (frame index & 1) changes between launches, so the left chain is captured once per parity into a
+// CUDA graph and replayed.  Everything a frame hands to the next one (pyramid, points, ids, track counts,
+// undistorted points, landmark id, time) lives in HBM, double-buffered by parity; nothing but the two images
+// goes up and nothing but the <= max_cnt records comes down.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "vf_common.cuh"
+#include "vf_kernels.h"
+
+using namespace vf;
+
+static thread_local std::string g_last_error;
+
+extern "C" const char* vf_last_global_error(void) { return g_last_error.c_str(); }
+extern "C" void vf_internal_set_error(const char* msg) { g_last_error = msg ? msg : ""; }
+
+struct vf_tracker {
+    vf_batch* batch;
+    int stream_index;
+    bool owns_batch;
+};
+
+struct vf_batch {
+    vf_config cfg;
+    int S = 0, device = 0;
+    cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr;
+    bool own_main = false;
+    cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr;
+    DevBatch h;               // host copy of the device descriptor
+    DevBatch* d = nullptr;    // device copy
+    std::vector<void*> allocs;
+    vf_feature* pin_out[2] = {nullptr, nullptr};
+    int* pin_counters[2] = {nullptr, nullptr};
+    double* pin_times = nullptr;
+    long frame = 0;
+    int last_parity = -1;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    int launches = 0;
+    std::string err;
+    std::vector<vf_tracker> views;
+    size_t bytes_allocated = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (dev >= 0 && dev != prev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define VF_CUDA(bt, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t e__ = (call);                                                                           \
+        if (e__ != cudaSuccess) {                                                                           \
+            char buf__[512];                                                                                \
+            snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            if (bt) (bt)->err = buf__;                                                                      \
+            g_last_error = buf__;                                                                           \
+            return VF_ERR_CUDA;                                                                             \
+        }                                                                                                   \
+    } while (0)
+
+vf_status fail(vf_batch* b, vf_status st, const std::string& msg) {
+    if (b) b->err = msg;
+    g_last_error = msg;
+    return st;
+}
+
+int effective_levels(int w, int h, int max_level, int win) {   // buildOpticalFlowPyramid's early stop
+    int n = 1;
+    for (int l = 0; l <= max_level; ++l) {
+        n = l + 1;
+        const int nw = (w + 1) / 2, nh = (h + 1) / 2;
+        if (nw <= win || nh <= win) break;
+        w = nw; h = nh;
+    }
+    return n;
+}
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+template <typename T>
+vf_status dalloc(vf_batch* b, T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    VF_CUDA(b, cudaMalloc(&p, bytes));
+    VF_CUDA(b, cudaMemset(p, 0, bytes));
+    b->allocs.push_back(p);
+    b->bytes_allocated += bytes;
+    *out = reinterpret_cast<T*>(p);
+    return VF_OK;
+}
+
+vf_status alloc_pyramid(vf_batch* b, PyrView& pv, int W, int H, int n_levels, int S) {
+    memset(&pv, 0, sizeof(pv));
+    pv.n_levels = n_levels;
+    int w = W, h = H;
+    for (int l = 0; l < n_levels; ++l) {
+        pv.w[l] = w; pv.h[l] = h; pv.pitch[l] = align_up(w, 128);
+        b->h.lvl_stream_stride[l] = (size_t)pv.pitch[l] * h;
+        vf_status st = dalloc(b, &pv.lvl[l], (size_t)pv.pitch[l] * h * S);
+        if (st != VF_OK) return st;
+        w = (w + 1) / 2; h = (h + 1) / 2;
+    }
+    return VF_OK;
+}
+
+vf_status validate_config(const vf_config* c, int n_streams) {
+    if (!c) return fail(nullptr, VF_ERR_INVALID_ARG, "config is null");
+    if (n_streams < 1 || n_streams > 4096) return fail(nullptr, VF_ERR_INVALID_ARG, "n_streams must be in [1, 4096]");
+    if (c->width < 64 || c->height < 64 || c->width > 16384 || c->height > 16384)
+        return fail(nullptr, VF_ERR_INVALID_ARG, "image size must be within [64, 16384] in both dimensions");
+    if (c->max_cnt < 1 || c->max_cnt > 4096) return fail(nullptr, VF_ERR_INVALID_ARG, "max_cnt must be in [1, 4096]");
+    if (c->min_dist < 0 || c->min_dist > 1024) return fail(nullptr, VF_ERR_INVALID_ARG, "min_dist must be in [0, 1024]");
+    if (c->lk_win != 21) return fail(nullptr, VF_ERR_INVALID_ARG, "lk_win must be 21 (the reference's cv::Size(21,21))");
+    if (c->lk_max_level < 0 || c->lk_max_level >= kMaxLevels)
+        return fail(nullptr, VF_ERR_INVALID_ARG, "lk_max_level must be in [0, 7]");
+    if (!(c->quality_level > 0.0 && c->quality_level <= 1.0))
+        return fail(nullptr, VF_ERR_INVALID_ARG, "quality_level must be in (0, 1]");
+    for (int k = 0; k < 2; ++k) {
+        if (c->cam[k].model != VF_CAM_MEI && c->cam[k].model != VF_CAM_PINHOLE)
+            return fail(nullptr, VF_ERR_INVALID_ARG, "camera model must be VF_CAM_MEI or VF_CAM_PINHOLE");
+        if (c->cam[k].fx == 0.0 || c->cam[k].fy == 0.0)
+            return fail(nullptr, VF_ERR_INVALID_ARG, "camera focal lengths must be non-zero");
+    }
+    return VF_OK;
+}
+
+CamParams to_cam(const vf_camera& c) {
+    CamParams p;
+    p.model = c.model; p.xi = c.xi; p.k1 = c.k1; p.k2 = c.k2; p.p1 = c.p1; p.p2 = c.p2;
+    p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+    return p;
+}
+
+void destroy_batch(vf_batch* b) {
+    if (!b) return;
+    DeviceGuard g(b->device);
+    if (b->main) cudaStreamSynchronize(b->main);
+    for (int p = 0; p < 2; ++p) if (b->graph[p]) cudaGraphExecDestroy(b->graph[p]);
+    for (void* p : b->allocs) cudaFree(p);
+    if (b->d) cudaFree(b->d);
+    for (int p = 0; p < 2; ++p) {
+        if (b->pin_out[p]) cudaFreeHost(b->pin_out[p]);
+        if (b->pin_counters[p]) cudaFreeHost(b->pin_counters[p]);
+        if (b->ev_done[p]) cudaEventDestroy(b->ev_done[p]);
+    }
+    if (b->pin_times) cudaFreeHost(b->pin_times);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    if (b->ev_resp) cudaEventDestroy(b->ev_resp);
+    if (b->ev_right) cudaEventDestroy(b->ev_right);
+    if (b->ev_img) cudaEventDestroy(b->ev_img);
+    if (b->side_a) cudaStreamDestroy(b->side_a);
+    if (b->side_b) cudaStreamDestroy(b->side_b);
+    if (b->own_main && b->main) cudaStreamDestroy(b->main);
+    delete b;
+}
+
+vf_status reset_state(vf_batch* b) {
+    DeviceGuard g(b->device);
+    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    const size_t S = b->S;
+    for (int p = 0; p < 2; ++p) {
+        VF_CUDA(b, cudaMemsetAsync(b->h.counters[p], 0, sizeof(int) * S * C_COUNT, b->main));
+        VF_CUDA(b, cudaMemsetAsync(b->h.times[p], 0, sizeof(double) * S, b->main));
+        VF_CUDA(b, cudaMemsetAsync(b->h.right_ok[p], 0, S * b->h.cap, b->main));
+    }
+    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    b->frame = 0;
+    b->last_parity = -1;
+    return VF_OK;
+}
+
+// The kernels of the left chain, issued on main/side_a (directly, or under stream capture).
+vf_status issue_left_chain(vf_batch* b, int parity) {
+    const DevBatch& h = b->h;
+    int n = 0;
+    launch_clear_frame(b->d, h, parity, b->main); ++n;
+    VF_CUDA(b, cudaEventRecord(b->ev_fork, b->main));
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_fork, 0));
+    launch_response_nms(b->d, h, parity, b->side_a); ++n;
+    launch_bucket_scan(b->d, h, parity, b->side_a); ++n;
+    launch_bucket_scatter(b->d, h, parity, b->side_a); ++n;
+    VF_CUDA(b, cudaEventRecord(b->ev_resp, b->side_a));
+    const PyrView& pv = h.left[parity];
+    for (int l = 1; l < pv.n_levels; ++l) {
+        launch_pyrdown(pv.lvl[l - 1], pv.w[l - 1], pv.h[l - 1], pv.pitch[l - 1], h.lvl_stream_stride[l - 1], pv.lvl[l], pv.w[l],
+                       pv.h[l], pv.pitch[l], h.lvl_stream_stride[l], b->S, b->main);
+        ++n;
+    }
+    launch_lk_temporal(b->d, h, parity, b->main); ++n;
+    launch_select_tracked(b->d, h, parity, b->main); ++n;
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_resp, 0));
+    launch_mask_and_max(b->d, h, parity, b->main); ++n;
+    launch_gftt_select(b->d, h, parity, b->main); ++n;
+    VF_CUDA(b, cudaGetLastError());
+    b->launches = n;
+    return VF_OK;
+}
+
+vf_status build_graph(vf_batch* b, int parity) {
+    cudaGraph_t graph = nullptr;
+    VF_CUDA(b, cudaStreamBeginCapture(b->main, cudaStreamCaptureModeThreadLocal));
+    vf_status st = issue_left_chain(b, parity);
+    cudaError_t e = cudaStreamEndCapture(b->main, &graph);
+    if (st != VF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+    VF_CUDA(b, e);
+    e = cudaGraphInstantiate(&b->graph[parity], graph, 0);
+    cudaGraphDestroy(graph);
+    VF_CUDA(b, e);
+    return VF_OK;
+}
+
+// Enqueue one frame.  img pointers: host or device (kind says which); image s of camera c at img[c] + s*img_stride
+// when `contiguous`, else at imgs[c][s].
+vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* img0, const uint8_t* const* img1,
+                        const uint8_t* base0, const uint8_t* base1, size_t image_stride, size_t stride0, size_t stride1,
+                        cudaMemcpyKind kind) {
+    DeviceGuard g(b->device);
+    if (!g.ok) return fail(b, VF_ERR_CUDA, "cudaSetDevice failed");
+    const DevBatch& h = b->h;
+    const int S = b->S, W = h.W, H = h.H, parity = (int)(b->frame & 1);
+    if (!times) return fail(b, VF_ERR_INVALID_ARG, "times is null");
+    // at most two frames in flight: the pinned staging of this parity was last used two frames ago
+    VF_CUDA(b, cudaEventSynchronize(b->ev_done[parity]));
+    if (stride0 < (size_t)W || stride1 < (size_t)W) return fail(b, VF_ERR_INVALID_ARG, "row stride is smaller than the image width");
+    for (int s = 0; s < S; ++s) {
+        const uint8_t* a = base0 ? base0 + (size_t)s * image_stride : (img0 ? img0[s] : nullptr);
+        const uint8_t* c = base1 ? base1 + (size_t)s * image_stride : (img1 ? img1[s] : nullptr);
+        // the reference asserts both images are non-empty (stereo only): feature_tracker.cpp:30
+        if (!a || !c) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
+    }
+    double* pt = b->pin_times + (size_t)parity * S;
+    for (int s = 0; s < S; ++s) pt[s] = times[s];
+    VF_CUDA(b, cudaMemcpyAsync(h.times[parity], pt, sizeof(double) * S, cudaMemcpyHostToDevice, b->main));
+    // right image + right pyramid on side B, overlapping the left chain
+    VF_CUDA(b, cudaEventRecord(b->ev_img, b->main));            // orders side B after the previous frame's lk_stereo
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_img, 0));
+    for (int s = 0; s < S; ++s) {
+        const uint8_t* a = base0 ? base0 + (size_t)s * image_stride : img0[s];
+        const uint8_t* c = base1 ? base1 + (size_t)s * image_stride : img1[s];
+        VF_CUDA(b, cudaMemcpy2DAsync(h.left[parity].lvl[0] + (size_t)s * h.lvl_stream_stride[0], h.left[parity].pitch[0], a,
+                                     stride0, W, H, kind, b->main));
+        VF_CUDA(b, cudaMemcpy2DAsync(h.right.lvl[0] + (size_t)s * h.lvl_stream_stride[0], h.right.pitch[0], c, stride1, W, H,
+                                     kind, b->side_b));
+    }
+    int n_launch = 0;
+    for (int l = 1; l < h.right.n_levels; ++l) {
+        launch_pyrdown(h.right.lvl[l - 1], h.right.w[l - 1], h.right.h[l - 1], h.right.pitch[l - 1], h.lvl_stream_stride[l - 1],
+                       h.right.lvl[l], h.right.w[l], h.right.h[l], h.right.pitch[l], h.lvl_stream_stride[l], S, b->side_b);
+        ++n_launch;
+    }
+    VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
+    // left chain
+    if (b->cfg.use_cuda_graph) {
+        if (!b->graph[parity]) {
+            vf_status st = build_graph(b, parity);
+            if (st != VF_OK) return st;
+        }
+        VF_CUDA(b, cudaGraphLaunch(b->graph[parity], b->main));
+    } else {
+        vf_status st = issue_left_chain(b, parity);
+        if (st != VF_OK) return st;
+    }
+    n_launch += b->launches;
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
+    launch_lk_stereo(b->d, h, parity, b->main); ++n_launch;
+    VF_CUDA(b, cudaGetLastError());
+    VF_CUDA(b, cudaMemcpyAsync(b->pin_out[parity], h.out, sizeof(vf_feature) * (size_t)S * h.cap, cudaMemcpyDeviceToHost, b->main));
+    VF_CUDA(b, cudaMemcpyAsync(b->pin_counters[parity], h.counters[parity], sizeof(int) * (size_t)S * C_COUNT,
+                               cudaMemcpyDeviceToHost, b->main));
+    VF_CUDA(b, cudaEventRecord(b->ev_done[parity], b->main));
+    b->launches = n_launch;
+    b->last_parity = parity;
+    b->frame++;
+    return VF_OK;
+}
+
+vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out) {
+    if (b->last_parity < 0) return fail(b, VF_ERR_STATE, "no frame has been enqueued");
+    DeviceGuard g(b->device);
+    const int p = b->last_parity, S = b->S, cap = b->h.cap;
+    VF_CUDA(b, cudaEventSynchronize(b->ev_done[p]));
+    for (int s = 0; s < S; ++s) {
+        const int n = b->pin_counters[p][s * C_COUNT + C_N_TOTAL];
+        if (n_out) n_out[s] = n;
+        if (out) memcpy(out + (size_t)s * cap, b->pin_out[p] + (size_t)s * cap, sizeof(vf_feature) * (size_t)n);
+    }
+    return VF_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void vf_config_default(vf_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->width = 752; cfg->height = 480;
+    cfg->max_cnt = 200; cfg->min_dist = 15; cfg->flow_back = 1;   // euroc_stero.yaml:44-51
+    cfg->lk_max_level = 3; cfg->lk_win = 21; cfg->quality_level = 0.01;   // feature_tracker.cpp:42,90
+    for (int k = 0; k < 2; ++k) {
+        cfg->cam[k].model = VF_CAM_PINHOLE; cfg->cam[k].image_width = 752; cfg->cam[k].image_height = 480;
+        cfg->cam[k].fx = cfg->cam[k].fy = 460.0; cfg->cam[k].cx = 376.0; cfg->cam[k].cy = 240.0;
+    }
+    cfg->device = -1;
+    cfg->use_cuda_graph = 1;
+    cfg->cuda_stream = nullptr;
+}
+
+int32_t vf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+vf_status vf_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(nullptr, VF_ERR_INVALID_ARG, "out is null");
+    VF_CUDA((vf_batch*)nullptr, cudaMallocHost(out, bytes ? bytes : 1));
+    return VF_OK;
+}
+void vf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** out) {
+    if (!out) return fail(nullptr, VF_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    vf_status st = validate_config(cfg, n_streams);
+    if (st != VF_OK) return st;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VF_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    int dev = cfg->device;
+    if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) return fail(nullptr, VF_ERR_CUDA, "cudaGetDevice failed"); }
+    if (dev >= ndev) return fail(nullptr, VF_ERR_INVALID_ARG, "device ordinal out of range");
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(nullptr, VF_ERR_CUDA, "cudaSetDevice failed");
+
+    vf_batch* b = new vf_batch();
+    b->cfg = *cfg; b->S = n_streams; b->device = dev;
+    auto bail = [&](vf_status s) { std::string e = b->err; destroy_batch(b); g_last_error = e; return s; };
+#define TRY(x) do { vf_status s__ = (x); if (s__ != VF_OK) return bail(s__); } while (0)
+#define TRYC(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { b->err = std::string(#x) + ": " + cudaGetErrorString(e__); return bail(VF_ERR_CUDA); } } while (0)
+
+    if (cfg->cuda_stream) { b->main = (cudaStream_t)cfg->cuda_stream; b->own_main = false; }
+    else { TRYC(cudaStreamCreateWithFlags(&b->main, cudaStreamNonBlocking)); b->own_main = true; }
+    TRYC(cudaStreamCreateWithFlags(&b->side_a, cudaStreamNonBlocking));
+    TRYC(cudaStreamCreateWithFlags(&b->side_b, cudaStreamNonBlocking));
+    TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_resp, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_right, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_img, cudaEventDisableTiming));
+    for (int p = 0; p < 2; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_done[p], cudaEventDisableTiming));
+
+    DevBatch& h = b->h;
+    memset(&h, 0, sizeof(h));
+    const int S = n_streams, W = cfg->width, H = cfg->height, cap = cfg->max_cnt;
+    h.n_streams = S; h.W = W; h.H = H; h.cap = cap; h.min_dist = cfg->min_dist; h.flow_back = cfg->flow_back ? 1 : 0;
+    h.lk_max_level = cfg->lk_max_level; h.quality = cfg->quality_level;
+    h.n_levels = effective_levels(W, H, cfg->lk_max_level, cfg->lk_win);
+    h.bucket_bits = ((size_t)W * H <= (1u << 20)) ? 13 : kMaxBucketBits;
+    h.n_buckets = 1 << h.bucket_bits;
+    h.cand_cap = 1;
+    while (h.cand_cap < (size_t)W * H) h.cand_cap <<= 1;
+    h.cam[0] = to_cam(cfg->cam[0]); h.cam[1] = to_cam(cfg->cam[1]);
+    for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.left[p], W, H, h.n_levels, S));
+    TRY(alloc_pyramid(b, h.right, W, H, h.n_levels, S));
+    const size_t SC = (size_t)S * cap, SP = (size_t)S * W * H;
+    for (int p = 0; p < 2; ++p) {
+        TRY(dalloc(b, &h.kps[p], SC)); TRY(dalloc(b, &h.ids[p], SC)); TRY(dalloc(b, &h.cnt[p], SC));
+        TRY(dalloc(b, &h.un_left[p], SC)); TRY(dalloc(b, &h.un_right[p], SC)); TRY(dalloc(b, &h.right_ok[p], SC));
+        TRY(dalloc(b, &h.counters[p], (size_t)S * C_COUNT)); TRY(dalloc(b, &h.times[p], (size_t)S));
+    }
+    TRY(dalloc(b, &h.fwd_pts, SC)); TRY(dalloc(b, &h.fwd_st, SC)); TRY(dalloc(b, &h.rev_pts, SC)); TRY(dalloc(b, &h.rev_st, SC));
+    TRY(dalloc(b, &h.temporal_st, SC)); TRY(dalloc(b, &h.lr_pts, SC)); TRY(dalloc(b, &h.lr_st, SC)); TRY(dalloc(b, &h.rl_pts, SC));
+    TRY(dalloc(b, &h.rl_st, SC)); TRY(dalloc(b, &h.sort_perm, SC)); TRY(dalloc(b, &h.lk_iters, SC));
+    TRY(dalloc(b, &h.eig, SP)); TRY(dalloc(b, &h.mask, SP));
+    TRY(dalloc(b, &h.cand, (size_t)S * h.cand_cap)); TRY(dalloc(b, &h.cand_sorted, (size_t)S * h.cand_cap));
+    TRY(dalloc(b, &h.hist, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start, (size_t)S * (h.n_buckets + 1)));
+    TRY(dalloc(b, &h.bucket_fill, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz, (size_t)S * h.n_buckets));
+    if (cap > 512) TRY(dalloc(b, &h.conflict, (size_t)S * cap * ((cap + 31) / 32)));
+    TRY(dalloc(b, &h.out, SC));
+    TRYC(cudaMalloc(&b->d, sizeof(DevBatch)));
+    TRYC(cudaMemcpy(b->d, &h, sizeof(DevBatch), cudaMemcpyHostToDevice));
+    for (int p = 0; p < 2; ++p) {
+        TRYC(cudaMallocHost(&b->pin_out[p], sizeof(vf_feature) * SC));
+        TRYC(cudaMallocHost(&b->pin_counters[p], sizeof(int) * (size_t)S * C_COUNT));
+    }
+    TRYC(cudaMallocHost(&b->pin_times, sizeof(double) * (size_t)S * 2));
+    TRYC(select_tracked_prepare(cap));
+    TRYC(cudaDeviceSynchronize());
+    b->views.resize(S);
+    for (int s = 0; s < S; ++s) { b->views[s].batch = b; b->views[s].stream_index = s; b->views[s].owns_batch = false; }
+#undef TRY
+#undef TRYC
+    *out = b;
+    return VF_OK;
+}
+
+void vf_batch_destroy(vf_batch* b) { destroy_batch(b); }
+vf_status vf_batch_reset(vf_batch* b) { return b ? reset_state(b) : fail(nullptr, VF_ERR_INVALID_ARG, "batch is null"); }
+int32_t vf_batch_size(const vf_batch* b) { return b ? b->S : 0; }
+const char* vf_batch_last_error(const vf_batch* b) { return b ? b->err.c_str() : g_last_error.c_str(); }
+void* vf_batch_cuda_stream(const vf_batch* b) { return b ? (void*)b->main : nullptr; }
+int32_t vf_batch_launches_per_frame(const vf_batch* b) { return b ? b->launches : 0; }
+vf_tracker* vf_batch_stream(vf_batch* b, int32_t s) { return (b && s >= 0 && s < b->S) ? &b->views[s] : nullptr; }
+
+vf_status vf_batch_track(vf_batch* b, const double* times, const uint8_t* const* img0, size_t stride0,
+                         const uint8_t* const* img1, size_t stride1, vf_feature* out, int32_t* n_out) {
+    if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
+    if (!img0 || !img1) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
+    vf_status st = enqueue_frame(b, times, img0, img1, nullptr, nullptr, 0, stride0, stride1, cudaMemcpyHostToDevice);
+    if (st != VF_OK) return st;
+    return fetch_frame(b, out, n_out);
+}
+
+vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
+                                  size_t row_stride, size_t image_stride_bytes) {
+    if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
+    if (!d_img0 || !d_img1) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
+    if (b->S > 1 && image_stride_bytes < row_stride * (size_t)b->h.H)
+        return fail(b, VF_ERR_INVALID_ARG, "image_stride_bytes is smaller than one image");
+    return enqueue_frame(b, times, nullptr, nullptr, d_img0, d_img1, image_stride_bytes, row_stride, row_stride,
+                         cudaMemcpyDeviceToDevice);
+}
+
+vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out) {
+    if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
+    return fetch_frame(b, out, n_out);
+}
+
+vf_status vf_batch_track_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
+                                size_t row_stride, size_t image_stride_bytes, vf_feature* out, int32_t* n_out) {
+    vf_status st = vf_batch_enqueue_device(b, times, d_img0, d_img1, row_stride, image_stride_bytes);
+    if (st != VF_OK) return st;
+    return fetch_frame(b, out, n_out);
+}
+
+// ---- single stream = batch of one ----
+vf_status vf_tracker_create(const vf_config* cfg, vf_tracker** out) {
+    if (!out) return fail(nullptr, VF_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    vf_batch* b = nullptr;
+    vf_status st = vf_batch_create(cfg, 1, &b);
+    if (st != VF_OK) return st;
+    vf_tracker* t = new vf_tracker();
+    t->batch = b; t->stream_index = 0; t->owns_batch = true;
+    *out = t;
+    return VF_OK;
+}
+
+void vf_tracker_destroy(vf_tracker* t) {
+    if (!t) return;
+    if (t->owns_batch) { destroy_batch(t->batch); delete t; }
+}
+
+vf_status vf_tracker_reset(vf_tracker* t) {
+    if (!t) return fail(nullptr, VF_ERR_INVALID_ARG, "tracker is null");
+    return reset_state(t->batch);
+}
+
+const char* vf_last_error(const vf_tracker* t) { return t ? t->batch->err.c_str() : g_last_error.c_str(); }
+
+vf_status vf_tracker_track(vf_tracker* t, double time_s, const uint8_t* img0, size_t stride0, const uint8_t* img1,
+                           size_t stride1, vf_feature* out, int32_t* n_out) {
+    if (!t) return fail(nullptr, VF_ERR_INVALID_ARG, "tracker is null");
+    if (t->batch->S != 1) return fail(t->batch, VF_ERR_INVALID_ARG, "use vf_batch_track on a multi-stream batch");
+    if (!out || !n_out) return fail(t->batch, VF_ERR_INVALID_ARG, "out / n_out is null");
+    const uint8_t* a[1] = {img0};
+    const uint8_t* c[1] = {img1};
+    return vf_batch_track(t->batch, &time_s, a, stride0, c, stride1, out, n_out);
+}
+
+vf_status vf_tracker_track_device(vf_tracker* t, double time_s, const uint8_t* d_img0, size_t stride0, const uint8_t* d_img1,
+                                  size_t stride1, vf_feature* out, int32_t* n_out) {
+    if (!t) return fail(nullptr, VF_ERR_INVALID_ARG, "tracker is null");
+    if (t->batch->S != 1) return fail(t->batch, VF_ERR_INVALID_ARG, "use vf_batch_track_device on a multi-stream batch");
+    if (!out || !n_out) return fail(t->batch, VF_ERR_INVALID_ARG, "out / n_out is null");
+    if (stride0 != stride1) return fail(t->batch, VF_ERR_INVALID_ARG, "device images must share one row stride");
+    return vf_batch_track_device(t->batch, &time_s, d_img0, d_img1, stride0, stride0 * (size_t)t->batch->h.H, out, n_out);
+}
+
+// ---- debug getters ----
+vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* buf, size_t cap_bytes, size_t* size_out) {
+    if (!t || !size_out) return fail(nullptr, VF_ERR_INVALID_ARG, "tracker / size_out is null");
+    vf_batch* b = t->batch;
+    if (b->last_parity < 0) return fail(b, VF_ERR_STATE, "debug getters are valid after the first frame");
+    DeviceGuard g(b->device);
+    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    const DevBatch& h = b->h;
+    const int s = t->stream_index, p = b->last_parity, cap = h.cap;
+    const int* cn = b->pin_counters[p] + s * C_COUNT;
+    int cnt_now[C_COUNT];
+    VF_CUDA(b, cudaMemcpy(cnt_now, h.counters[p] + s * C_COUNT, sizeof(cnt_now), cudaMemcpyDeviceToHost));
+    (void)cn;
+    const size_t so = (size_t)s * cap;
+    const void* src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+        case VF_DBG_PYR_LEFT:
+        case VF_DBG_PYR_RIGHT: {
+            const PyrView& pv = (what == VF_DBG_PYR_LEFT) ? h.left[p] : h.right;
+            if (arg < 0 || arg >= pv.n_levels) return fail(b, VF_ERR_INVALID_ARG, "pyramid level out of range");
+            bytes = (size_t)pv.w[arg] * pv.h[arg];
+            *size_out = bytes;
+            if (!buf || cap_bytes < bytes) return fail(b, VF_ERR_INVALID_ARG, "buffer too small");
+            VF_CUDA(b, cudaMemcpy2D(buf, pv.w[arg], pv.lvl[arg] + (size_t)s * h.lvl_stream_stride[arg], pv.pitch[arg], pv.w[arg],
+                                    pv.h[arg], cudaMemcpyDeviceToHost));
+            return VF_OK;
+        }
+        case VF_DBG_EIG: src = h.eig + (size_t)s * h.W * h.H; bytes = sizeof(float) * (size_t)h.W * h.H; break;
+        case VF_DBG_MASK: src = h.mask + (size_t)s * h.W * h.H; bytes = (size_t)h.W * h.H; break;
+        case VF_DBG_FWD_PTS: src = h.fwd_pts + so; bytes = sizeof(float2) * (size_t)cnt_now[C_N_PREV]; break;
+        case VF_DBG_FWD_STATUS: src = h.fwd_st + so; bytes = (size_t)cnt_now[C_N_PREV]; break;
+        case VF_DBG_REV_PTS: src = h.rev_pts + so; bytes = sizeof(float2) * (size_t)cnt_now[C_N_PREV]; break;
+        case VF_DBG_REV_STATUS: src = h.rev_st + so; bytes = (size_t)cnt_now[C_N_PREV]; break;
+        case VF_DBG_TEMPORAL_STATUS: src = h.temporal_st + so; bytes = (size_t)cnt_now[C_N_PREV]; break;
+        case VF_DBG_SORT_PERM: src = h.sort_perm + so; bytes = sizeof(int) * (size_t)cnt_now[C_N_TRACKED]; break;
+        case VF_DBG_LR_PTS: src = h.lr_pts + so; bytes = sizeof(float2) * (size_t)cnt_now[C_N_TOTAL]; break;
+        case VF_DBG_LR_STATUS: src = h.lr_st + so; bytes = (size_t)cnt_now[C_N_TOTAL]; break;
+        case VF_DBG_RL_PTS: src = h.rl_pts + so; bytes = sizeof(float2) * (size_t)cnt_now[C_N_TOTAL]; break;
+        case VF_DBG_RL_STATUS: src = h.rl_st + so; bytes = (size_t)cnt_now[C_N_TOTAL]; break;
+        case VF_DBG_COUNTS: {
+            int v[8] = {cnt_now[C_N_PREV], cnt_now[C_N_TRACKED], cnt_now[C_N_KEPT], cnt_now[C_N_NEW],
+                        cnt_now[C_N_TOTAL], cnt_now[C_N_RIGHT], cnt_now[C_N_LOCALMAX], cnt_now[C_LANDMARK_ID]};
+            *size_out = sizeof(v);
+            if (!buf || cap_bytes < sizeof(v)) return fail(b, VF_ERR_INVALID_ARG, "buffer too small");
+            memcpy(buf, v, sizeof(v));
+            return VF_OK;
+        }
+        default: return fail(b, VF_ERR_INVALID_ARG, "unknown debug item");
+    }
+    *size_out = bytes;
+    if (bytes == 0) return VF_OK;
+    if (!buf || cap_bytes < bytes) return fail(b, VF_ERR_INVALID_ARG, "buffer too small");
+    VF_CUDA(b, cudaMemcpy(buf, src, bytes, cudaMemcpyDeviceToHost));
+    return VF_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// Stand-alone stage operators on host buffers.  Each mirrors one OpenCV / camodocal routine the reference calls,
+// runs the same kernels the tracker uses, and exists so the parity tests can pin every stage separately.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct TempPyr {
+    PyrView pv;
+    std::vector<void*> allocs;
+    ~TempPyr() { for (void* p : allocs) cudaFree(p); }
+};
+
+vf_status temp_pyramid(TempPyr& tp, const uint8_t* img, int w, int h, int max_level, cudaStream_t st) {
+    memset(&tp.pv, 0, sizeof(tp.pv));
+    const int n = effective_levels(w, h, max_level, kWin);
+    tp.pv.n_levels = n;
+    int lw = w, lh = h;
+    for (int l = 0; l < n; ++l) {
+        tp.pv.w[l] = lw; tp.pv.h[l] = lh; tp.pv.pitch[l] = align_up(lw, 128);
+        void* p = nullptr;
+        VF_CUDA((vf_batch*)nullptr, cudaMalloc(&p, (size_t)tp.pv.pitch[l] * lh));
+        tp.allocs.push_back(p);
+        tp.pv.lvl[l] = (uint8_t*)p;
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy2DAsync(tp.pv.lvl[0], tp.pv.pitch[0], img, w, w, h, cudaMemcpyHostToDevice, st));
+    for (int l = 1; l < n; ++l)
+        launch_pyrdown(tp.pv.lvl[l - 1], tp.pv.w[l - 1], tp.pv.h[l - 1], tp.pv.pitch[l - 1], 0, tp.pv.lvl[l], tp.pv.w[l],
+                       tp.pv.h[l], tp.pv.pitch[l], 0, 1, st);
+    VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
+    return VF_OK;
+}
+
+vf_status op_device(int device, DeviceGuard** g) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VF_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device >= ndev) return fail(nullptr, VF_ERR_INVALID_ARG, "device ordinal out of range");
+    *g = new DeviceGuard(device);
+    return VF_OK;
+}
+
+struct GuardHolder {
+    DeviceGuard* g = nullptr;
+    ~GuardHolder() { delete g; }
+};
+
+vf_status temp_batch(int w, int h, int cap, int min_dist, double quality, int device, vf_batch** out) {
+    vf_config cfg;
+    vf_config_default(&cfg);
+    cfg.width = w; cfg.height = h; cfg.max_cnt = cap; cfg.min_dist = min_dist; cfg.quality_level = quality;
+    cfg.device = device; cfg.use_cuda_graph = 0;
+    return vf_batch_create(&cfg, 1, out);
+}
+
+struct BatchHolder {
+    vf_batch* b = nullptr;
+    ~BatchHolder() { destroy_batch(b); }
+};
+
+}  // namespace
+
+extern "C" {
+
+vf_status vf_op_build_pyramid(const uint8_t* img, int32_t w, int32_t h, int32_t max_level, int32_t device,
+                              uint8_t* levels_out, int32_t* ws, int32_t* hs, int32_t* n_levels) {
+    if (!img || !levels_out || !ws || !hs || !n_levels) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
+    if (w < 1 || h < 1 || max_level < 0 || max_level >= kMaxLevels) return fail(nullptr, VF_ERR_INVALID_ARG, "bad size / level");
+    GuardHolder gh;
+    vf_status st = op_device(device, &gh.g);
+    if (st != VF_OK) return st;
+    TempPyr tp;
+    st = temp_pyramid(tp, img, w, h, max_level, 0);
+    if (st != VF_OK) return st;
+    size_t off = 0;
+    for (int l = 0; l < tp.pv.n_levels; ++l) {
+        VF_CUDA((vf_batch*)nullptr, cudaMemcpy2D(levels_out + off, tp.pv.w[l], tp.pv.lvl[l], tp.pv.pitch[l], tp.pv.w[l],
+                                                tp.pv.h[l], cudaMemcpyDeviceToHost));
+        ws[l] = tp.pv.w[l]; hs[l] = tp.pv.h[l];
+        off += (size_t)tp.pv.w[l] * tp.pv.h[l];
+    }
+    *n_levels = tp.pv.n_levels;
+    return VF_OK;
+}
+
+vf_status vf_op_scharr(const uint8_t* img, int32_t w, int32_t h, int32_t device, int16_t* out) {
+    if (!img || !out) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
+    if (w < 1 || h < 1) return fail(nullptr, VF_ERR_INVALID_ARG, "bad size");
+    GuardHolder gh;
+    vf_status st = op_device(device, &gh.g);
+    if (st != VF_OK) return st;
+    TempPyr tp;
+    st = temp_pyramid(tp, img, w, h, 0, 0);
+    if (st != VF_OK) return st;
+    int16_t* d = nullptr;
+    VF_CUDA((vf_batch*)nullptr, cudaMalloc(&d, sizeof(int16_t) * 2 * (size_t)w * h));
+    tp.allocs.push_back(d);
+    launch_scharr(tp.pv.lvl[0], w, h, tp.pv.pitch[0], d, 0);
+    VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy(out, d, sizeof(int16_t) * 2 * (size_t)w * h, cudaMemcpyDeviceToHost));
+    return VF_OK;
+}
+
+vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t h, const float* prev_pts, float* next_pts,
+                   uint8_t* status, int32_t n, int32_t max_level, int32_t use_initial_flow, int32_t device, int32_t* iters_out) {
+    if (!prev || !next || (n > 0 && (!prev_pts || !next_pts || !status))) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
+    if (w < 1 || h < 1 || n < 0 || max_level < 0 || max_level >= kMaxLevels) return fail(nullptr, VF_ERR_INVALID_ARG, "bad size / level");
+    if (n == 0) return VF_OK;   // calcOpticalFlowPyrLK with no points returns empty outputs
+    GuardHolder gh;
+    vf_status st = op_device(device, &gh.g);
+    if (st != VF_OK) return st;
+    TempPyr a, c;
+    st = temp_pyramid(a, prev, w, h, max_level, 0);
+    if (st != VF_OK) return st;
+    st = temp_pyramid(c, next, w, h, max_level, 0);
+    if (st != VF_OK) return st;
+    float2 *dp = nullptr, *dn = nullptr;
+    uint8_t* ds = nullptr;
+    int* di = nullptr;
+    VF_CUDA((vf_batch*)nullptr, cudaMalloc(&dp, sizeof(float2) * n)); a.allocs.push_back(dp);
+    VF_CUDA((vf_batch*)nullptr, cudaMalloc(&dn, sizeof(float2) * n)); a.allocs.push_back(dn);
+    VF_CUDA((vf_batch*)nullptr, cudaMalloc(&ds, n)); a.allocs.push_back(ds);
+    VF_CUDA((vf_batch*)nullptr, cudaMalloc(&di, sizeof(int) * n)); a.allocs.push_back(di);
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy(dp, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy(dn, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    launch_lk_op(a.pv, c.pv, dp, dn, ds, di, n, max_level, use_initial_flow, 0);
+    VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy(next_pts, dn, sizeof(float2) * n, cudaMemcpyDeviceToHost));
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy(status, ds, n, cudaMemcpyDeviceToHost));
+    if (iters_out) VF_CUDA((vf_batch*)nullptr, cudaMemcpy(iters_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    return VF_OK;
+}
+
+vf_status vf_op_min_eigen(const uint8_t* img, int32_t w, int32_t h, int32_t device, float* out) {
+    if (!img || !out) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
+    BatchHolder bh;
+    vf_status st = temp_batch(w, h, 1, 1, 0.01, device, &bh.b);
+    if (st != VF_OK) return st;
+    vf_batch* b = bh.b;
+    DeviceGuard g(b->device);
+    VF_CUDA(b, cudaMemcpy2DAsync(b->h.left[0].lvl[0], b->h.left[0].pitch[0], img, w, w, h, cudaMemcpyHostToDevice, b->main));
+    launch_clear_frame(b->d, b->h, 0, b->main);
+    launch_response_nms(b->d, b->h, 0, b->main);
+    VF_CUDA(b, cudaGetLastError());
+    VF_CUDA(b, cudaMemcpyAsync(out, b->h.eig, sizeof(float) * (size_t)w * h, cudaMemcpyDeviceToHost, b->main));
+    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    return VF_OK;
+}
+
+vf_status vf_op_good_features(const uint8_t* img, int32_t w, int32_t h, int32_t max_corners, double quality, int32_t min_dist,
+                              const uint8_t* mask, int32_t device, float* out_xy, int32_t* n_out) {
+    if (!img || !out_xy || !n_out) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
+    if (max_corners < 1) return fail(nullptr, VF_ERR_INVALID_ARG, "max_corners must be >= 1");
+    BatchHolder bh;
+    vf_status st = temp_batch(w, h, max_corners, min_dist, quality, device, &bh.b);
+    if (st != VF_OK) return st;
+    vf_batch* b = bh.b;
+    DeviceGuard g(b->device);
+    const size_t npx = (size_t)w * h;
+    VF_CUDA(b, cudaMemcpy2DAsync(b->h.left[0].lvl[0], b->h.left[0].pitch[0], img, w, w, h, cudaMemcpyHostToDevice, b->main));
+    launch_clear_frame(b->d, b->h, 0, b->main);
+    launch_response_nms(b->d, b->h, 0, b->main);
+    launch_bucket_scan(b->d, b->h, 0, b->main);
+    launch_bucket_scatter(b->d, b->h, 0, b->main);
+    if (mask) VF_CUDA(b, cudaMemcpyAsync(b->h.mask, mask, npx, cudaMemcpyHostToDevice, b->main));
+    else VF_CUDA(b, cudaMemsetAsync(b->h.mask, 255, npx, b->main));
+    launch_masked_max_from_mask(b->d, b->h, 0, b->main);
+    launch_gftt_select(b->d, b->h, 0, b->main);   // C_N_KEPT == 0 -> tops up to max_corners
+    VF_CUDA(b, cudaGetLastError());
+    int counters[C_COUNT];
+    VF_CUDA(b, cudaMemcpyAsync(counters, b->h.counters[0], sizeof(counters), cudaMemcpyDeviceToHost, b->main));
+    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    const int n = counters[C_N_NEW];
+    if (n > 0) VF_CUDA(b, cudaMemcpy(out_xy, b->h.kps[0], sizeof(float2) * (size_t)n, cudaMemcpyDeviceToHost));
+    *n_out = n;
+    return VF_OK;
+}
+
+vf_status vf_op_set_mask(const float* pts, const int32_t* track_cnt, int32_t n, int32_t w, int32_t h, int32_t min_dist,
+                         int32_t device, int32_t* perm_out, int32_t* keep_out, int32_t* n_keep, uint8_t* mask_out) {
+    if (n < 0 || (n > 0 && (!pts || !track_cnt)) || !n_keep) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
+    for (int i = 0; i < n; ++i) {   // mask.at<uchar>(pt) of the reference needs the rounded point inside the image
+        const long x = lrintf(pts[2 * i]), y = lrintf(pts[2 * i + 1]);
+        if (x < 0 || x >= w || y < 0 || y >= h) return fail(nullptr, VF_ERR_INVALID_ARG, "point outside the image");
+    }
+    BatchHolder bh;
+    vf_status st = temp_batch(w, h, n > 0 ? n : 1, min_dist, 0.01, device, &bh.b);
+    if (st != VF_OK) return st;
+    vf_batch* b = bh.b;
+    DeviceGuard g(b->device);
+    const DevBatch& hb = b->h;
+    // frame parity 0 consumes the "previous" state of parity 1
+    std::vector<int> ids(n > 0 ? n : 1), cnt(n > 0 ? n : 1);
+    std::vector<uint8_t> ones(n > 0 ? n : 1, 1);
+    for (int i = 0; i < n; ++i) { ids[i] = i; cnt[i] = track_cnt[i] - 1; }   // the kernel applies ++track_count
+    int counters[C_COUNT] = {0};
+    counters[C_N_TOTAL] = n;
+    VF_CUDA(b, cudaMemcpy(hb.counters[1], counters, sizeof(counters), cudaMemcpyHostToDevice));
+    if (n > 0) {
+        VF_CUDA(b, cudaMemcpy(hb.fwd_pts, pts, sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice));
+        VF_CUDA(b, cudaMemcpy(hb.temporal_st, ones.data(), (size_t)n, cudaMemcpyHostToDevice));
+        VF_CUDA(b, cudaMemcpy(hb.ids[1], ids.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+        VF_CUDA(b, cudaMemcpy(hb.cnt[1], cnt.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    launch_clear_frame(b->d, hb, 0, b->main);
+    launch_select_tracked(b->d, hb, 0, b->main);
+    launch_mask_and_max(b->d, hb, 0, b->main);
+    VF_CUDA(b, cudaGetLastError());
+    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    VF_CUDA(b, cudaMemcpy(counters, hb.counters[0], sizeof(counters), cudaMemcpyDeviceToHost));
+    const int nk = counters[C_N_KEPT];
+    *n_keep = nk;
+    if (perm_out && n > 0) VF_CUDA(b, cudaMemcpy(perm_out, hb.sort_perm, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (keep_out && nk > 0) VF_CUDA(b, cudaMemcpy(keep_out, hb.ids[0], sizeof(int) * (size_t)nk, cudaMemcpyDeviceToHost));
+    if (mask_out) VF_CUDA(b, cudaMemcpy(mask_out, hb.mask, (size_t)w * h, cudaMemcpyDeviceToHost));
+    return VF_OK;
+}
+
+vf_status vf_op_undistort(const vf_camera* cam, const float* uv, int32_t n, int32_t device, float* out_xy) {
+    if (!cam || n < 0 || (n > 0 && (!uv || !out_xy))) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
+    if (cam->model != VF_CAM_MEI && cam->model != VF_CAM_PINHOLE) return fail(nullptr, VF_ERR_INVALID_ARG, "unsupported camera model");
+    if (n == 0) return VF_OK;
+    GuardHolder gh;
+    vf_status st = op_device(device, &gh.g);
+    if (st != VF_OK) return st;
+    TempPyr tp;   // only used as an allocation holder
+    float2 *d_in = nullptr, *d_out = nullptr;
+    VF_CUDA((vf_batch*)nullptr, cudaMalloc(&d_in, sizeof(float2) * n)); tp.allocs.push_back(d_in);
+    VF_CUDA((vf_batch*)nullptr, cudaMalloc(&d_out, sizeof(float2) * n)); tp.allocs.push_back(d_out);
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy(d_in, uv, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    launch_undistort(to_cam(*cam), d_in, d_out, n, 0);
+    VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
+    VF_CUDA((vf_batch*)nullptr, cudaMemcpy(out_xy, d_out, sizeof(float2) * n, cudaMemcpyDeviceToHost));
+    return VF_OK;
+}
+
+}  // extern "C"

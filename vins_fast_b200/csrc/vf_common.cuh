@@ -1,0 +1,76 @@
+// Shared device/host definitions of the B200-native front-end (sm_100a).
+// Data layout in HBM and the per-stream state are described in DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vins_fast_b200.h"
+
+namespace vf {
+
+constexpr int kMaxLevels = 8;        // pyramid levels 0..7 (BASELINE configs use maxLevel 3..5)
+constexpr int kWin = 21;             // LK window (reference: cv::Size(21,21), feature_tracker.cpp:42)
+constexpr int kWinPx = kWin * kWin;  // 441
+constexpr int kNumSms = 148;         // B200
+
+// One image pyramid resident in HBM: unpadded levels, rows padded to a 128-byte pitch so every row
+// starts on a cache line and 16-byte vector stores are always aligned.
+struct PyrView {
+    uint8_t* lvl[kMaxLevels];
+    int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+    int n_levels;
+};
+
+struct CamParams {   // camodocal liftProjective inputs (CataCamera.cc:320-323 inverse K is derived on device)
+    int model;
+    double xi, k1, k2, p1, p2, fx, fy, cx, cy;
+};
+
+// Sortable key of a float (monotone for all finite values, negative included).
+__host__ __device__ __forceinline__ uint32_t float_key(float v) {
+#if defined(__CUDA_ARCH__)
+    uint32_t b = __float_as_uint(v);
+#else
+    union { float f; uint32_t u; } c; c.f = v; uint32_t b = c.u;
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float key_float(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+
+__host__ __device__ __forceinline__ int refl101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+// Corner-candidate bucketing over the top `bits` bits of the sortable key: 13 bits (sign, 8 exponent bits,
+// 4 mantissa bits -> 16 buckets per octave) up to 1 Mpx, 16 bits (128 per octave) above, so that a bucket
+// normally holds far fewer keys than one selection chunk (1024).
+constexpr int kMaxBucketBits = 16;
+__host__ __device__ __forceinline__ int bucket_of(uint32_t key, int bits) { return (int)(key >> (32 - bits)); }
+
+// Per-stream counters kept on the device (int32 each).
+enum Counter {
+    C_N_PREV = 0,       // features carried in from the previous frame (previous_kps_.size())
+    C_N_TRACKED = 1,    // survivors of the temporal LK + flow-back + InBorder
+    C_N_KEPT = 2,       // survivors of SetFeatureExtractorMask
+    C_N_NEW = 3,        // corners added by goodFeaturesToTrack
+    C_N_TOTAL = 4,      // current_kps_.size()
+    C_N_RIGHT = 5,      // ids_right_.size()
+    C_N_LOCALMAX = 6,   // 3x3 local maxima of the response (threshold- and mask-independent)
+    C_LANDMARK_ID = 7,  // landmark_id_ (unsigned, wraps)
+    C_N_PREV_LEFT_UN = 8,   // size of previous_left_un_distortion_ids_kps_map_
+    C_N_PREV_RIGHT_UN = 9,  // size of previous_right_un_distortion_ids_kps_map_
+    C_MAXKEY = 10,      // masked max of the response, as sortable key (0 = no unmasked pixel)
+    C_N_NZ_BUCKETS = 11,    // non-empty candidate buckets
+    C_COUNT = 16
+};
+
+}  // namespace vf

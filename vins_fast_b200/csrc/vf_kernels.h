@@ -1,0 +1,78 @@
+// Host-callable launchers of the sm_100a kernels (one translation unit per stage).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vf_common.cuh"
+
+namespace vf {
+
+// Device-resident description of a batch of S independent streams (one copy in device memory, one on the host).
+// Per-stream arrays are laid out [S][cap] (or [S][H][W]); "parity" double-buffers what one frame hands to the next.
+struct DevBatch {
+    int n_streams, W, H, cap, min_dist, flow_back, lk_max_level, n_levels;
+    int bucket_bits, n_buckets;      // candidate bucketing resolution (vf_common.cuh: bucket_of)
+    size_t cand_cap;                 // per-stream capacity of cand / cand_sorted (power of two >= W*H)
+    double quality;
+    CamParams cam[2];
+
+    PyrView left[2];                 // left pyramids, slot = frame parity (cur) / parity^1 (prev); stream 0 base
+    PyrView right;                   // right pyramid of the current frame
+    size_t lvl_stream_stride[kMaxLevels];   // bytes between consecutive streams of one level
+
+    float2* kps[2];                  // [parity][S][cap] current_kps_ at the end of the frame
+    int* ids[2];                     // [parity][S][cap] ids_
+    int* cnt[2];                     // [parity][S][cap] track_count_
+    float2* un_left[2];              // [parity][S][cap] current_un_distortion_kps_ (keyed by ids[parity])
+    float2* un_right[2];             // [parity][S][cap] right undistorted point where right_ok
+    uint8_t* right_ok[2];            // [parity][S][cap] 1 = id has a right observation this frame
+    int* counters[2];                // [parity][S][C_COUNT]
+    double* times[2];                // [parity][S]
+
+    // per-frame intermediates (kept for the debug getters)
+    float2* fwd_pts; uint8_t* fwd_st; float2* rev_pts; uint8_t* rev_st; uint8_t* temporal_st;   // [S][cap]
+    float2* lr_pts; uint8_t* lr_st; float2* rl_pts; uint8_t* rl_st;                              // [S][cap]
+    int* sort_perm;                  // [S][cap]
+    int* lk_iters;                   // [S][cap] inner LK iterations spent on the feature this frame
+
+    float* eig;                      // [S][H][W] cornerMinEigenVal of the current left image
+    uint8_t* mask;                   // [S][H][W] SetFeatureExtractorMask
+    unsigned long long* cand;        // [S][cand_cap] local maxima, key = float_key(eig) << 32 | raster index (unordered);
+                                     //               reused as sort scratch by gftt_select once scattered
+    unsigned long long* cand_sorted; // [S][cand_cap] same keys grouped by bucket, strongest bucket first
+    unsigned int* hist;              // [S][n_buckets]
+    unsigned int* bucket_start;      // [S][n_buckets + 1] start of bucket d in cand_sorted, d = n_buckets-1-bucket (descending)
+    unsigned int* bucket_fill;       // [S][n_buckets] scatter cursors (indexed by d)
+    int* bucket_nz;                  // [S][n_buckets] the non-empty d, ascending (counter C_N_NZ_BUCKETS)
+    uint32_t* conflict;              // [S][cap][(cap+31)/32] min_dist conflict bit-matrix of select_tracked when cap > 512
+
+    vf_feature* out;                 // [S][cap] packed result records
+};
+
+// ---- vf_pyramid.cu ----
+void launch_pyrdown(const uint8_t* src, int sw, int sh, int spitch, size_t s_img_stride, uint8_t* dst, int dw, int dh,
+                    int dpitch, size_t d_img_stride, int n_images, cudaStream_t stream);
+void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cudaStream_t stream);
+
+// ---- vf_lk.cu ----
+void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
+                  int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream);
+
+// ---- vf_corners.cu ----
+void launch_response_nms(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_bucket_scan(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_bucket_scatter(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_mask_and_max(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_gftt_select(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_clear_frame(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_masked_max_from_mask(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+void launch_undistort(const CamParams& cam, const float2* uv, float2* out, int n, cudaStream_t stream);
+
+// ---- vf_select.cu ----
+void launch_select_tracked(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+size_t select_tracked_smem_bytes(int cap);
+cudaError_t select_tracked_prepare(int cap);
+
+}  // namespace vf

@@ -1,0 +1,410 @@
+// Iterative pyramidal Lucas-Kanade for sm_100a: forward + reverse (flow_back) temporal tracking and
+// left->right->left stereo tracking, one CTA per feature, one launch per pair of LK calls.
+//
+// Replaces the four cv::calcOpticalFlowPyrLK calls of the reference
+// (vins/estimator/feature_tracker.cpp:41-42, 50-53, 117-119, 125-127) and the status logic around them
+// (:55-67, :128-133), plus RemoveDistortion / ComputeKpsVelocity (:310-363) in the stereo epilogue.
+//
+// Arithmetic = OpenCV's LKTrackerInvoker (modules/video/src/lkpyramid.cpp), restated in oracle/vf_oracle.c:
+//   * 21x21 bilinear patch of I and of its Scharr derivative in W_BITS=14 fixed point (integers);
+//   * A11,A12,A22 and b1,b2 are FLOAT sums accumulated in the exact order OpenCV's 128-bit SIMD loop uses
+//     (4 / 8 interleaved lane accumulators over columns 0..15, a scalar tail over columns 16..20, then the
+//     v_reduce_sum tree), so positions and status flags are bit-identical to the OpenCV CPU path instead of
+//     "within 0.01 px".  The terms of those sums are produced by all 128 threads; one warp then runs the
+//     order-dependent chains (<= 105 dependent FADDs), which is the latency floor of an iteration.
+//   * the Scharr derivative is never materialised in HBM: each level stages a 24x24 uint8 tile of I in shared
+//     memory and derives the 22x22 (Ix,Iy) tile from it (zero outside the image, reflect-101 inside), so the
+//     kernel reads only the uint8 pyramids.
+// All float expressions use explicit round-to-nearest intrinsics (no FMA contraction).
+#include <float.h>
+
+#include "vf_camera.cuh"
+#include "vf_common.cuh"
+#include "vf_kernels.h"
+
+namespace vf {
+
+constexpr int kLkThreads = 128;
+constexpr int kTileI = 24;                   // staged I tile (window + bilinear tap + Scharr ring)
+constexpr int kTileD = 22;                   // derivative tile (window + bilinear tap)
+constexpr int kAStride = 85;                 // 84 terms per SIMD-lane chain of A (+1: bank spread)
+constexpr int kBStride = 42;                 // 42 terms per SIMD-lane chain of b
+constexpr int kTail = 105;                   // 21 rows x 5 tail columns
+constexpr int kTermFloats = 12 * kAStride + 3 * kTail;   // 1335 (b needs 8*42 + 2*105 = 546)
+
+struct LkSmem {
+    uint8_t tileI[kTileI * kTileI];
+    short2 dtile[kTileD * kTileD];
+    short Iw[kWinPx];
+    short2 dI[kWinPx];
+    float terms[kTermFloats];
+    float bcast[4];
+    int found[2];
+};
+
+#define VF_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+
+__device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
+    const float one_a = __fsub_rn(1.f, a), one_b = __fsub_rn(1.f, b);
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(one_a, one_b), 16384.f));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, one_b), 16384.f));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(one_a, b), 16384.f));
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+// Sequential float chain: acc = (((0 + t0) + t1) + ...), the order OpenCV's accumulators see.
+__device__ __forceinline__ float chain_sum(const float* src, int len) {
+    float acc = 0.f;
+#pragma unroll 7
+    for (int s = 0; s < kTail; ++s) {
+        if (s < len) acc = __fadd_rn(acc, src[s]);
+    }
+    return acc;
+}
+
+// One calcOpticalFlowPyrLK for one point, executed cooperatively by the CTA (all threads pass identical
+// arguments and return identical results).
+__device__ void lk_track_point(LkSmem& sm, const PyrView& I, const PyrView& J, float2 prev_pt, float2 init_pt,
+                               bool use_init, int max_level, float2& out_pt, int& out_status, int& iters) {
+    const int tid = threadIdx.x;
+    const float half = 10.f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    int status = 1;
+    float outx = init_pt.x, outy = init_pt.y;
+
+    for (int level = max_level; level >= 0; --level) {
+        const int cols = I.w[level], rows = I.h[level], ipitch = I.pitch[level];
+        const int jcols = J.w[level], jrows = J.h[level], jpitch = J.pitch[level];
+        const uint8_t* __restrict__ Iimg = I.lvl[level];
+        const uint8_t* __restrict__ Jimg = J.lvl[level];
+        const float scale = 1.f / (float)(1 << level);
+        float ppx = __fmul_rn(prev_pt.x, scale), ppy = __fmul_rn(prev_pt.y, scale);
+        float nx, ny;
+        if (level == max_level) {
+            if (use_init) { nx = __fmul_rn(outx, scale); ny = __fmul_rn(outy, scale); }
+            else { nx = ppx; ny = ppy; }
+        } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
+        outx = nx; outy = ny;
+
+        ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
+        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+        if (ipx < -kWin || ipx >= cols || ipy < -kWin || ipy >= rows) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        int w00, w01, w10, w11;
+        bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
+
+        // ---- stage the 24x24 tile of I (origin ip-1), reflect-101 ----
+        __syncthreads();   // previous level / previous pass may still be reading the shared buffers
+        {
+            const bool inside = ipx >= 1 && ipy >= 1 && ipx + kTileI - 1 <= cols && ipy + kTileI - 1 <= rows;
+            for (int i = tid; i < kTileI * kTileI; i += kLkThreads) {
+                const int ty = i / kTileI, tx = i - ty * kTileI;
+                int gx = ipx - 1 + tx, gy = ipy - 1 + ty;
+                if (!inside) { gx = refl101(gx, cols); gy = refl101(gy, rows); }
+                sm.tileI[i] = __ldg(Iimg + (size_t)gy * ipitch + gx);
+            }
+        }
+        __syncthreads();
+        // ---- Scharr (Ix,Iy) on the 22x22 tap positions; zero outside the image ----
+        for (int i = tid; i < kTileD * kTileD; i += kLkThreads) {
+            const int ty = i / kTileD, tx = i - ty * kTileD;
+            const int x = ipx + tx, y = ipy + ty;
+            short2 d = make_short2(0, 0);
+            if (x >= 0 && x < cols && y >= 0 && y < rows) {
+                const uint8_t* p = &sm.tileI[(ty + 1) * kTileI + (tx + 1)];
+                const int a00 = p[-kTileI - 1], a01 = p[-kTileI], a02 = p[-kTileI + 1];
+                const int a10 = p[-1], a12 = p[1];
+                const int a20 = p[kTileI - 1], a21 = p[kTileI], a22 = p[kTileI + 1];
+                const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
+                const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
+                d = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
+            }
+            sm.dtile[i] = d;
+        }
+        __syncthreads();
+        // ---- 21x21 bilinear patch (I in 2^5, derivatives in Scharr units) + terms of A ----
+        for (int i = tid; i < kWinPx; i += kLkThreads) {
+            const int y = i / kWin, x = i - y * kWin;
+            const uint8_t* s = &sm.tileI[(y + 1) * kTileI + (x + 1)];
+            const int ival = VF_DESCALE(s[0] * w00 + s[1] * w01 + s[kTileI] * w10 + s[kTileI + 1] * w11, 9);
+            const short2 d00 = sm.dtile[y * kTileD + x], d01 = sm.dtile[y * kTileD + x + 1];
+            const short2 d10 = sm.dtile[(y + 1) * kTileD + x], d11 = sm.dtile[(y + 1) * kTileD + x + 1];
+            const int ixval = VF_DESCALE(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14);
+            const int iyval = VF_DESCALE(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14);
+            sm.Iw[i] = (short)ival;
+            sm.dI[i] = make_short2((short)ixval, (short)iyval);
+            const float fx = (float)ixval, fy = (float)iyval;   // products are < 2^24: exact in float
+            const float t11 = __fmul_rn(fx, fx), t12 = __fmul_rn(fx, fy), t22 = __fmul_rn(fy, fy);
+            if (x < 16) {
+                const int l = x & 3, slot = y * 4 + (x >> 2);
+                sm.terms[(0 + l) * kAStride + slot] = t11;
+                sm.terms[(4 + l) * kAStride + slot] = t12;
+                sm.terms[(8 + l) * kAStride + slot] = t22;
+            } else {
+                const int slot = y * 5 + (x - 16);
+                sm.terms[12 * kAStride + 0 * kTail + slot] = t11;
+                sm.terms[12 * kAStride + 1 * kTail + slot] = t12;
+                sm.terms[12 * kAStride + 2 * kTail + slot] = t22;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int lane = tid;
+            const float* src = lane < 12 ? &sm.terms[lane * kAStride] : &sm.terms[12 * kAStride + (lane - 12) * kTail];
+            const float acc = chain_sum(src, lane < 12 ? 84 : (lane < 15 ? kTail : 0));
+            float r[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const float q0 = __shfl_sync(0xffffffffu, acc, m * 4 + 0), q1 = __shfl_sync(0xffffffffu, acc, m * 4 + 1);
+                const float q2 = __shfl_sync(0xffffffffu, acc, m * 4 + 2), q3 = __shfl_sync(0xffffffffu, acc, m * 4 + 3);
+                const float tail = __shfl_sync(0xffffffffu, acc, 12 + m);
+                r[m] = __fadd_rn(tail, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+            }
+            if (lane == 0) { sm.bcast[0] = r[0]; sm.bcast[1] = r[1]; sm.bcast[2] = r[2]; }
+        }
+        __syncthreads();
+        const float A11 = __fmul_rn(sm.bcast[0], FLT_SCALE), A12 = __fmul_rn(sm.bcast[1], FLT_SCALE),
+                    A22 = __fmul_rn(sm.bcast[2], FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * kWin * kWin));
+        if (minEig < 1e-4f || D < FLT_EPSILON) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < 30; ++j) {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (inx < -kWin || inx >= jcols || iny < -kWin || iny >= jrows) {
+                if (level == 0) status = 0;
+                break;
+            }
+            ++iters;
+            bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            const bool inside = inx >= 0 && iny >= 0 && inx + kWin < jcols && iny + kWin < jrows;
+            auto jdiff = [&](int y, int x) -> int {
+                int v;
+                if (inside) {
+                    const uint8_t* p = Jimg + (size_t)(iny + y) * jpitch + (inx + x);
+                    v = __ldg(p) * w00 + __ldg(p + 1) * w01 + __ldg(p + jpitch) * w10 + __ldg(p + jpitch + 1) * w11;
+                } else {
+                    const int x0 = refl101(inx + x, jcols), x1 = refl101(inx + x + 1, jcols);
+                    const uint8_t* r0 = Jimg + (size_t)refl101(iny + y, jrows) * jpitch;
+                    const uint8_t* r1 = Jimg + (size_t)refl101(iny + y + 1, jrows) * jpitch;
+                    v = __ldg(r0 + x0) * w00 + __ldg(r0 + x1) * w01 + __ldg(r1 + x0) * w10 + __ldg(r1 + x1) * w11;
+                }
+                return VF_DESCALE(v, 9) - (int)sm.Iw[y * kWin + x];
+            };
+            // terms of b: 168 column pairs (c, c+4) of the 8-wide SIMD groups + 105 tail pixels
+            for (int i = tid; i < 168 + kTail; i += kLkThreads) {
+                if (i < 168) {
+                    const int y = i >> 3, g = (i >> 2) & 1, c = i & 3;
+                    const int xa = 8 * g + c, xb = xa + 4;
+                    const int da = jdiff(y, xa), db = jdiff(y, xb);
+                    const short2 ia = sm.dI[y * kWin + xa], ib = sm.dI[y * kWin + xb];
+                    const int slot = y * 2 + g;
+                    sm.terms[(2 * c + 0) * kBStride + slot] = (float)(da * ia.x + db * ib.x);   // pmaddwd pair, then cvt
+                    sm.terms[(2 * c + 1) * kBStride + slot] = (float)(da * ia.y + db * ib.y);
+                } else {
+                    const int t = i - 168, y = t / 5, x = 16 + (t - y * 5);
+                    const int d = jdiff(y, x);
+                    const short2 id = sm.dI[y * kWin + x];
+                    sm.terms[8 * kBStride + t] = (float)(d * id.x);
+                    sm.terms[8 * kBStride + kTail + t] = (float)(d * id.y);
+                }
+            }
+            __syncthreads();
+            if (tid < 32) {
+                const int lane = tid;
+                const float* src = lane < 8 ? &sm.terms[lane * kBStride] : &sm.terms[8 * kBStride + (lane - 8) * kTail];
+                const float acc = chain_sum(src, lane < 8 ? 42 : (lane < 10 ? kTail : 0));
+                float k[10];
+#pragma unroll
+                for (int q = 0; q < 10; ++q) k[q] = __shfl_sync(0xffffffffu, acc, q);
+                // qb0+qb1 -> (s0,s1,s2,s3); ib1 += (s0+0)+(s2+0); ib2 += (s1+0)+(s3+0)
+                const float s0 = __fadd_rn(k[0], k[4]), s1 = __fadd_rn(k[1], k[5]);
+                const float s2 = __fadd_rn(k[2], k[6]), s3 = __fadd_rn(k[3], k[7]);
+                if (lane == 0) {
+                    sm.bcast[0] = __fadd_rn(k[8], __fadd_rn(s0, s2));
+                    sm.bcast[1] = __fadd_rn(k[9], __fadd_rn(s1, s3));
+                }
+            }
+            __syncthreads();
+            const float b1 = __fmul_rn(sm.bcast[0], FLT_SCALE), b2 = __fmul_rn(sm.bcast[1], FLT_SCALE);
+            const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
+            outx = __fadd_rn(nx, half); outy = __fadd_rn(ny, half);
+            const double dd = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy));
+            if (dd <= 0.01 * 0.01) break;
+            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+                outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0) {   // the caller passes an err vector: final window test (lkpyramid.cpp)
+            const int ix = __float2int_rd(__fsub_rn(outx, half)), iy = __float2int_rd(__fsub_rn(outy, half));
+            if (ix < -kWin || ix >= jcols || iy < -kWin || iy >= jrows) status = 0;
+        }
+    }
+    out_pt = make_float2(outx, outy);
+    out_status = status;
+}
+
+__device__ __forceinline__ bool in_border(float2 p, int rows, int cols) {   // feature_tracker.cpp:20-25
+    const int x = __float2int_rn(p.x), y = __float2int_rn(p.y);
+    return 1 <= x && x < cols - 1 && 1 <= y && y < rows - 1;
+}
+__device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // feature_tracker.cpp:457-462
+    const double dx = (double)__fsub_rn(a.x, b.x), dy = (double)__fsub_rn(a.y, b.y);
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ PyrView stream_view(const PyrView& base, const size_t* stride, int s) {
+    PyrView v = base;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l)
+        if (l < base.n_levels) v.lvl[l] = base.lvl[l] + (size_t)s * stride[l];
+    return v;
+}
+
+// ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
+__global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch* __restrict__ bp, int parity) {
+    __shared__ LkSmem sm;
+    const DevBatch& b = *bp;
+    const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
+    const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
+    if (i >= n_prev) return;
+    const PyrView prev = stream_view(b.left[parity ^ 1], b.lvl_stream_stride, s);
+    const PyrView cur = stream_view(b.left[parity], b.lvl_stream_stride, s);
+    const float2 p0 = b.kps[parity ^ 1][(size_t)s * cap + i];
+    float2 fwd, rev = p0;
+    int st = 0, rst = 0, iters = 0;
+    const int L = min(b.lk_max_level, prev.n_levels - 1);
+    lk_track_point(sm, prev, cur, p0, p0, false, L, fwd, st, iters);
+    int ok = st;
+    if (b.flow_back) {
+        // the reference also runs the reverse pass on points whose forward status is already 0 and then
+        // discards the result (:55-59); the device skips that work, the outcome is the same.
+        if (st) lk_track_point(sm, cur, prev, fwd, p0, true, min(1, L), rev, rst, iters);
+        ok = st && rst && pt_distance(p0, rev) <= 0.5;
+    }
+    if (ok && !in_border(fwd, b.H, b.W)) ok = 0;
+    if (threadIdx.x == 0) {
+        const size_t o = (size_t)s * cap + i;
+        b.fwd_pts[o] = fwd; b.fwd_st[o] = (uint8_t)st;
+        b.rev_pts[o] = rev; b.rev_st[o] = (uint8_t)rst;
+        b.temporal_st[o] = (uint8_t)ok;
+        b.lk_iters[o] = iters;
+    }
+}
+
+// velocity of ComputeKpsVelocity (:323-363): (cur - prev) as float, / dt as double, stored as float.
+__device__ __forceinline__ float2 velocity(float2 cur, float2 prev, double dt) {
+    return make_float2((float)((double)__fsub_rn(cur.x, prev.x) / dt), (float)((double)__fsub_rn(cur.y, prev.y) / dt));
+}
+
+// ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
+//      RemoveDistortion + ComputeKpsVelocity for both cameras and the packed featureFrame record ----
+__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* __restrict__ bp, int parity) {
+    __shared__ LkSmem sm;
+    const DevBatch& b = *bp;
+    const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
+    const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
+    const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
+    if (i >= n) return;
+    const size_t o = (size_t)s * cap + i;
+    const PyrView left = stream_view(b.left[parity], b.lvl_stream_stride, s);
+    const PyrView right = stream_view(b.right, b.lvl_stream_stride, s);
+    const float2 p0 = b.kps[parity][o];
+    const int id = b.ids[parity][o];
+    float2 rp, back = p0;
+    int st = 0, rst = 0, iters = 0;
+    const int L = min(b.lk_max_level, left.n_levels - 1);
+    lk_track_point(sm, left, right, p0, p0, false, L, rp, st, iters);
+    int ok = st;
+    if (b.flow_back) {
+        if (st) lk_track_point(sm, right, left, rp, rp, false, L, back, rst, iters);
+        ok = st && rst && in_border(rp, b.H, b.W) && pt_distance(p0, back) <= 0.5;
+    }
+    // id lookup in the previous frame's maps (previous_left/right_un_distortion_ids_kps_map_)
+    if (tid < 2) sm.found[tid] = -1;
+    __syncthreads();
+    const int n_prev = cnt_prev[C_N_TOTAL];
+    const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
+    for (int j = tid; j < n_prev; j += kLkThreads)
+        if (prev_ids[j] == id) { sm.found[0] = j; if (b.right_ok[parity ^ 1][(size_t)s * cap + j]) sm.found[1] = j; }
+    __syncthreads();
+    if (tid == 0) {
+        const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
+        vf_feature rec;
+        rec.id = id; rec.track_cnt = b.cnt[parity][o]; rec.has_right = ok;
+        const float2 un = undistort_point(b.cam[0], p0);
+        float2 v = make_float2(0.f, 0.f);
+        if (sm.found[0] >= 0) v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + sm.found[0]], dt);
+        rec.x = un.x; rec.y = un.y; rec.u = p0.x; rec.v = p0.y; rec.vx = v.x; rec.vy = v.y;
+        rec.xr = rec.yr = rec.ur = rec.vr = rec.vxr = rec.vyr = 0.f;
+        float2 unr = make_float2(0.f, 0.f);
+        if (ok) {
+            unr = undistort_point(b.cam[1], rp);
+            float2 vr = make_float2(0.f, 0.f);
+            if (sm.found[1] >= 0) vr = velocity(unr, b.un_right[parity ^ 1][(size_t)s * cap + sm.found[1]], dt);
+            rec.xr = unr.x; rec.yr = unr.y; rec.ur = rp.x; rec.vr = rp.y; rec.vxr = vr.x; rec.vyr = vr.y;
+        }
+        b.out[o] = rec;
+        b.un_left[parity][o] = un;
+        b.un_right[parity][o] = unr;
+        b.right_ok[parity][o] = (uint8_t)ok;
+        b.lr_pts[o] = rp; b.lr_st[o] = (uint8_t)st; b.rl_pts[o] = back; b.rl_st[o] = (uint8_t)rst;
+        b.lk_iters[o] += iters;
+        if (ok) atomicAdd(&b.counters[parity][s * C_COUNT + C_N_RIGHT], 1);
+    }
+}
+
+// ---- stand-alone calcOpticalFlowPyrLK (vf_op_lk) ----
+__global__ void __launch_bounds__(kLkThreads) lk_op_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts,
+                                                           float2* __restrict__ next_pts, uint8_t* __restrict__ status,
+                                                           int* __restrict__ iters_out, int n, int max_level, int use_init) {
+    __shared__ LkSmem sm;
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    float2 out;
+    int st = 0, iters = 0;
+    const int L = min(max_level, min(prev.n_levels, next.n_levels) - 1);
+    lk_track_point(sm, prev, next, prev_pts[i], next_pts[i], use_init != 0, L, out, st, iters);
+    if (threadIdx.x == 0) {
+        next_pts[i] = out; status[i] = (uint8_t)st;
+        if (iters_out) iters_out[i] = iters;
+    }
+}
+
+__global__ void undistort_kernel(CamParams cam, const float2* __restrict__ uv, float2* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = undistort_point(cam, uv[i]);
+}
+void launch_undistort(const CamParams& cam, const float2* uv, float2* out, int n, cudaStream_t stream) {
+    if (n <= 0) return;
+    undistort_kernel<<<(n + 127) / 128, 128, 0, stream>>>(cam, uv, out, n);
+}
+
+void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
+    dim3 grid(h.cap, h.n_streams);
+    lk_temporal_kernel<<<grid, kLkThreads, 0, stream>>>(d_batch, parity);
+}
+void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
+    dim3 grid(h.cap, h.n_streams);
+    lk_stereo_kernel<<<grid, kLkThreads, 0, stream>>>(d_batch, parity);
+}
+void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
+                  int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {
+    if (n <= 0) return;
+    lk_op_kernel<<<n, kLkThreads, 0, stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow);
+}
+
+}  // namespace vf
