@@ -125,6 +125,12 @@ const char* vf_batch_last_error(const vf_batch* b);
 void* vf_batch_cuda_stream(const vf_batch* b);        /* cudaStream_t the frame work is ordered on      */
 int32_t vf_batch_launches_per_frame(const vf_batch* b); /* kernels launched by the last frame            */
 vf_tracker* vf_batch_stream(vf_batch* b, int32_t s);  /* borrowed view of stream s (for debug getters)  */
+/* Measurement aid: CUDA events around every kernel / copy of a frame (plain launches instead of the graph replay).
+ * vf_batch_stage_times fills ms_out[vf_batch_stage_count()] with the device times of the last fetched frame. */
+vf_status vf_batch_set_profiling(vf_batch* b, int32_t enable);
+int32_t vf_batch_stage_count(void);
+const char* vf_batch_stage_name(int32_t i);
+vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap);
 
 /* ---- stage-level debug getters (parity tests only; valid after a frame) --------------------------- */
 enum {
@@ -142,7 +148,8 @@ enum {
     VF_DBG_LR_STATUS = 11,   /* uint8 n                                                                  */
     VF_DBG_RL_PTS = 12,      /* float 2*n     right->left LK result                                      */
     VF_DBG_RL_STATUS = 13,   /* uint8 n                                                                  */
-    VF_DBG_COUNTS = 14       /* int32[8]: n_prev, n_tracked, n_kept, n_new, n_total, n_right, n_local_max, landmark_id */
+    VF_DBG_COUNTS = 14,      /* int32[8]: n_prev, n_tracked, n_kept, n_new, n_total, n_right, n_local_max, landmark_id */
+    VF_DBG_LK_ITERS = 15     /* arg 0: int32 n_prev, temporal passes; arg 1: int32 n, stereo passes: inner LK iterations per feature */
 };
 /* Copies the item into `buf` (capacity `cap_bytes`), writes the byte size to *size_out. */
 vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* buf, size_t cap_bytes, size_t* size_out);

@@ -18,7 +18,8 @@ VF_CAM_MEI, VF_CAM_PINHOLE = 0, 1
 STATUS_NAMES = {0: "VF_OK", 1: "VF_ERR_INVALID_ARG", 2: "VF_ERR_CUDA", 3: "VF_ERR_IO", 4: "VF_ERR_PARSE", 5: "VF_ERR_STATE"}
 
 (DBG_PYR_LEFT, DBG_PYR_RIGHT, DBG_EIG, DBG_MASK, DBG_FWD_PTS, DBG_FWD_STATUS, DBG_REV_PTS, DBG_REV_STATUS,
- DBG_TEMPORAL_STATUS, DBG_SORT_PERM, DBG_LR_PTS, DBG_LR_STATUS, DBG_RL_PTS, DBG_RL_STATUS, DBG_COUNTS) = range(15)
+ DBG_TEMPORAL_STATUS, DBG_SORT_PERM, DBG_LR_PTS, DBG_LR_STATUS, DBG_RL_PTS, DBG_RL_STATUS, DBG_COUNTS,
+ DBG_LK_ITERS) = range(16)
 
 
 class VfCamera(C.Structure):
@@ -50,6 +51,7 @@ EXPORTS = [
     "vf_batch_create", "vf_batch_destroy", "vf_batch_reset", "vf_batch_size", "vf_batch_track", "vf_batch_track_device",
     "vf_batch_enqueue_device", "vf_batch_fetch", "vf_batch_last_error", "vf_batch_cuda_stream",
     "vf_batch_launches_per_frame", "vf_batch_stream",
+    "vf_batch_set_profiling", "vf_batch_stage_count", "vf_batch_stage_name", "vf_batch_stage_times",
     "vf_tracker_debug_get",
     "vf_op_build_pyramid", "vf_op_scharr", "vf_op_lk", "vf_op_min_eigen", "vf_op_good_features", "vf_op_set_mask",
     "vf_op_undistort",
@@ -99,6 +101,10 @@ def load() -> C.CDLL:
         "vf_batch_cuda_stream": (P, [P]),
         "vf_batch_launches_per_frame": (I32, [P]),
         "vf_batch_stream": (P, [P, I32]),
+        "vf_batch_set_profiling": (I32, [P, I32]),
+        "vf_batch_stage_count": (I32, []),
+        "vf_batch_stage_name": (C.c_char_p, [I32]),
+        "vf_batch_stage_times": (I32, [P, P, I32]),
         "vf_tracker_debug_get": (I32, [P, I32, I32, P, SZ, P]),
         "vf_op_build_pyramid": (I32, [P, I32, I32, I32, I32, P, P, P, P]),
         "vf_op_scharr": (I32, [P, I32, I32, I32, P]),

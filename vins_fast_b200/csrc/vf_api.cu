@@ -60,10 +60,29 @@ struct vf_batch {
     long frame = 0;
     int last_parity = -1;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
-    int launches = 0;
+    int launches = 0, chain_launches = 0;
     std::string err;
     std::vector<vf_tracker> views;
     size_t bytes_allocated = 0;
+    // optional per-stage timing (vf_batch_set_profiling): CUDA events around every kernel, plain launches only
+    bool profiling = false;
+    cudaEvent_t st_beg[16] = {nullptr}, st_end[16] = {nullptr};
+    bool st_used[16] = {false};
+    float stage_ms[16] = {0};
+};
+
+enum Stage { ST_H2D_LEFT = 0, ST_PYR_LEFT, ST_LK_TEMPORAL, ST_SELECT_TRACKED, ST_RESPONSE_NMS, ST_BUCKET_SCAN, ST_BUCKET_SCATTER,
+             ST_MASK_AND_MAX, ST_GFTT_SELECT, ST_H2D_RIGHT, ST_PYR_RIGHT, ST_LK_STEREO, ST_D2H, ST_CLEAR, ST_COUNT };
+static const char* kStageNames[ST_COUNT] = {"h2d_left", "pyrdown_left", "lk_temporal", "select_tracked", "response_nms", "bucket_scan",
+                                            "bucket_scatter", "mask_and_max", "gftt_select", "h2d_right", "pyrdown_right", "lk_stereo",
+                                            "d2h", "clear_frame"};
+
+struct StageTimer {   // records begin/end events on `st` around a scope when profiling is on
+    vf_batch* b; int id; cudaStream_t st;
+    StageTimer(vf_batch* b_, int id_, cudaStream_t st_) : b(b_), id(id_), st(st_) {
+        if (b->profiling) { cudaEventRecord(b->st_beg[id], st); b->st_used[id] = true; }
+    }
+    ~StageTimer() { if (b->profiling) cudaEventRecord(b->st_end[id], st); }
 };
 
 namespace {
@@ -126,7 +145,7 @@ vf_status alloc_pyramid(vf_batch* b, PyrView& pv, int W, int H, int n_levels, in
     pv.n_levels = n_levels;
     int w = W, h = H;
     for (int l = 0; l < n_levels; ++l) {
-        pv.w[l] = w; pv.h[l] = h; pv.pitch[l] = align_up(w, 128);
+        pv.w[l] = w; pv.h[l] = h; pv.pitch[l] = align_up(w, 16);
         b->h.lvl_stream_stride[l] = (size_t)pv.pitch[l] * h;
         vf_status st = dalloc(b, &pv.lvl[l], (size_t)pv.pitch[l] * h * S);
         if (st != VF_OK) return st;
@@ -180,6 +199,7 @@ void destroy_batch(vf_batch* b) {
     if (b->ev_resp) cudaEventDestroy(b->ev_resp);
     if (b->ev_right) cudaEventDestroy(b->ev_right);
     if (b->ev_img) cudaEventDestroy(b->ev_img);
+    for (int k = 0; k < 16; ++k) { if (b->st_beg[k]) cudaEventDestroy(b->st_beg[k]); if (b->st_end[k]) cudaEventDestroy(b->st_end[k]); }
     if (b->side_a) cudaStreamDestroy(b->side_a);
     if (b->side_b) cudaStreamDestroy(b->side_b);
     if (b->own_main && b->main) cudaStreamDestroy(b->main);
@@ -205,26 +225,25 @@ vf_status reset_state(vf_batch* b) {
 vf_status issue_left_chain(vf_batch* b, int parity) {
     const DevBatch& h = b->h;
     int n = 0;
-    launch_clear_frame(b->d, h, parity, b->main); ++n;
+    { StageTimer t(b, ST_CLEAR, b->main); launch_clear_frame(b->d, h, parity, b->main); ++n; }
     VF_CUDA(b, cudaEventRecord(b->ev_fork, b->main));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_fork, 0));
-    launch_response_nms(b->d, h, parity, b->side_a); ++n;
-    launch_bucket_scan(b->d, h, parity, b->side_a); ++n;
-    launch_bucket_scatter(b->d, h, parity, b->side_a); ++n;
+    { StageTimer t(b, ST_RESPONSE_NMS, b->side_a); launch_response_nms(b->d, h, parity, b->side_a); ++n; }
+    { StageTimer t(b, ST_BUCKET_SCAN, b->side_a); launch_bucket_scan(b->d, h, parity, b->side_a); ++n; }
+    { StageTimer t(b, ST_BUCKET_SCATTER, b->side_a); launch_bucket_scatter(b->d, h, parity, b->side_a); ++n; }
     VF_CUDA(b, cudaEventRecord(b->ev_resp, b->side_a));
     const PyrView& pv = h.left[parity];
-    for (int l = 1; l < pv.n_levels; ++l) {
-        launch_pyrdown(pv.lvl[l - 1], pv.w[l - 1], pv.h[l - 1], pv.pitch[l - 1], h.lvl_stream_stride[l - 1], pv.lvl[l], pv.w[l],
-                       pv.h[l], pv.pitch[l], h.lvl_stream_stride[l], b->S, b->main);
-        ++n;
+    {
+        StageTimer t(b, ST_PYR_LEFT, b->main);
+        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main);
     }
-    launch_lk_temporal(b->d, h, parity, b->main); ++n;
-    launch_select_tracked(b->d, h, parity, b->main); ++n;
+    { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, b->main); ++n; }
+    { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); ++n; }
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_resp, 0));
-    launch_mask_and_max(b->d, h, parity, b->main); ++n;
-    launch_gftt_select(b->d, h, parity, b->main); ++n;
+    { StageTimer t(b, ST_MASK_AND_MAX, b->main); launch_mask_and_max(b->d, h, parity, b->main); ++n; }
+    { StageTimer t(b, ST_GFTT_SELECT, b->main); launch_gftt_select(b->d, h, parity, b->main); ++n; }
     VF_CUDA(b, cudaGetLastError());
-    b->launches = n;
+    b->chain_launches = n;
     return VF_OK;
 }
 
@@ -266,23 +285,37 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     // right image + right pyramid on side B, overlapping the left chain
     VF_CUDA(b, cudaEventRecord(b->ev_img, b->main));            // orders side B after the previous frame's lk_stereo
     VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_img, 0));
-    for (int s = 0; s < S; ++s) {
-        const uint8_t* a = base0 ? base0 + (size_t)s * image_stride : img0[s];
-        const uint8_t* c = base1 ? base1 + (size_t)s * image_stride : img1[s];
-        VF_CUDA(b, cudaMemcpy2DAsync(h.left[parity].lvl[0] + (size_t)s * h.lvl_stream_stride[0], h.left[parity].pitch[0], a,
-                                     stride0, W, H, kind, b->main));
-        VF_CUDA(b, cudaMemcpy2DAsync(h.right.lvl[0] + (size_t)s * h.lvl_stream_stride[0], h.right.pitch[0], c, stride1, W, H,
-                                     kind, b->side_b));
+    for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
+    {
+        StageTimer t(b, ST_H2D_LEFT, b->main);
+        for (int s = 0; s < S; ++s) {
+            const uint8_t* a = base0 ? base0 + (size_t)s * image_stride : img0[s];
+            uint8_t* dst = h.left[parity].lvl[0] + (size_t)s * h.lvl_stream_stride[0];
+            if (stride0 == (size_t)h.left[parity].pitch[0])   // contiguous on both sides: one linear DMA
+                VF_CUDA(b, cudaMemcpyAsync(dst, a, stride0 * (size_t)H, kind, b->main));
+            else
+                VF_CUDA(b, cudaMemcpy2DAsync(dst, h.left[parity].pitch[0], a, stride0, W, H, kind, b->main));
+        }
+    }
+    {
+        StageTimer t(b, ST_H2D_RIGHT, b->side_b);
+        for (int s = 0; s < S; ++s) {
+            const uint8_t* c = base1 ? base1 + (size_t)s * image_stride : img1[s];
+            uint8_t* dst = h.right.lvl[0] + (size_t)s * h.lvl_stream_stride[0];
+            if (stride1 == (size_t)h.right.pitch[0])
+                VF_CUDA(b, cudaMemcpyAsync(dst, c, stride1 * (size_t)H, kind, b->side_b));
+            else
+                VF_CUDA(b, cudaMemcpy2DAsync(dst, h.right.pitch[0], c, stride1, W, H, kind, b->side_b));
+        }
     }
     int n_launch = 0;
-    for (int l = 1; l < h.right.n_levels; ++l) {
-        launch_pyrdown(h.right.lvl[l - 1], h.right.w[l - 1], h.right.h[l - 1], h.right.pitch[l - 1], h.lvl_stream_stride[l - 1],
-                       h.right.lvl[l], h.right.w[l], h.right.h[l], h.right.pitch[l], h.lvl_stream_stride[l], S, b->side_b);
-        ++n_launch;
+    {
+        StageTimer t(b, ST_PYR_RIGHT, b->side_b);
+        n_launch += launch_pyramid(h.right, h.lvl_stream_stride, S, b->side_b);
     }
     VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
     // left chain
-    if (b->cfg.use_cuda_graph) {
+    if (b->cfg.use_cuda_graph && !b->profiling) {
         if (!b->graph[parity]) {
             vf_status st = build_graph(b, parity);
             if (st != VF_OK) return st;
@@ -292,13 +325,16 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         vf_status st = issue_left_chain(b, parity);
         if (st != VF_OK) return st;
     }
-    n_launch += b->launches;
+    n_launch += b->chain_launches;
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
-    launch_lk_stereo(b->d, h, parity, b->main); ++n_launch;
+    { StageTimer t(b, ST_LK_STEREO, b->main); launch_lk_stereo(b->d, h, parity, b->main); ++n_launch; }
     VF_CUDA(b, cudaGetLastError());
-    VF_CUDA(b, cudaMemcpyAsync(b->pin_out[parity], h.out, sizeof(vf_feature) * (size_t)S * h.cap, cudaMemcpyDeviceToHost, b->main));
-    VF_CUDA(b, cudaMemcpyAsync(b->pin_counters[parity], h.counters[parity], sizeof(int) * (size_t)S * C_COUNT,
-                               cudaMemcpyDeviceToHost, b->main));
+    {
+        StageTimer t(b, ST_D2H, b->main);
+        VF_CUDA(b, cudaMemcpyAsync(b->pin_out[parity], h.out, sizeof(vf_feature) * (size_t)S * h.cap, cudaMemcpyDeviceToHost, b->main));
+        VF_CUDA(b, cudaMemcpyAsync(b->pin_counters[parity], h.counters[parity], sizeof(int) * (size_t)S * C_COUNT,
+                                   cudaMemcpyDeviceToHost, b->main));
+    }
     VF_CUDA(b, cudaEventRecord(b->ev_done[parity], b->main));
     b->launches = n_launch;
     b->last_parity = parity;
@@ -311,6 +347,14 @@ vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out) {
     DeviceGuard g(b->device);
     const int p = b->last_parity, S = b->S, cap = b->h.cap;
     VF_CUDA(b, cudaEventSynchronize(b->ev_done[p]));
+    if (b->profiling) {
+        VF_CUDA(b, cudaStreamSynchronize(b->side_a));
+        VF_CUDA(b, cudaStreamSynchronize(b->side_b));
+        for (int k = 0; k < ST_COUNT; ++k) {
+            b->stage_ms[k] = 0.f;
+            if (b->st_used[k]) cudaEventElapsedTime(&b->stage_ms[k], b->st_beg[k], b->st_end[k]);
+        }
+    }
     for (int s = 0; s < S; ++s) {
         const int n = b->pin_counters[p][s * C_COUNT + C_N_TOTAL];
         if (n_out) n_out[s] = n;
@@ -405,7 +449,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     }
     TRY(dalloc(b, &h.fwd_pts, SC)); TRY(dalloc(b, &h.fwd_st, SC)); TRY(dalloc(b, &h.rev_pts, SC)); TRY(dalloc(b, &h.rev_st, SC));
     TRY(dalloc(b, &h.temporal_st, SC)); TRY(dalloc(b, &h.lr_pts, SC)); TRY(dalloc(b, &h.lr_st, SC)); TRY(dalloc(b, &h.rl_pts, SC));
-    TRY(dalloc(b, &h.rl_st, SC)); TRY(dalloc(b, &h.sort_perm, SC)); TRY(dalloc(b, &h.lk_iters, SC));
+    TRY(dalloc(b, &h.rl_st, SC)); TRY(dalloc(b, &h.sort_perm, SC)); TRY(dalloc(b, &h.lk_iters, SC)); TRY(dalloc(b, &h.lk_iters_stereo, SC));
     TRY(dalloc(b, &h.eig, SP)); TRY(dalloc(b, &h.mask, SP));
     TRY(dalloc(b, &h.cand, (size_t)S * h.cand_cap)); TRY(dalloc(b, &h.cand_sorted, (size_t)S * h.cand_cap));
     TRY(dalloc(b, &h.hist, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start, (size_t)S * (h.n_buckets + 1)));
@@ -430,6 +474,25 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
 }
 
 void vf_batch_destroy(vf_batch* b) { destroy_batch(b); }
+
+// Per-stage device times of the last fetched frame (CUDA events on the launching streams).  Profiling mode issues
+// plain launches (no graph replay) so that events can sit between the kernels; it is a measurement aid, off by default.
+vf_status vf_batch_set_profiling(vf_batch* b, int32_t enable) {
+    if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
+    DeviceGuard g(b->device);
+    if (enable && !b->st_beg[0])
+        for (int k = 0; k < ST_COUNT; ++k) { VF_CUDA(b, cudaEventCreate(&b->st_beg[k])); VF_CUDA(b, cudaEventCreate(&b->st_end[k])); }
+    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    b->profiling = enable != 0;
+    return VF_OK;
+}
+int32_t vf_batch_stage_count(void) { return ST_COUNT; }
+const char* vf_batch_stage_name(int32_t i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
+vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap) {
+    if (!b || !ms_out || cap < ST_COUNT) return fail(b, VF_ERR_INVALID_ARG, "bad argument");
+    for (int k = 0; k < ST_COUNT; ++k) ms_out[k] = b->stage_ms[k];
+    return VF_OK;
+}
 vf_status vf_batch_reset(vf_batch* b) { return b ? reset_state(b) : fail(nullptr, VF_ERR_INVALID_ARG, "batch is null"); }
 int32_t vf_batch_size(const vf_batch* b) { return b ? b->S : 0; }
 const char* vf_batch_last_error(const vf_batch* b) { return b ? b->err.c_str() : g_last_error.c_str(); }
@@ -552,6 +615,8 @@ vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* b
         case VF_DBG_LR_STATUS: src = h.lr_st + so; bytes = (size_t)cnt_now[C_N_TOTAL]; break;
         case VF_DBG_RL_PTS: src = h.rl_pts + so; bytes = sizeof(float2) * (size_t)cnt_now[C_N_TOTAL]; break;
         case VF_DBG_RL_STATUS: src = h.rl_st + so; bytes = (size_t)cnt_now[C_N_TOTAL]; break;
+        case VF_DBG_LK_ITERS: src = (arg == 0 ? h.lk_iters : h.lk_iters_stereo) + so;
+            bytes = sizeof(int) * (size_t)cnt_now[arg == 0 ? C_N_PREV : C_N_TOTAL]; break;
         case VF_DBG_COUNTS: {
             int v[8] = {cnt_now[C_N_PREV], cnt_now[C_N_TRACKED], cnt_now[C_N_KEPT], cnt_now[C_N_NEW],
                         cnt_now[C_N_TOTAL], cnt_now[C_N_RIGHT], cnt_now[C_N_LOCALMAX], cnt_now[C_LANDMARK_ID]};
@@ -589,7 +654,7 @@ vf_status temp_pyramid(TempPyr& tp, const uint8_t* img, int w, int h, int max_le
     tp.pv.n_levels = n;
     int lw = w, lh = h;
     for (int l = 0; l < n; ++l) {
-        tp.pv.w[l] = lw; tp.pv.h[l] = lh; tp.pv.pitch[l] = align_up(lw, 128);
+        tp.pv.w[l] = lw; tp.pv.h[l] = lh; tp.pv.pitch[l] = align_up(lw, 16);
         void* p = nullptr;
         VF_CUDA((vf_batch*)nullptr, cudaMalloc(&p, (size_t)tp.pv.pitch[l] * lh));
         tp.allocs.push_back(p);
@@ -597,9 +662,7 @@ vf_status temp_pyramid(TempPyr& tp, const uint8_t* img, int w, int h, int max_le
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy2DAsync(tp.pv.lvl[0], tp.pv.pitch[0], img, w, w, h, cudaMemcpyHostToDevice, st));
-    for (int l = 1; l < n; ++l)
-        launch_pyrdown(tp.pv.lvl[l - 1], tp.pv.w[l - 1], tp.pv.h[l - 1], tp.pv.pitch[l - 1], 0, tp.pv.lvl[l], tp.pv.w[l],
-                       tp.pv.h[l], tp.pv.pitch[l], 0, 1, st);
+    launch_pyramid(tp.pv, nullptr, 1, st);
     VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
     return VF_OK;
 }

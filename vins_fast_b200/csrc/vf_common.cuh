@@ -13,8 +13,8 @@ constexpr int kWin = 21;             // LK window (reference: cv::Size(21,21), f
 constexpr int kWinPx = kWin * kWin;  // 441
 constexpr int kNumSms = 148;         // B200
 
-// One image pyramid resident in HBM: unpadded levels, rows padded to a 128-byte pitch so every row
-// starts on a cache line and 16-byte vector stores are always aligned.
+// One image pyramid resident in HBM: unpadded levels, rows padded to a 16-byte pitch so 16-byte vector
+// loads/stores are always aligned (a 752-wide level 0 has pitch 752: the upload is one linear DMA).
 struct PyrView {
     uint8_t* lvl[kMaxLevels];
     int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];

@@ -33,7 +33,8 @@ struct DevBatch {
     float2* fwd_pts; uint8_t* fwd_st; float2* rev_pts; uint8_t* rev_st; uint8_t* temporal_st;   // [S][cap]
     float2* lr_pts; uint8_t* lr_st; float2* rl_pts; uint8_t* rl_st;                              // [S][cap]
     int* sort_perm;                  // [S][cap]
-    int* lk_iters;                   // [S][cap] inner LK iterations spent on the feature this frame
+    int* lk_iters;                   // [S][cap] inner LK iterations of the temporal passes (indexed like previous_kps_)
+    int* lk_iters_stereo;            // [S][cap] inner LK iterations of the stereo passes (indexed like current_kps_)
 
     float* eig;                      // [S][H][W] cornerMinEigenVal of the current left image
     uint8_t* mask;                   // [S][H][W] SetFeatureExtractorMask
@@ -50,8 +51,7 @@ struct DevBatch {
 };
 
 // ---- vf_pyramid.cu ----
-void launch_pyrdown(const uint8_t* src, int sw, int sh, int spitch, size_t s_img_stride, uint8_t* dst, int dw, int dh,
-                    int dpitch, size_t d_img_stride, int n_images, cudaStream_t stream);
+int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream);
 void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cudaStream_t stream);
 
 // ---- vf_lk.cu ----

@@ -24,20 +24,31 @@
 
 namespace vf {
 
-constexpr int kLkThreads = 128;
+constexpr int kLkThreads = 256;
 constexpr int kTileI = 24;                   // staged I tile (window + bilinear tap + Scharr ring)
 constexpr int kTileD = 22;                   // derivative tile (window + bilinear tap)
-constexpr int kAStride = 85;                 // 84 terms per SIMD-lane chain of A (+1: bank spread)
-constexpr int kBStride = 42;                 // 42 terms per SIMD-lane chain of b
+constexpr int kJMargin = 5;                  // staged J tile = 22x22 taps + this margin on every side
+constexpr int kTileJ = 22 + 2 * kJMargin;    // 32
 constexpr int kTail = 105;                   // 21 rows x 5 tail columns
-constexpr int kTermFloats = 12 * kAStride + 3 * kTail;   // 1335 (b needs 8*42 + 2*105 = 546)
+constexpr int kChain = 108;                  // every summation chain is padded with zeros to 27 float4
+constexpr int kChainsA = 15;                 // 3 x 4 SIMD-lane accumulators (84 terms) + 3 scalar tails (105 terms)
+constexpr int kChainsB = 10;                 // 8 SIMD-lane accumulators (42 terms) + 2 scalar tails (105 terms)
+constexpr int kItemsB = 168 + 53;            // phase-1 work items of one iteration: 168 column pairs + 53 tail pairs
+
+struct LevelRef {
+    const uint8_t* p;
+    int w, h, pitch;
+};
 
 struct LkSmem {
+    alignas(16) float termsA[kChainsA * kChain];
+    alignas(16) float termsB[kChainsB * kChain];
     uint8_t tileI[kTileI * kTileI];
+    uint8_t tileJ[kTileJ * kTileJ];
     short2 dtile[kTileD * kTileD];
-    short Iw[kWinPx];
+    short Iw[kWinPx + 1];
     short2 dI[kWinPx];
-    float terms[kTermFloats];
+    LevelRef pyr[2][kMaxLevels];
     float bcast[4];
     int found[2];
 };
@@ -52,20 +63,42 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
     w11 = 16384 - w00 - w01 - w10;
 }
 
-// Sequential float chain: acc = (((0 + t0) + t1) + ...), the order OpenCV's accumulators see.
-__device__ __forceinline__ float chain_sum(const float* src, int len) {
+// Zero the padding slots of the summation chains once per kernel: the terms never overwrite them, and adding +0.0f
+// to a chain value is an exact identity (a chain of integer-valued floats can never be -0.0f).
+__device__ __forceinline__ void lk_smem_init(LkSmem& sm) {
+    for (int i = threadIdx.x; i < kChainsA * kChain; i += kLkThreads) sm.termsA[i] = 0.f;
+    for (int i = threadIdx.x; i < kChainsB * kChain; i += kLkThreads) sm.termsB[i] = 0.f;
+}
+
+// Sequential float chain acc = (((0 + t0) + t1) + ...) in the order OpenCV's accumulators see the terms: 27 vector
+// loads, 108 dependent FADDs (the latency floor of one LK iteration).
+__device__ __forceinline__ float chain_sum(const float* src) {
+    const float4* p = reinterpret_cast<const float4*>(src);
     float acc = 0.f;
-#pragma unroll 7
-    for (int s = 0; s < kTail; ++s) {
-        if (s < len) acc = __fadd_rn(acc, src[s]);
+#pragma unroll 9
+    for (int i = 0; i < kChain / 4; ++i) {
+        const float4 v = p[i];
+        acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
     }
     return acc;
 }
 
+// Stage a TS x TS tile of `img` with origin (x0, y0), reflect-101 outside the image.
+template <int TS>
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const LevelRef& L, int x0, int y0) {
+    const bool inside = x0 >= 0 && y0 >= 0 && x0 + TS <= L.w && y0 + TS <= L.h;
+    for (int i = threadIdx.x; i < TS * TS; i += kLkThreads) {
+        const int ty = i / TS, tx = i - ty * TS;
+        int gx = x0 + tx, gy = y0 + ty;
+        if (!inside) { gx = refl101(gx, L.w); gy = refl101(gy, L.h); }
+        tile[i] = __ldg(L.p + (size_t)gy * L.pitch + gx);
+    }
+}
+
 // One calcOpticalFlowPyrLK for one point, executed cooperatively by the CTA (all threads pass identical
-// arguments and return identical results).
-__device__ void lk_track_point(LkSmem& sm, const PyrView& I, const PyrView& J, float2 prev_pt, float2 init_pt,
-                               bool use_init, int max_level, float2& out_pt, int& out_status, int& iters) {
+// arguments and return identical results).  ia / ja select the source and target pyramids in sm.pyr.
+__device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init, int max_level,
+                               float2& out_pt, int& out_status, int& iters) {
     const int tid = threadIdx.x;
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (1 << 20);
@@ -73,10 +106,8 @@ __device__ void lk_track_point(LkSmem& sm, const PyrView& I, const PyrView& J, f
     float outx = init_pt.x, outy = init_pt.y;
 
     for (int level = max_level; level >= 0; --level) {
-        const int cols = I.w[level], rows = I.h[level], ipitch = I.pitch[level];
-        const int jcols = J.w[level], jrows = J.h[level], jpitch = J.pitch[level];
-        const uint8_t* __restrict__ Iimg = I.lvl[level];
-        const uint8_t* __restrict__ Jimg = J.lvl[level];
+        const LevelRef LI = sm.pyr[ia][level], LJ = sm.pyr[ja][level];
+        const int cols = LI.w, rows = LI.h, jcols = LJ.w, jrows = LJ.h;
         const float scale = 1.f / (float)(1 << level);
         float ppx = __fmul_rn(prev_pt.x, scale), ppy = __fmul_rn(prev_pt.y, scale);
         float nx, ny;
@@ -95,17 +126,11 @@ __device__ void lk_track_point(LkSmem& sm, const PyrView& I, const PyrView& J, f
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
 
-        // ---- stage the 24x24 tile of I (origin ip-1), reflect-101 ----
+        // ---- stage the 24x24 tile of I (origin ip-1) and a 32x32 tile of J around the start of the search ----
+        int jx0 = __float2int_rd(__fsub_rn(nx, half)) - kJMargin, jy0 = __float2int_rd(__fsub_rn(ny, half)) - kJMargin;
         __syncthreads();   // previous level / previous pass may still be reading the shared buffers
-        {
-            const bool inside = ipx >= 1 && ipy >= 1 && ipx + kTileI - 1 <= cols && ipy + kTileI - 1 <= rows;
-            for (int i = tid; i < kTileI * kTileI; i += kLkThreads) {
-                const int ty = i / kTileI, tx = i - ty * kTileI;
-                int gx = ipx - 1 + tx, gy = ipy - 1 + ty;
-                if (!inside) { gx = refl101(gx, cols); gy = refl101(gy, rows); }
-                sm.tileI[i] = __ldg(Iimg + (size_t)gy * ipitch + gx);
-            }
-        }
+        stage_tile<kTileI>(sm.tileI, LI, ipx - 1, ipy - 1);
+        stage_tile<kTileJ>(sm.tileJ, LJ, jx0, jy0);
         __syncthreads();
         // ---- Scharr (Ix,Iy) on the 22x22 tap positions; zero outside the image ----
         for (int i = tid; i < kTileD * kTileD; i += kLkThreads) {
@@ -137,30 +162,29 @@ __device__ void lk_track_point(LkSmem& sm, const PyrView& I, const PyrView& J, f
             sm.dI[i] = make_short2((short)ixval, (short)iyval);
             const float fx = (float)ixval, fy = (float)iyval;   // products are < 2^24: exact in float
             const float t11 = __fmul_rn(fx, fx), t12 = __fmul_rn(fx, fy), t22 = __fmul_rn(fy, fy);
-            if (x < 16) {
+            if (x < 16) {   // SIMD lane l = x & 3 sees columns l, 4+l, 8+l, 12+l of every row in turn
                 const int l = x & 3, slot = y * 4 + (x >> 2);
-                sm.terms[(0 + l) * kAStride + slot] = t11;
-                sm.terms[(4 + l) * kAStride + slot] = t12;
-                sm.terms[(8 + l) * kAStride + slot] = t22;
-            } else {
+                sm.termsA[(0 + l) * kChain + slot] = t11;
+                sm.termsA[(4 + l) * kChain + slot] = t12;
+                sm.termsA[(8 + l) * kChain + slot] = t22;
+            } else {        // scalar tail: columns 16..20 of every row in turn
                 const int slot = y * 5 + (x - 16);
-                sm.terms[12 * kAStride + 0 * kTail + slot] = t11;
-                sm.terms[12 * kAStride + 1 * kTail + slot] = t12;
-                sm.terms[12 * kAStride + 2 * kTail + slot] = t22;
+                sm.termsA[12 * kChain + slot] = t11;
+                sm.termsA[13 * kChain + slot] = t12;
+                sm.termsA[14 * kChain + slot] = t22;
             }
         }
         __syncthreads();
         if (tid < 32) {
             const int lane = tid;
-            const float* src = lane < 12 ? &sm.terms[lane * kAStride] : &sm.terms[12 * kAStride + (lane - 12) * kTail];
-            const float acc = chain_sum(src, lane < 12 ? 84 : (lane < 15 ? kTail : 0));
+            const float acc = chain_sum(&sm.termsA[min(lane, kChainsA - 1) * kChain]);
             float r[3];
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
                 const float q0 = __shfl_sync(0xffffffffu, acc, m * 4 + 0), q1 = __shfl_sync(0xffffffffu, acc, m * 4 + 1);
                 const float q2 = __shfl_sync(0xffffffffu, acc, m * 4 + 2), q3 = __shfl_sync(0xffffffffu, acc, m * 4 + 3);
                 const float tail = __shfl_sync(0xffffffffu, acc, 12 + m);
-                r[m] = __fadd_rn(tail, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+                r[m] = __fadd_rn(tail, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));   // iA += v_reduce_sum(qA)
             }
             if (lane == 0) { sm.bcast[0] = r[0]; sm.bcast[1] = r[1]; sm.bcast[2] = r[2]; }
         }
@@ -185,44 +209,47 @@ __device__ void lk_track_point(LkSmem& sm, const PyrView& I, const PyrView& J, f
                 break;
             }
             ++iters;
+            if (inx < jx0 || iny < jy0 || inx + kTileD > jx0 + kTileJ || iny + kTileD > jy0 + kTileJ) {
+                // the window left the staged tile: re-centre it (uniform branch)
+                jx0 = inx - kJMargin; jy0 = iny - kJMargin;
+                __syncthreads();
+                stage_tile<kTileJ>(sm.tileJ, LJ, jx0, jy0);
+                __syncthreads();
+            }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            const bool inside = inx >= 0 && iny >= 0 && inx + kWin < jcols && iny + kWin < jrows;
+            const uint8_t* jt = &sm.tileJ[(iny - jy0) * kTileJ + (inx - jx0)];
             auto jdiff = [&](int y, int x) -> int {
-                int v;
-                if (inside) {
-                    const uint8_t* p = Jimg + (size_t)(iny + y) * jpitch + (inx + x);
-                    v = __ldg(p) * w00 + __ldg(p + 1) * w01 + __ldg(p + jpitch) * w10 + __ldg(p + jpitch + 1) * w11;
-                } else {
-                    const int x0 = refl101(inx + x, jcols), x1 = refl101(inx + x + 1, jcols);
-                    const uint8_t* r0 = Jimg + (size_t)refl101(iny + y, jrows) * jpitch;
-                    const uint8_t* r1 = Jimg + (size_t)refl101(iny + y + 1, jrows) * jpitch;
-                    v = __ldg(r0 + x0) * w00 + __ldg(r0 + x1) * w01 + __ldg(r1 + x0) * w10 + __ldg(r1 + x1) * w11;
-                }
+                const uint8_t* p = jt + y * kTileJ + x;
+                const int v = p[0] * w00 + p[1] * w01 + p[kTileJ] * w10 + p[kTileJ + 1] * w11;
                 return VF_DESCALE(v, 9) - (int)sm.Iw[y * kWin + x];
             };
-            // terms of b: 168 column pairs (c, c+4) of the 8-wide SIMD groups + 105 tail pixels
-            for (int i = tid; i < 168 + kTail; i += kLkThreads) {
-                if (i < 168) {
-                    const int y = i >> 3, g = (i >> 2) & 1, c = i & 3;
-                    const int xa = 8 * g + c, xb = xa + 4;
-                    const int da = jdiff(y, xa), db = jdiff(y, xb);
-                    const short2 ia = sm.dI[y * kWin + xa], ib = sm.dI[y * kWin + xb];
-                    const int slot = y * 2 + g;
-                    sm.terms[(2 * c + 0) * kBStride + slot] = (float)(da * ia.x + db * ib.x);   // pmaddwd pair, then cvt
-                    sm.terms[(2 * c + 1) * kBStride + slot] = (float)(da * ia.y + db * ib.y);
-                } else {
-                    const int t = i - 168, y = t / 5, x = 16 + (t - y * 5);
-                    const int d = jdiff(y, x);
-                    const short2 id = sm.dI[y * kWin + x];
-                    sm.terms[8 * kBStride + t] = (float)(d * id.x);
-                    sm.terms[8 * kBStride + kTail + t] = (float)(d * id.y);
+            // terms of b, one work item per thread: 168 column pairs (c, c+4) of the two 8-wide SIMD groups of every
+            // row (pmaddwd pair sums), then 53 pairs of tail pixels (columns 16..20)
+            if (tid < 168) {
+                const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3;
+                const int xa = 8 * g + c, xb = xa + 4;
+                const int da = jdiff(y, xa), db = jdiff(y, xb);
+                const short2 pa = sm.dI[y * kWin + xa], pb = sm.dI[y * kWin + xb];
+                const int slot = y * 2 + g;
+                sm.termsB[(2 * c + 0) * kChain + slot] = (float)(da * pa.x + db * pb.x);   // exact int32 pair sum, then cvt
+                sm.termsB[(2 * c + 1) * kChain + slot] = (float)(da * pa.y + db * pb.y);
+            } else if (tid < kItemsB) {
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int t = 2 * (tid - 168) + h2;
+                    if (t < kTail) {
+                        const int y = t / 5, x = 16 + (t - y * 5);
+                        const int d = jdiff(y, x);
+                        const short2 pd = sm.dI[y * kWin + x];
+                        sm.termsB[8 * kChain + t] = (float)(d * pd.x);
+                        sm.termsB[9 * kChain + t] = (float)(d * pd.y);
+                    }
                 }
             }
             __syncthreads();
             if (tid < 32) {
                 const int lane = tid;
-                const float* src = lane < 8 ? &sm.terms[lane * kBStride] : &sm.terms[8 * kBStride + (lane - 8) * kTail];
-                const float acc = chain_sum(src, lane < 8 ? 42 : (lane < 10 ? kTail : 0));
+                const float acc = chain_sum(&sm.termsB[min(lane, kChainsB - 1) * kChain]);
                 float k[10];
 #pragma unroll
                 for (int q = 0; q < 10; ++q) k[q] = __shfl_sync(0xffffffffu, acc, q);
@@ -257,6 +284,18 @@ __device__ void lk_track_point(LkSmem& sm, const PyrView& I, const PyrView& J, f
     out_status = status;
 }
 
+// Fill sm.pyr[slot] with stream s of a pyramid (threads 0..kMaxLevels-1 of the given quarter).
+__device__ __forceinline__ void load_pyr(LkSmem& sm, int slot, const PyrView& pv, const size_t* stride, int s) {
+    const int l = threadIdx.x - slot * kMaxLevels;
+    if (l >= 0 && l < kMaxLevels) {
+        LevelRef r;
+        const bool ok = l < pv.n_levels;
+        r.p = ok ? pv.lvl[l] + (stride ? (size_t)s * stride[l] : 0) : nullptr;
+        r.w = ok ? pv.w[l] : 0; r.h = ok ? pv.h[l] : 0; r.pitch = ok ? pv.pitch[l] : 0;
+        sm.pyr[slot][l] = r;
+    }
+}
+
 __device__ __forceinline__ bool in_border(float2 p, int rows, int cols) {   // feature_tracker.cpp:20-25
     const int x = __float2int_rn(p.x), y = __float2int_rn(p.y);
     return 1 <= x && x < cols - 1 && 1 <= y && y < rows - 1;
@@ -266,14 +305,6 @@ __device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // f
     return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
-__device__ __forceinline__ PyrView stream_view(const PyrView& base, const size_t* stride, int s) {
-    PyrView v = base;
-#pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l)
-        if (l < base.n_levels) v.lvl[l] = base.lvl[l] + (size_t)s * stride[l];
-    return v;
-}
-
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
 __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch* __restrict__ bp, int parity) {
     __shared__ LkSmem sm;
@@ -281,18 +312,20 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch*
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
     if (i >= n_prev) return;
-    const PyrView prev = stream_view(b.left[parity ^ 1], b.lvl_stream_stride, s);
-    const PyrView cur = stream_view(b.left[parity], b.lvl_stream_stride, s);
+    lk_smem_init(sm);
+    load_pyr(sm, 0, b.left[parity ^ 1], b.lvl_stream_stride, s);   // 0 = previous left
+    load_pyr(sm, 1, b.left[parity], b.lvl_stream_stride, s);       // 1 = current left
+    __syncthreads();
     const float2 p0 = b.kps[parity ^ 1][(size_t)s * cap + i];
     float2 fwd, rev = p0;
     int st = 0, rst = 0, iters = 0;
-    const int L = min(b.lk_max_level, prev.n_levels - 1);
-    lk_track_point(sm, prev, cur, p0, p0, false, L, fwd, st, iters);
+    const int L = min(b.lk_max_level, b.left[parity].n_levels - 1);
+    lk_track_point(sm, 0, 1, p0, p0, false, L, fwd, st, iters);
     int ok = st;
     if (b.flow_back) {
         // the reference also runs the reverse pass on points whose forward status is already 0 and then
         // discards the result (:55-59); the device skips that work, the outcome is the same.
-        if (st) lk_track_point(sm, cur, prev, fwd, p0, true, min(1, L), rev, rst, iters);
+        if (st) lk_track_point(sm, 1, 0, fwd, p0, true, min(1, L), rev, rst, iters);
         ok = st && rst && pt_distance(p0, rev) <= 0.5;
     }
     if (ok && !in_border(fwd, b.H, b.W)) ok = 0;
@@ -320,17 +353,19 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
     if (i >= n) return;
     const size_t o = (size_t)s * cap + i;
-    const PyrView left = stream_view(b.left[parity], b.lvl_stream_stride, s);
-    const PyrView right = stream_view(b.right, b.lvl_stream_stride, s);
+    lk_smem_init(sm);
+    load_pyr(sm, 0, b.left[parity], b.lvl_stream_stride, s);   // 0 = current left
+    load_pyr(sm, 1, b.right, b.lvl_stream_stride, s);          // 1 = current right
+    __syncthreads();
     const float2 p0 = b.kps[parity][o];
     const int id = b.ids[parity][o];
     float2 rp, back = p0;
     int st = 0, rst = 0, iters = 0;
-    const int L = min(b.lk_max_level, left.n_levels - 1);
-    lk_track_point(sm, left, right, p0, p0, false, L, rp, st, iters);
+    const int L = min(b.lk_max_level, b.right.n_levels - 1);
+    lk_track_point(sm, 0, 1, p0, p0, false, L, rp, st, iters);
     int ok = st;
     if (b.flow_back) {
-        if (st) lk_track_point(sm, right, left, rp, rp, false, L, back, rst, iters);
+        if (st) lk_track_point(sm, 1, 0, rp, rp, false, L, back, rst, iters);
         ok = st && rst && in_border(rp, b.H, b.W) && pt_distance(p0, back) <= 0.5;
     }
     // id lookup in the previous frame's maps (previous_left/right_un_distortion_ids_kps_map_)
@@ -362,7 +397,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
         b.un_right[parity][o] = unr;
         b.right_ok[parity][o] = (uint8_t)ok;
         b.lr_pts[o] = rp; b.lr_st[o] = (uint8_t)st; b.rl_pts[o] = back; b.rl_st[o] = (uint8_t)rst;
-        b.lk_iters[o] += iters;
+        b.lk_iters_stereo[o] = iters;
         if (ok) atomicAdd(&b.counters[parity][s * C_COUNT + C_N_RIGHT], 1);
     }
 }
@@ -374,10 +409,14 @@ __global__ void __launch_bounds__(kLkThreads) lk_op_kernel(PyrView prev, PyrView
     __shared__ LkSmem sm;
     const int i = blockIdx.x;
     if (i >= n) return;
+    lk_smem_init(sm);
+    load_pyr(sm, 0, prev, nullptr, 0);
+    load_pyr(sm, 1, next, nullptr, 0);
+    __syncthreads();
     float2 out;
     int st = 0, iters = 0;
     const int L = min(max_level, min(prev.n_levels, next.n_levels) - 1);
-    lk_track_point(sm, prev, next, prev_pts[i], next_pts[i], use_init != 0, L, out, st, iters);
+    lk_track_point(sm, 0, 1, prev_pts[i], next_pts[i], use_init != 0, L, out, st, iters);
     if (threadIdx.x == 0) {
         next_pts[i] = out; status[i] = (uint8_t)st;
         if (iters_out) iters_out[i] = iters;

@@ -1,101 +1,150 @@
 // uint8 Gaussian pyramid (pyrDown) and Scharr derivative planes for sm_100a.
 //
-// pyrdown_u8: what cv::buildOpticalFlowPyramid / cv::pyrDown compute for the reference's four
-// calcOpticalFlowPyrLK calls (vins/estimator/feature_tracker.cpp:41,50,117,125):
+// What cv::buildOpticalFlowPyramid / cv::pyrDown compute for the reference's four calcOpticalFlowPyrLK calls
+// (vins/estimator/feature_tracker.cpp:41,50,117,125):
 //   dst(x,y) = ( sum_{i,j in [-2,2]} k[i]k[j] src(refl101(2x+j), refl101(2y+i)) + 128 ) >> 8,  k = [1 4 6 4 1]
-// Integer, bit-exact.  HBM-bound streaming stencil: one CTA stages a (2*TH+3) x (2*TW+4) input tile in
-// shared memory (16-byte loads in the interior, reflect-101 indexing on the frame edge), runs the
-// horizontal 5-tap into a uint16 tile, then each thread runs the vertical 5-tap for PX consecutive
-// outputs and writes them with one PX-byte vector store (PX = 16 -> 16-byte HBM stores).
+// Integer, bit-exact.
 #include "vf_common.cuh"
 #include "vf_kernels.h"
 
 namespace vf {
 
-template <int TW, int TH, int PX>
-__global__ void __launch_bounds__((TW / PX) * TH)
-pyrdown_u8_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, size_t s_img_stride,
-                  uint8_t* __restrict__ dst, int dw, int dh, int dpitch, size_t d_img_stride) {
-    constexpr int IW = 2 * TW + 4;          // input tile width  (cols 2*x0-2 .. 2*x0+2*TW+1)
-    constexpr int IH = 2 * TH + 3;          // input tile height (rows 2*y0-2 .. 2*y0+2*TH)
-    constexpr int IWP = (IW + 15) / 16 * 16 + 16;   // smem pitch, allows 16-byte aligned vector fill
-    constexpr int NT = (TW / PX) * TH;
-    __shared__ __align__(16) uint8_t tile[IH][IWP];
-    __shared__ __align__(16) uint16_t hs[IH][TW];
+// ------------------------------------------------------------------------------------------------------
+// Fused multi-level pyramid: ONE launch builds NL consecutive levels.  A CTA owns a TW x TH tile of the last
+// level and recomputes the halo it needs of every level in between from a single staged tile of the input
+// level (85 x 85 pixels for NL = 3, TW = TH = 8), so levels 1..NL never travel through HBM between stages and
+// the dependent launch chain of the frame shrinks from NL launches to one.  Each level is still written out
+// (by the CTA that owns the pixels) because LK reads every level.
+// Regions are kept in in-image coordinates and consumers reflect their tap index (REFLECT_101) into the
+// region, which is exactly cv::pyrDown's border rule on every intermediate level.
+// ------------------------------------------------------------------------------------------------------
+struct FusedPyrArgs {
+    const uint8_t* src; int sw, sh, spitch; size_t s_stride;          // input level
+    uint8_t* dst[3]; int dw[3], dh[3], dpitch[3]; size_t d_stride[3];  // NL output levels
+};
 
-    const int img = blockIdx.z;
-    src += (size_t)img * s_img_stride;
-    dst += (size_t)img * d_img_stride;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const int tid = threadIdx.x;
-    const int ix0 = 2 * x0 - 2, iy0 = 2 * y0 - 2;
+template <int NL, int TW, int TH>
+__global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
+    constexpr int NT = 256;
+    // maximal region extents per relative level k (k = 0 input ... NL top)
+    constexpr int RW3 = TW, RH3 = TH;
+    constexpr int RW2 = 2 * RW3 + 3, RH2 = 2 * RH3 + 3;
+    constexpr int RW1 = NL >= 2 ? 2 * RW2 + 3 : RW2, RH1 = NL >= 2 ? 2 * RH2 + 3 : RH2;
+    constexpr int RW0 = NL >= 3 ? 2 * RW1 + 3 : RW1, RH0 = NL >= 3 ? 2 * RH1 + 3 : RH1;
+    constexpr int P0 = (RW0 + 15 + 15) / 16 * 16;                      // input tile pitch (16-byte aligned chunks)
+    constexpr int PW = NL >= 3 ? RW1 : (NL >= 2 ? RW2 : RW3);          // widest level-1 region
+    constexpr int PI = (PW + 3) / 4 * 4;                               // pitch of intermediate regions
+    __shared__ __align__(16) uint8_t buf0[RH0 * P0];
+    __shared__ __align__(16) uint8_t bufA[(NL >= 3 ? RH1 : (NL >= 2 ? RH2 : RH3)) * PI];
+    __shared__ __align__(16) uint8_t bufB[(NL >= 3 ? RH2 : RH3) * PI];
+    __shared__ uint16_t tmp[RH0 * PW];
 
-    // ---- stage the input tile.  tile[r][c + SH] = src(iy0 + r, ix0 + c); SH aligns 16-byte chunks ----
-    // ix0 = 2*x0-2 with x0 a multiple of TW (>= 64): (ix0 + 2) is 16-byte aligned, so shift by 2... we
-    // instead align on the global side: chunk k covers global columns [gx, gx+16), gx = (ix0 & ~15) + 16k.
-    const int gbase = ix0 & ~15;            // floor to 16 (works for negative ix0 too: two's complement)
-    const int shift = ix0 - gbase;          // 0..15, tile column of ix0 inside the chunked row
-    constexpr int CHUNKS = IWP / 16;
-    for (int i = tid; i < IH * CHUNKS; i += NT) {
-        const int r = i / CHUNKS, k = i - r * CHUNKS;
-        const int gy = refl101(iy0 + r, sh);
-        const int gx = gbase + 16 * k;
-        const uint8_t* row = src + (size_t)gy * spitch;
-        uint4 v;
-        if (gx >= 0 && gx + 16 <= sw) {
-            v = *reinterpret_cast<const uint4*>(row + gx);    // pitch and gx are multiples of 16
-        } else {
-            uint8_t b[16];
+    const int tid = threadIdx.x, img = blockIdx.z;
+    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
+    int lox[NL + 1], hix[NL + 1], loy[NL + 1], hiy[NL + 1], lw[NL + 1], lh[NL + 1];
+    lw[0] = a.sw; lh[0] = a.sh;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) b[j] = row[refl101(gx + j, sw)];
-            v = *reinterpret_cast<uint4*>(b);
+    for (int k = 1; k <= NL; ++k) { lw[k] = a.dw[k - 1]; lh[k] = a.dh[k - 1]; }
+    lox[NL] = tx0; hix[NL] = min(tx0 + TW, lw[NL]) - 1;
+    loy[NL] = ty0; hiy[NL] = min(ty0 + TH, lh[NL]) - 1;
+#pragma unroll
+    for (int k = NL - 1; k >= 0; --k) {
+        lox[k] = max(0, 2 * lox[k + 1] - 2); hix[k] = min(lw[k] - 1, 2 * hix[k + 1] + 2);
+        loy[k] = max(0, 2 * loy[k + 1] - 2); hiy[k] = min(lh[k] - 1, 2 * hiy[k + 1] + 2);
+    }
+    // ---- stage the input region with aligned 16-byte loads (row pitch and base are multiples of 16) ----
+    const uint8_t* src = a.src + (size_t)img * a.s_stride;
+    const int ax0 = lox[0] & ~15;
+    const int nchunk = (hix[0] - ax0) / 16 + 1, nrow0 = hiy[0] - loy[0] + 1;
+    for (int i = tid; i < nrow0 * nchunk; i += NT) {
+        const int r = i / nchunk, c = i - r * nchunk;
+        *reinterpret_cast<uint4*>(&buf0[r * P0 + 16 * c]) =
+            *reinterpret_cast<const uint4*>(src + (size_t)(loy[0] + r) * a.spitch + ax0 + 16 * c);
+    }
+    __syncthreads();
+
+    const uint8_t* in = buf0;
+    int in_pitch = P0, in_ox = ax0;
+#pragma unroll
+    for (int k = 0; k < NL; ++k) {
+        uint8_t* out = (k & 1) ? bufB : bufA;
+        const int ow = hix[k + 1] - lox[k + 1] + 1, oh = hiy[k + 1] - loy[k + 1] + 1;
+        const int ih = hiy[k] - loy[k] + 1;
+        // horizontal [1 4 6 4 1] at even columns of every staged input row
+        for (int i = tid; i < ih * ow; i += NT) {
+            const int r = i / ow, c = i - r * ow;
+            const int gx = 2 * (lox[k + 1] + c);
+            const uint8_t* row = in + r * in_pitch - in_ox;
+            const int v = row[refl101(gx - 2, lw[k])] + 4 * row[refl101(gx - 1, lw[k])] + 6 * row[gx] +
+                          4 * row[refl101(gx + 1, lw[k])] + row[refl101(gx + 2, lw[k])];
+            tmp[r * PW + c] = (uint16_t)v;
         }
-        *reinterpret_cast<uint4*>(&tile[r][16 * k]) = v;
-    }
-    __syncthreads();
-
-    // ---- horizontal [1 4 6 4 1] at even columns ----
-    for (int i = tid; i < IH * TW; i += NT) {
-        const int r = i / TW, x = i - r * TW;
-        const uint8_t* p = &tile[r][shift + 2 * x];
-        hs[r][x] = (uint16_t)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
-    }
-    __syncthreads();
-
-    // ---- vertical pass, PX outputs per thread, one vector store ----
-    const int ty = tid / (TW / PX), tx = (tid - ty * (TW / PX)) * PX;
-    const int oy = y0 + ty, ox = x0 + tx;
-    if (oy >= dh || ox >= dw) return;
-    uint8_t o[PX];
+        __syncthreads();
+        // vertical pass -> region of level k+1 (kept in shared memory for the next transition)
+        for (int i = tid; i < oh * ow; i += NT) {
+            const int r = i / ow, c = i - r * ow;
+            const int gy = 2 * (loy[k + 1] + r);
+            const int r0 = refl101(gy - 2, lh[k]) - loy[k], r1 = refl101(gy - 1, lh[k]) - loy[k], r2 = gy - loy[k];
+            const int r3 = refl101(gy + 1, lh[k]) - loy[k], r4 = refl101(gy + 2, lh[k]) - loy[k];
+            const int v = tmp[r0 * PW + c] + 4 * tmp[r1 * PW + c] + 6 * tmp[r2 * PW + c] + 4 * tmp[r3 * PW + c] + tmp[r4 * PW + c];
+            out[r * PI + c] = (uint8_t)((v + 128) >> 8);
+        }
+        __syncthreads();
+        // write the part of level k+1 this CTA owns: tile scaled by 2^(NL-1-k), 8 pixels per store
+        {
+            const int sh_ = NL - 1 - k;
+            const int ox0 = tx0 << sh_, oy0 = ty0 << sh_;
+            const int ox1 = min((tx0 + TW) << sh_, lw[k + 1]), oy1 = min((ty0 + TH) << sh_, lh[k + 1]);
+            const int n8 = (ox1 - ox0 + 7) / 8, nr = oy1 - oy0;
+            uint8_t* dst = a.dst[k] + (size_t)img * a.d_stride[k];
+            for (int i = tid; i < nr * n8; i += NT) {
+                const int r = i / n8, c8 = i - r * n8;
+                const int gx = ox0 + 8 * c8, gy = oy0 + r;
+                const uint8_t* p = out + (gy - loy[k + 1]) * PI + (gx - lox[k + 1]);
+                uint32_t lo = 0, hi = 0;
 #pragma unroll
-    for (int j = 0; j < PX; ++j) {
-        const int r = 2 * ty;
-        int v = hs[r][tx + j] + 4 * hs[r + 1][tx + j] + 6 * hs[r + 2][tx + j] + 4 * hs[r + 3][tx + j] + hs[r + 4][tx + j];
-        o[j] = (uint8_t)((v + 128) >> 8);
-    }
-    uint8_t* out = dst + (size_t)oy * dpitch + ox;
-    if (ox + PX <= dpitch) {               // rows are padded to a 128-byte pitch: the vector store always fits
-        if (PX == 16) *reinterpret_cast<uint4*>(out) = *reinterpret_cast<uint4*>(o);
-        else if (PX == 8) *reinterpret_cast<uint2*>(out) = *reinterpret_cast<uint2*>(o);
-        else { for (int j = 0; j < PX; ++j) out[j] = o[j]; }
-    } else {
-        for (int j = 0; j < PX && ox + j < dw; ++j) out[j] = o[j];
+                for (int j = 0; j < 4; ++j) {
+                    if (gx + j < ox1) lo |= (uint32_t)p[j] << (8 * j);
+                    if (gx + 4 + j < ox1) hi |= (uint32_t)p[4 + j] << (8 * j);
+                }
+                *reinterpret_cast<uint2*>(dst + (size_t)gy * a.dpitch[k] + gx) = make_uint2(lo, hi);   // pitch is a multiple of 16
+            }
+        }
+        in = out; in_pitch = PI; in_ox = lox[k + 1];
+        // the next transition overwrites tmp and the other ping-pong buffer only after every thread passed the barriers above
     }
 }
 
-void launch_pyrdown(const uint8_t* src, int sw, int sh, int spitch, size_t s_img_stride, uint8_t* dst, int dw, int dh,
-                    int dpitch, size_t d_img_stride, int n_images, cudaStream_t stream) {
-    if (dw >= 1024) {
-        constexpr int TW = 256, TH = 16, PX = 16;
-        dim3 grid((dw + TW - 1) / TW, (dh + TH - 1) / TH, n_images);
-        pyrdown_u8_kernel<TW, TH, PX><<<grid, (TW / PX) * TH, 0, stream>>>(src, sw, sh, spitch, s_img_stride, dst, dw, dh,
-                                                                         dpitch, d_img_stride);
-    } else {
-        constexpr int TW = 128, TH = 8, PX = 16;   // 64 threads: more CTAs for the small EuRoC levels
-        dim3 grid((dw + TW - 1) / TW, (dh + TH - 1) / TH, n_images);
-        pyrdown_u8_kernel<TW, TH, PX><<<grid, (TW / PX) * TH, 0, stream>>>(src, sw, sh, spitch, s_img_stride, dst, dw, dh,
-                                                                         dpitch, d_img_stride);
+// Builds levels first+1 .. first+count of a pyramid (count <= 3) in one launch.
+static void launch_pyr_fused(const PyrView& pv, const size_t* stride, int first, int count, int n_images, cudaStream_t stream) {
+    FusedPyrArgs a;
+    a.src = pv.lvl[first]; a.sw = pv.w[first]; a.sh = pv.h[first]; a.spitch = pv.pitch[first]; a.s_stride = stride ? stride[first] : 0;
+    for (int k = 0; k < 3; ++k) {
+        const int l = first + 1 + (k < count ? k : count - 1);
+        a.dst[k] = pv.lvl[l]; a.dw[k] = pv.w[l]; a.dh[k] = pv.h[l]; a.dpitch[k] = pv.pitch[l]; a.d_stride[k] = stride ? stride[l] : 0;
     }
+    const int tw = pv.w[first + count], th = pv.h[first + count];
+    if (count == 3) {
+        dim3 grid((tw + 7) / 8, (th + 7) / 8, n_images);
+        pyr_fused_kernel<3, 8, 8><<<grid, 256, 0, stream>>>(a);
+    } else if (count == 2) {
+        dim3 grid((tw + 15) / 16, (th + 7) / 8, n_images);
+        pyr_fused_kernel<2, 16, 8><<<grid, 256, 0, stream>>>(a);
+    } else {
+        dim3 grid((tw + 31) / 32, (th + 7) / 8, n_images);
+        pyr_fused_kernel<1, 32, 8><<<grid, 256, 0, stream>>>(a);
+    }
+}
+
+// All levels 1..n_levels-1 of a pyramid from its level 0, in ceil((n_levels-1)/3) launches.  Returns the launch count.
+int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream) {
+    int first = 0, left = pv.n_levels - 1, n = 0;
+    while (left > 0) {
+        const int cnt = (left == 4) ? 2 : (left < 3 ? left : 3);
+        launch_pyr_fused(pv, stride, first, cnt, n_images, stream);
+        first += cnt; left -= cnt; ++n;
+    }
+    return n;
 }
 
 // calcScharrDeriv (video/lkpyramid.cpp) as a stand-alone plane kernel: int16 interleaved (Ix, Iy).

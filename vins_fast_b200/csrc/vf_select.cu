@@ -5,9 +5,10 @@
 //
 // The reference's std::sort is unstable and its comparator sees the track count only, so the order among
 // equally old features is whatever libstdc++'s introsort produces.  That order decides which of two close
-// features survives and the order of ids_, so it is reproduced exactly (introsort_emul.h): thread 0 replays
-// the introsort loop (median-of-3 + Hoare partition on ranges > 16, heap-sort fallback), and because the final
-// insertion sort is stable the finish is a parallel stable rank by track count.
+// features survives and the order of ids_, so it is reproduced exactly (introsort_emul.h): one warp replays
+// the introsort loop (median-of-3 + Hoare partition on ranges > 16 with the partition itself evaluated in
+// parallel, heap-sort fallback), and because the final insertion sort is stable the finish is a parallel
+// stable rank by track count.
 //
 // The greedy keep ("visit in sorted order, keep a feature iff no kept feature lies within min_dist of its
 // rounded centre", i.e. the filled cv::circle test dx^2+dy^2 <= r^2) is evaluated with a conflict bit-matrix
@@ -24,7 +25,7 @@ constexpr int kConflictSmemCap = 512;   // conflict matrix lives in shared memor
 
 // dynamic shared memory layout for `cap` features
 struct SelLayout {
-    size_t off_pts, off_ids, off_cnt, off_items, off_order, off_state, off_words, off_conf, total;
+    size_t off_pts, off_ids, off_cnt, off_items, off_order, off_state, off_lists, off_words, off_conf, total;
     int words;
     __host__ __device__ explicit SelLayout(int cap) {
         words = (cap + 31) / 32;
@@ -35,6 +36,7 @@ struct SelLayout {
         off_cnt = o;   o += sizeof(int) * cap;
         off_order = o; o += sizeof(int) * cap;
         off_state = o; o += sizeof(int) * cap;                  // rounded centres packed (x | y << 16) after sorting
+        off_lists = o; o += sizeof(int) * cap * 2;              // left / right stopper lists of the parallel partition
         off_words = o; o += sizeof(uint32_t) * words * 4;       // accepted / undecided masks, double use
         off_conf = o;  o += (cap <= kConflictSmemCap) ? sizeof(uint32_t) * (size_t)cap * words : 0;
         total = o;
@@ -42,6 +44,77 @@ struct SelLayout {
 };
 
 size_t select_tracked_smem_bytes(int cap) { return SelLayout(cap > 0 ? cap : 1).total + 64; }
+
+// std::__introsort_loop replayed by ONE WARP.  The control flow (explicit stack, depth limit, median-of-3, heap-sort
+// fallback) is the sequential algorithm of introsort_emul.h; only std::__unguarded_partition is evaluated in parallel:
+//   L = positions in (first, last) whose key does not precede the pivot's  (where the left scan stops),  ascending
+//   R = positions in (first, last) which the pivot does not precede        (where the right scan stops), descending
+//   the k-th swap of the sequential loop exchanges L[k] and R[k] for every k with L[k] < R[k]  (m of them), and the
+//   returned cut is min(L[m], R[m-1]).
+// (both scans only ever look at elements no swap has touched yet; tests/cpp/test_introsort.cpp checks this form
+//  against the real std::sort.)
+__device__ void warp_introsort_loop(SortItem* v, int n, int* stack, int* Lpos, int* Rpos) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = (1u << lane) - 1u;
+    if (n <= 16) return;
+    int sp = 0;
+    if (lane == 0) { stack[0] = 0; stack[1] = n; stack[2] = 2 * floor_log2(n); }
+    sp = 3;
+    __syncwarp();
+    while (sp > 0) {
+        int depth = stack[sp - 1], last = stack[sp - 2], first = stack[sp - 3];
+        sp -= 3;
+        __syncwarp();
+        while (last - first > 16) {
+            if (depth == 0) {
+                if (lane == 0) heap_sort_range(v + first, last - first);
+                __syncwarp();
+                break;
+            }
+            --depth;
+            if (lane == 0) move_median_to_first(v, first, first + 1, first + (last - first) / 2, last - 1);
+            __syncwarp();
+            const int pk = v[first].key;
+            int nL = 0, nR = 0;
+            for (int base = first + 1; base < last; base += 32) {
+                const int p = base + lane;
+                const bool stop = p < last && !(v[p].key > pk);
+                const unsigned int bal = __ballot_sync(0xffffffffu, stop);
+                if (stop) Lpos[nL + __popc(bal & lt)] = p;
+                nL += __popc(bal);
+            }
+            for (int base = last - 1; base > first; base -= 32) {
+                const int p = base - lane;
+                const bool stop = p > first && !(pk > v[p].key);
+                const unsigned int bal = __ballot_sync(0xffffffffu, stop);
+                if (stop) Rpos[nR + __popc(bal & lt)] = p;
+                nR += __popc(bal);
+            }
+            __syncwarp();
+            const int K = min(nL, nR);
+            int m = 0;
+            for (int base = 0; base < K; base += 32) {
+                const int k = base + lane;
+                const bool ok = k < K && Lpos[k] < Rpos[k];
+                const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+                if (bal == 0xffffffffu) { m += 32; continue; }
+                m += __ffs(~bal) - 1;
+                break;
+            }
+            for (int k = lane; k < m; k += 32) {
+                const int a = Lpos[k], c = Rpos[k];
+                const SortItem t = v[a]; v[a] = v[c]; v[c] = t;
+            }
+            const int a_m = m < nL ? Lpos[m] : 0x7fffffff, b_prev = m > 0 ? Rpos[m - 1] : 0x7fffffff;
+            const int cut = min(a_m, b_prev);
+            __syncwarp();
+            if (lane == 0) { stack[sp] = cut; stack[sp + 1] = last; stack[sp + 2] = depth; }
+            sp += 3;
+            last = cut;
+        }
+        __syncwarp();
+    }
+}
 
 __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBatch* __restrict__ bp, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -56,6 +129,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
     int* cnts = reinterpret_cast<int*>(smem_raw + L.off_cnt);
     int* order = reinterpret_cast<int*>(smem_raw + L.off_order);
     int* centre = reinterpret_cast<int*>(smem_raw + L.off_state);
+    int* lists = reinterpret_cast<int*>(smem_raw + L.off_lists);
     uint32_t* accw = reinterpret_cast<uint32_t*>(smem_raw + L.off_words);
     uint32_t* undw = accw + L.words;
     uint32_t* conf = (cap <= kConflictSmemCap) ? reinterpret_cast<uint32_t*>(smem_raw + L.off_conf)
@@ -88,7 +162,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
     }
 
     // ---- 2. libstdc++ std::sort order: introsort loop (sequential replay) + stable rank (parallel) ----
-    if (tid == 0 && n_tr > 16) vf_introsort_loop(items, n_tr, stack);
+    if (wid == 0) warp_introsort_loop(items, n_tr, stack, lists, lists + cap);
     __syncthreads();
     for (int j = tid; j < n_tr; j += ST_THREADS) {
         const int kj = items[j].key;

@@ -246,6 +246,15 @@ class Batch:
     def launches_per_frame(self) -> int:
         return int(self._lib.vf_batch_launches_per_frame(self._h))
 
+    def set_profiling(self, enable: bool):
+        check(self._lib.vf_batch_set_profiling(self._h, 1 if enable else 0), self.last_error)
+
+    def stage_times_ms(self) -> dict:
+        n = self._lib.vf_batch_stage_count()
+        ms = np.zeros(n, np.float32)
+        check(self._lib.vf_batch_stage_times(self._h, ms.ctypes.data, n), self.last_error)
+        return {self._lib.vf_batch_stage_name(i).decode(): float(ms[i]) for i in range(n)}
+
     def debug(self, stream: int, what: int, arg: int = 0, dtype=np.uint8, shape=None) -> np.ndarray:
         view = self._lib.vf_batch_stream(self._h, stream)
         return _debug_get(self._lib, view, what, arg, dtype, shape, self.cfg)
