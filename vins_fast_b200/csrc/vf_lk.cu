@@ -43,7 +43,7 @@ struct LevelRef {
 struct LkSmem {
     alignas(16) float termsA[kChainsA * kChain];
     alignas(16) float termsB[kChainsB * kChain];
-    uint8_t tileI[kTileI * kTileI];
+    uint8_t tileIs[kMaxLevels][kTileI * kTileI];   // I tiles of every level of the current pass (prefetched together)
     uint8_t tileJ[kTileJ * kTileJ];
     short2 dtile[kTileD * kTileD];
     short Iw[kWinPx + 1];
@@ -54,6 +54,19 @@ struct LkSmem {
 };
 
 #define VF_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+
+// Optional phase timing (build with -DVF_LK_TIMING): thread 0 of every CTA accumulates clock64() deltas per phase and
+// adds them to vf_lk_timing[k] (cycles) / vf_lk_timing[16 + k] (visits).  Measurement aid only; the marks split lane 0
+// from its warp, which inflates whatever follows a mark until the next reconvergence.
+#ifdef VF_LK_TIMING
+__device__ unsigned long long vf_lk_timing[32];
+#define LK_T_DECL long long lk_t_last = clock64();
+#define LK_T(k) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&vf_lk_timing[k], (unsigned long long)(t__ - lk_t_last)); \
+                     atomicAdd(&vf_lk_timing[16 + (k)], 1ull); lk_t_last = t__; } } while (0)
+#else
+#define LK_T_DECL
+#define LK_T(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
     const float one_a = __fsub_rn(1.f, a), one_b = __fsub_rn(1.f, b);
@@ -72,10 +85,11 @@ __device__ __forceinline__ void lk_smem_init(LkSmem& sm) {
 
 // Sequential float chain acc = (((0 + t0) + t1) + ...) in the order OpenCV's accumulators see the terms: 27 vector
 // loads, 108 dependent FADDs (the latency floor of one LK iteration).
-__device__ __forceinline__ float chain_sum(const float* src) {
+// Not inlined: one copy serves A and b, which keeps the per-iteration code inside the instruction cache.
+__device__ __noinline__ float chain_sum(const float* src) {
     const float4* p = reinterpret_cast<const float4*>(src);
     float acc = 0.f;
-#pragma unroll 9
+#pragma unroll
     for (int i = 0; i < kChain / 4; ++i) {
         const float4 v = p[i];
         acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
@@ -84,27 +98,63 @@ __device__ __forceinline__ float chain_sum(const float* src) {
 }
 
 // Stage a TS x TS tile of `img` with origin (x0, y0), reflect-101 outside the image.
+// Reflect-101 for tile coordinates: two branch-free folds cover every index within 2n-2 of the image
+// (tiles reach at most 26 pixels outside a level, levels are at least 22 pixels wide).
+__device__ __forceinline__ int refl101_tile(int i, int n) {
+    i = i < 0 ? -i : i;
+    i = i >= n ? 2 * n - 2 - i : i;
+    i = i < 0 ? -i : i;
+    i = i >= n ? 2 * n - 2 - i : i;
+    return i;
+}
+
+// Stage a TS x TS tile of a level with origin (x0, y0), reflect-101 outside the image.  All loads of a thread are
+// issued before its first store (one memory round trip per tile).  Not inlined (code size, see lk_track_point).
 template <int TS>
-__device__ __forceinline__ void stage_tile(uint8_t* tile, const LevelRef& L, int x0, int y0) {
-    const bool inside = x0 >= 0 && y0 >= 0 && x0 + TS <= L.w && y0 + TS <= L.h;
-    for (int i = threadIdx.x; i < TS * TS; i += kLkThreads) {
+__device__ __noinline__ void stage_tile(uint8_t* tile, const LevelRef& L, int x0, int y0) {
+    constexpr int PER = (TS * TS + kLkThreads - 1) / kLkThreads;
+    uint8_t v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * kLkThreads;
         const int ty = i / TS, tx = i - ty * TS;
-        int gx = x0 + tx, gy = y0 + ty;
-        if (!inside) { gx = refl101(gx, L.w); gy = refl101(gy, L.h); }
-        tile[i] = __ldg(L.p + (size_t)gy * L.pitch + gx);
+        const int gx = refl101_tile(x0 + tx, L.w), gy = refl101_tile(min(y0 + ty, y0 + TS - 1), L.h);
+        v[k] = __ldg(L.p + (size_t)gy * L.pitch + gx);
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int i = threadIdx.x + k * kLkThreads;
+        if (i < TS * TS) tile[i] = v[k];
     }
 }
 
 // One calcOpticalFlowPyrLK for one point, executed cooperatively by the CTA (all threads pass identical
 // arguments and return identical results).  ia / ja select the source and target pyramids in sm.pyr.
-__device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init, int max_level,
-                               float2& out_pt, int& out_status, int& iters) {
+// Not inlined: the forward and the reverse pass of a kernel share one copy of this code (the kernel is latency-bound with
+// one CTA per SM, so instruction-cache misses are fully exposed; the body must stay well under the 32 KB L1.5 I-cache).
+__device__ __noinline__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init,
+                                            int max_level, float2& out_pt, int& out_status, int& iters) {
     const int tid = threadIdx.x;
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (1 << 20);
     int status = 1;
     float outx = init_pt.x, outy = init_pt.y;
+    LK_T_DECL
 
+    // The I tiles depend on prev_pt only: fetch them for every level of this pass now, in one burst of loads.
+    __syncthreads();   // the previous pass may still be reading the shared buffers
+#pragma unroll 1
+    for (int level = max_level; level >= 0; --level) {
+        const LevelRef LI = sm.pyr[ia][level];
+        const float scale = 1.f / (float)(1 << level);
+        const int ipx = __float2int_rd(__fsub_rn(__fmul_rn(prev_pt.x, scale), half));
+        const int ipy = __float2int_rd(__fsub_rn(__fmul_rn(prev_pt.y, scale), half));
+        if (ipx < -kWin || ipx >= LI.w || ipy < -kWin || ipy >= LI.h) continue;
+        stage_tile<kTileI>(sm.tileIs[level], LI, ipx - 1, ipy - 1);
+    }
+    LK_T(7);
+
+#pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
         const LevelRef LI = sm.pyr[ia][level], LJ = sm.pyr[ja][level];
         const int cols = LI.w, rows = LI.h, jcols = LJ.w, jrows = LJ.h;
@@ -126,19 +176,21 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
 
-        // ---- stage the 24x24 tile of I (origin ip-1) and a 32x32 tile of J around the start of the search ----
+        // ---- stage a 32x32 tile of J around the start of the search (the 24x24 tile of I is already resident) ----
         int jx0 = __float2int_rd(__fsub_rn(nx, half)) - kJMargin, jy0 = __float2int_rd(__fsub_rn(ny, half)) - kJMargin;
-        __syncthreads();   // previous level / previous pass may still be reading the shared buffers
-        stage_tile<kTileI>(sm.tileI, LI, ipx - 1, ipy - 1);
+        const uint8_t* tileI = sm.tileIs[level];
+        __syncthreads();   // the previous level may still be reading tileJ / the patch buffers
         stage_tile<kTileJ>(sm.tileJ, LJ, jx0, jy0);
         __syncthreads();
+        LK_T(0);
         // ---- Scharr (Ix,Iy) on the 22x22 tap positions; zero outside the image ----
+#pragma unroll 1
         for (int i = tid; i < kTileD * kTileD; i += kLkThreads) {
             const int ty = i / kTileD, tx = i - ty * kTileD;
             const int x = ipx + tx, y = ipy + ty;
             short2 d = make_short2(0, 0);
             if (x >= 0 && x < cols && y >= 0 && y < rows) {
-                const uint8_t* p = &sm.tileI[(ty + 1) * kTileI + (tx + 1)];
+                const uint8_t* p = &tileI[(ty + 1) * kTileI + (tx + 1)];
                 const int a00 = p[-kTileI - 1], a01 = p[-kTileI], a02 = p[-kTileI + 1];
                 const int a10 = p[-1], a12 = p[1];
                 const int a20 = p[kTileI - 1], a21 = p[kTileI], a22 = p[kTileI + 1];
@@ -149,10 +201,12 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
             sm.dtile[i] = d;
         }
         __syncthreads();
+        LK_T(1);
         // ---- 21x21 bilinear patch (I in 2^5, derivatives in Scharr units) + terms of A ----
+#pragma unroll 1
         for (int i = tid; i < kWinPx; i += kLkThreads) {
             const int y = i / kWin, x = i - y * kWin;
-            const uint8_t* s = &sm.tileI[(y + 1) * kTileI + (x + 1)];
+            const uint8_t* s = &tileI[(y + 1) * kTileI + (x + 1)];
             const int ival = VF_DESCALE(s[0] * w00 + s[1] * w01 + s[kTileI] * w10 + s[kTileI + 1] * w11, 9);
             const short2 d00 = sm.dtile[y * kTileD + x], d01 = sm.dtile[y * kTileD + x + 1];
             const short2 d10 = sm.dtile[(y + 1) * kTileD + x], d11 = sm.dtile[(y + 1) * kTileD + x + 1];
@@ -175,9 +229,14 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
             }
         }
         __syncthreads();
+        LK_T(2);
         if (tid < 32) {
             const int lane = tid;
+            // Converge the warp before the chain and before the shuffles: a warp that arrives split (e.g. lane 0 after the
+            // timing marks) would run the chain once per group and take the WARPSYNC.COLLECTIVE path on every shuffle.
+            __syncwarp();
             const float acc = chain_sum(&sm.termsA[min(lane, kChainsA - 1) * kChain]);
+            __syncwarp();
             float r[3];
 #pragma unroll
             for (int m = 0; m < 3; ++m) {
@@ -189,6 +248,7 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
             if (lane == 0) { sm.bcast[0] = r[0]; sm.bcast[1] = r[1]; sm.bcast[2] = r[2]; }
         }
         __syncthreads();
+        LK_T(3);
         const float A11 = __fmul_rn(sm.bcast[0], FLT_SCALE), A12 = __fmul_rn(sm.bcast[1], FLT_SCALE),
                     A22 = __fmul_rn(sm.bcast[2], FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -202,6 +262,7 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
         D = __fdiv_rn(1.f, D);
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
+#pragma unroll 1
         for (int j = 0; j < 30; ++j) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
             if (inx < -kWin || inx >= jcols || iny < -kWin || iny >= jrows) {
@@ -217,6 +278,7 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
                 __syncthreads();
             }
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            LK_T(4);
             const uint8_t* jt = &sm.tileJ[(iny - jy0) * kTileJ + (inx - jx0)];
             auto jdiff = [&](int y, int x) -> int {
                 const uint8_t* p = jt + y * kTileJ + x;
@@ -247,9 +309,12 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
                 }
             }
             __syncthreads();
+            LK_T(5);
             if (tid < 32) {
                 const int lane = tid;
+                __syncwarp();
                 const float acc = chain_sum(&sm.termsB[min(lane, kChainsB - 1) * kChain]);
+                __syncwarp();
                 float k[10];
 #pragma unroll
                 for (int q = 0; q < 10; ++q) k[q] = __shfl_sync(0xffffffffu, acc, q);
@@ -262,6 +327,7 @@ __device__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float
                 }
             }
             __syncthreads();
+            LK_T(6);
             const float b1 = __fmul_rn(sm.bcast[0], FLT_SCALE), b2 = __fmul_rn(sm.bcast[1], FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
@@ -447,3 +513,12 @@ void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_p
 }
 
 }  // namespace vf
+
+#ifdef VF_LK_TIMING
+// measurement aid (timing build only): read and clear the per-phase cycle counters
+extern "C" int vf_debug_lk_timing(unsigned long long* out16) {
+    unsigned long long zero[32] = {0};
+    if (cudaMemcpyFromSymbol(out16, vf::vf_lk_timing, sizeof(zero)) != cudaSuccess) return 1;
+    return cudaMemcpyToSymbol(vf::vf_lk_timing, zero, sizeof(zero)) != cudaSuccess;
+}
+#endif
