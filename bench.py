@@ -300,7 +300,7 @@ def main():
         # ---------------- per-kernel times (CUDA events on the launching streams) ----------------
         batch.reset()
         batch.set_profiling(True)
-        acc, n_prof, iters_t, iters_s, feats = {}, 0, 0, 0, 0
+        acc, n_prof, iters_t, iters_s, feats, fast_it = {}, 0, 0, 0, 0, 0
         from vins_fast_b200 import _lib as L
         for k in range(min(n_frames, Wm + 60)):
             batch.track_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
@@ -308,9 +308,10 @@ def main():
                 for name, ms in batch.stage_times_ms().items():
                     acc[name] = acc.get(name, 0.0) + ms
                 n_prof += 1
-                iters_t += int(batch.debug(0, L.DBG_LK_ITERS, 0, np.int32).sum())
+                it_t = batch.debug(0, L.DBG_LK_ITERS, 0, np.int32)
                 it_s = batch.debug(0, L.DBG_LK_ITERS, 1, np.int32)
-                iters_s += int(it_s.sum()); feats += len(it_s)
+                iters_t += int((it_t & 0xffff).sum()); iters_s += int((it_s & 0xffff).sum()); feats += len(it_s)
+                fast_it += int((it_t >> 16).sum()) + int((it_s >> 16).sum())
         batch.set_profiling(False)
         stages_us = {k: v / max(n_prof, 1) * 1e3 for k, v in acc.items()}
 
@@ -398,6 +399,8 @@ def main():
                 "d2h_bytes_per_step": MAX_CNT * 60 + 64, "clocks": clk2.summary()},
         "gpu_launches": launches, "launches_per_frame": batch.launches_per_frame,
         "stages_us": stages_us, "roofline": roofline, "multi_stream": multi,
+        "lk": {"iterations_per_frame": (iters_t + iters_s) / max(n_prof, 1),
+               "exact_integer_path_fraction": fast_it / max(iters_t + iters_s, 1)},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(frames, 160)

@@ -149,7 +149,8 @@ enum {
     VF_DBG_RL_PTS = 12,      /* float 2*n     right->left LK result                                      */
     VF_DBG_RL_STATUS = 13,   /* uint8 n                                                                  */
     VF_DBG_COUNTS = 14,      /* int32[8]: n_prev, n_tracked, n_kept, n_new, n_total, n_right, n_local_max, landmark_id */
-    VF_DBG_LK_ITERS = 15     /* arg 0: int32 n_prev, temporal passes; arg 1: int32 n, stereo passes: inner LK iterations per feature */
+    VF_DBG_LK_ITERS = 15     /* arg 0: int32 n_prev, temporal passes; arg 1: int32 n, stereo passes: inner LK iterations per feature
+                              * (low 16 bits; the high 16 bits count the iterations that took the exact-integer summation path) */
 };
 /* Copies the item into `buf` (capacity `cap_bytes`), writes the byte size to *size_out. */
 vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* buf, size_t cap_bytes, size_t* size_out);

@@ -33,7 +33,6 @@ constexpr int kTail = 105;                   // 21 rows x 5 tail columns
 constexpr int kChain = 108;                  // every summation chain is padded with zeros to 27 float4
 constexpr int kChainsA = 15;                 // 3 x 4 SIMD-lane accumulators (84 terms) + 3 scalar tails (105 terms)
 constexpr int kChainsB = 10;                 // 8 SIMD-lane accumulators (42 terms) + 2 scalar tails (105 terms)
-constexpr int kItemsB = 168 + 53;            // phase-1 work items of one iteration: 168 column pairs + 53 tail pairs
 
 struct LevelRef {
     const uint8_t* p;
@@ -51,6 +50,9 @@ struct LkSmem {
     LevelRef pyr[2][kMaxLevels];
     float bcast[4];
     int found[2];
+    int part[8][10];     // per-warp exact integer partial sums of the 10 chains of b
+    int bound[8];        // per-warp sum |term|
+    int fast_iters;      // iterations whose chains were provably exact integers (statistics)
 };
 
 #define VF_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
@@ -81,6 +83,8 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
 __device__ __forceinline__ void lk_smem_init(LkSmem& sm) {
     for (int i = threadIdx.x; i < kChainsA * kChain; i += kLkThreads) sm.termsA[i] = 0.f;
     for (int i = threadIdx.x; i < kChainsB * kChain; i += kLkThreads) sm.termsB[i] = 0.f;
+    if (threadIdx.x < 80) (&sm.part[0][0])[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sm.fast_iters = 0;
 }
 
 // Sequential float chain acc = (((0 + t0) + t1) + ...) in the order OpenCV's accumulators see the terms: 27 vector
@@ -285,35 +289,72 @@ __device__ __noinline__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 p
                 const int v = p[0] * w00 + p[1] * w01 + p[kTileJ] * w10 + p[kTileJ + 1] * w11;
                 return VF_DESCALE(v, 9) - (int)sm.Iw[y * kWin + x];
             };
-            // terms of b, one work item per thread: 168 column pairs (c, c+4) of the two 8-wide SIMD groups of every
-            // row (pmaddwd pair sums), then 53 pairs of tail pixels (columns 16..20)
+            // terms of b, one work item per thread: threads 0..167 take the 168 column pairs (c, c+4) of the two 8-wide
+            // SIMD groups of every row (pmaddwd pair sums), threads 192..244 take 53 pairs of tail pixels (columns 16..20).
+            // Besides the float terms of the ordered chains, every chain is also summed as an exact integer together with
+            // a bound on sum|term|: when the bound is below 2^24 every partial sum of every float chain is an exactly
+            // representable integer, the order of the additions cannot matter, and the chain value IS the integer sum --
+            // the 105-deep dependent FADD chain is skipped (bit-identical result).
+            int tx = 0, ty = 0, ab = 0;
             if (tid < 168) {
                 const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3;
                 const int xa = 8 * g + c, xb = xa + 4;
                 const int da = jdiff(y, xa), db = jdiff(y, xb);
                 const short2 pa = sm.dI[y * kWin + xa], pb = sm.dI[y * kWin + xb];
                 const int slot = y * 2 + g;
-                sm.termsB[(2 * c + 0) * kChain + slot] = (float)(da * pa.x + db * pb.x);   // exact int32 pair sum, then cvt
-                sm.termsB[(2 * c + 1) * kChain + slot] = (float)(da * pa.y + db * pb.y);
-            } else if (tid < kItemsB) {
+                tx = da * pa.x + db * pb.x; ty = da * pa.y + db * pb.y;             // exact int32 pair sums
+                ab = abs(tx) + abs(ty);
+                sm.termsB[(2 * c + 0) * kChain + slot] = (float)tx;
+                sm.termsB[(2 * c + 1) * kChain + slot] = (float)ty;
+            } else if (tid >= 192 && tid < 192 + 53) {
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
-                    const int t = 2 * (tid - 168) + h2;
+                    const int t = 2 * (tid - 192) + h2;
                     if (t < kTail) {
                         const int y = t / 5, x = 16 + (t - y * 5);
                         const int d = jdiff(y, x);
                         const short2 pd = sm.dI[y * kWin + x];
-                        sm.termsB[8 * kChain + t] = (float)(d * pd.x);
-                        sm.termsB[9 * kChain + t] = (float)(d * pd.y);
+                        const int ex = d * pd.x, ey = d * pd.y;
+                        tx += ex; ty += ey; ab += abs(ex) + abs(ey);
+                        sm.termsB[8 * kChain + t] = (float)ex;
+                        sm.termsB[9 * kChain + t] = (float)ey;
                     }
                 }
+            }
+            {
+                const int wid = tid >> 5, lane = tid & 31;
+                ab = __reduce_add_sync(0xffffffffu, ab);
+                if (wid < 6) {          // pair warps: lanes with equal (lane & 3) feed the same two chains
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {
+                        tx += __shfl_xor_sync(0xffffffffu, tx, o);
+                        ty += __shfl_xor_sync(0xffffffffu, ty, o);
+                    }
+                    if (lane < 4) { sm.part[wid][2 * lane] = tx; sm.part[wid][2 * lane + 1] = ty; }
+                } else {                // tail warps
+                    tx = __reduce_add_sync(0xffffffffu, tx);
+                    ty = __reduce_add_sync(0xffffffffu, ty);
+                    if (lane == 0) { sm.part[wid][8] = tx; sm.part[wid][9] = ty; }
+                }
+                if (lane == 0) sm.bound[wid] = ab;
             }
             __syncthreads();
             LK_T(5);
             if (tid < 32) {
                 const int lane = tid;
                 __syncwarp();
-                const float acc = chain_sum(&sm.termsB[min(lane, kChainsB - 1) * kChain]);
+                int isum = 0, bnd = 0;
+                if (lane < 8) {
+#pragma unroll
+                    for (int w = 0; w < 6; ++w) isum += sm.part[w][lane];
+                } else if (lane < 10) {
+                    isum = sm.part[6][lane] + sm.part[7][lane];
+                }
+#pragma unroll
+                for (int w = 0; w < 8; ++w) bnd += sm.bound[w];
+                float acc;
+                if (bnd < (1 << 24)) acc = (float)isum;                                   // exact: order-independent
+                else acc = chain_sum(&sm.termsB[min(lane, kChainsB - 1) * kChain]);       // OpenCV's summation order
                 __syncwarp();
                 float k[10];
 #pragma unroll
@@ -324,6 +365,7 @@ __device__ __noinline__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 p
                 if (lane == 0) {
                     sm.bcast[0] = __fadd_rn(k[8], __fadd_rn(s0, s2));
                     sm.bcast[1] = __fadd_rn(k[9], __fadd_rn(s1, s3));
+                    if (bnd < (1 << 24)) ++sm.fast_iters;
                 }
             }
             __syncthreads();
@@ -400,7 +442,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch*
         b.fwd_pts[o] = fwd; b.fwd_st[o] = (uint8_t)st;
         b.rev_pts[o] = rev; b.rev_st[o] = (uint8_t)rst;
         b.temporal_st[o] = (uint8_t)ok;
-        b.lk_iters[o] = iters;
+        b.lk_iters[o] = iters | (sm.fast_iters << 16);   // low 16 bits: iterations, high: of which on the exact-integer path
     }
 }
 
@@ -463,7 +505,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
         b.un_right[parity][o] = unr;
         b.right_ok[parity][o] = (uint8_t)ok;
         b.lr_pts[o] = rp; b.lr_st[o] = (uint8_t)st; b.rl_pts[o] = back; b.rl_st[o] = (uint8_t)rst;
-        b.lk_iters_stereo[o] = iters;
+        b.lk_iters_stereo[o] = iters | (sm.fast_iters << 16);
         if (ok) atomicAdd(&b.counters[parity][s * C_COUNT + C_N_RIGHT], 1);
     }
 }
