@@ -4,7 +4,7 @@
  *     estimator::FeatureTracker::TrackImage(t, img0, img1)      vins/estimator/feature_tracker.cpp:27-217
  * and the pieces it is made of.  Every entry point below cites the reference interface it replaces.
  * Plain pointers and sizes only (no torch / OpenCV / Eigen types).  The C++ class with the
- * reference's API (vins_fast_b200/csrc/feature_tracker.hpp) and the Python mirror
+ * reference's API (include/vins_fast_b200/feature_tracker.hpp, header-only) and the Python mirror
  * (vins_fast_b200/tracker.py) are thin layers over these calls.
  *
  * Conventions: all functions return vf_status (0 = VF_OK); nothing aborts or throws.  The caller owns
@@ -88,6 +88,9 @@ void vf_config_default(vf_config* cfg);
 vf_status vf_config_load_yaml(const char* estimator_yaml, vf_config* cfg);
 /* CameraFactory::generateCameraFromYamlFile (CameraFactory.cc:96-189) for MEI and PINHOLE. */
 vf_status vf_camera_load_yaml(const char* calib_yaml, vf_camera* cam);
+/* common::Setting::Get<T>(key) (vins/common/parameter.hpp:36-53): the raw scalar text of `key` (or "section.key")
+ * of an OpenCV-dialect YAML file, NUL-terminated into value_out[cap].  Missing key -> VF_ERR_PARSE. */
+vf_status vf_yaml_get(const char* yaml_path, const char* key, char* value_out, size_t cap);
 const char* vf_last_global_error(void);   /* message of the last failing call that had no handle */
 
 /* ---- one stream: replaces FeatureTracker ctor/dtor and TrackImage --------------------------------- */

@@ -57,6 +57,74 @@ def euroc_frames(euroc_seq):
     return [euroc_seq.frame(k) for k in range(24)]
 
 
+def build_cpp_test(name: str, link_lib: bool = True) -> str:
+    """g++ build of tests/cpp/<name>.cpp into tests/cpp/_build/ (rebuilt when a source or header is newer)."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
+    out_dir = os.path.join(ROOT, "tests", "cpp", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, name)
+    deps = [src, os.path.join(ROOT, "include", "vins_fast_b200.h"), os.path.join(ROOT, "vins_fast_b200", "csrc", "introsort_emul.h")]
+    inc = os.path.join(ROOT, "include", "vins_fast_b200")
+    deps += [os.path.join(inc, f) for f in os.listdir(inc)]
+    libdir = os.path.join(ROOT, "vins_fast_b200")
+    if link_lib:
+        from vins_fast_b200 import build
+        deps.append(build.build())
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        cmd = ["g++", "-std=c++14", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe]
+        if link_lib:
+            cmd += ["-L", libdir, "-lvinsfast_b200", "-Wl,-rpath," + libdir]
+        subprocess.check_call(cmd)
+    return exe
+
+
+def write_camera_yaml(path, cam, width: int, height: int):
+    """camodocal calibration file (vins/config/euroc/cam0_mei.yaml layout) for an oracle.camera.Camera."""
+    mei = cam.model == 0
+    lines = ["%YAML:1.0", "---", f"model_type: {'MEI' if mei else 'PINHOLE'}", "camera_name: camera",
+             f"image_width: {width}", f"image_height: {height}"]
+    if mei:
+        lines += ["mirror_parameters:", f"   xi: {cam.xi!r}"]
+    lines += ["distortion_parameters:", f"   k1: {cam.k1!r}", f"   k2: {cam.k2!r}", f"   p1: {cam.p1!r}", f"   p2: {cam.p2!r}",
+              "projection_parameters:"]
+    names = ("gamma1", "gamma2", "u0", "v0") if mei else ("fx", "fy", "cx", "cy")
+    lines += [f"   {n}: {v!r}" for n, v in zip(names, (cam.fx, cam.fy, cam.cx, cam.cy))]
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    return path
+
+
+def write_estimator_yaml(path, max_cnt: int, min_dist: int, flow_back: int, show_track: int = 0, width: int = 752, height: int = 480):
+    """Estimator configuration in the layout of vins/config/euroc/euroc_stero.yaml (tracker keys + an opencv-matrix)."""
+    text = f"""%YAML:1.0
+
+#common parameters
+imu: 0
+num_of_cam: 2
+cam0_calib: "cam0_mei.yaml"
+cam1_calib: "cam1_mei.yaml"
+image_width: {width}
+image_height: {height}
+body_T_cam0: !!opencv-matrix
+   rows: 4
+   cols: 4
+   dt: d
+   data: [0.0148655429818, -0.999880929698, 0.00414029679422, -0.0216401454975,
+           0.999557249008, 0.0149672133247, 0.025715529948, -0.064676986768,
+           0, 0, 0, 1]
+max_cnt: {max_cnt}            # max feature number in feature tracking
+min_dist: {min_dist}            # min distance between two features
+flow_back: {flow_back}            # perform forward and backward optical flow to improve feature tracking accuracy
+show_track: {show_track}
+frontend_wait_key: 1
+td: 0.5
+"""
+    with open(path, "w") as f:
+        f.write(text)
+    return path
+
+
 def assert_frames_equal(a: dict, b: dict, ctx: str = ""):
     """Bit-exact comparison of two tracker outputs (oracle dict layout)."""
     for key in ("ids", "track_cnt", "uv", "un", "vel", "ids_right", "uv_right", "un_right", "vel_right"):

@@ -158,3 +158,39 @@ def test_error_codes(lib):
     size = C.c_size_t(0)
     st = lib.vf_tracker_debug_get(tr._h, _lib.DBG_EIG, 0, None, 0, C.byref(size))
     assert st == _lib.VF_ERR_STATE                                        # no frame yet
+
+
+def test_cpp_feature_tracker_drop_in(lib, oracle, euroc_frames, tmp_path):
+    """The header-only C++ class (include/vins_fast_b200/feature_tracker.hpp), driven like Estimator::FrontendTracker
+    (estimator.cpp:143-158) from YAML files: its featureFrame maps equal the oracle's, value for value."""
+    import struct
+    import subprocess
+    from conftest import build_cpp_test, write_camera_yaml, write_estimator_yaml
+    exe = build_cpp_test("test_feature_tracker")
+    write_camera_yaml(tmp_path / "cam0_mei.yaml", EUROC_CAM0, 752, 480)
+    write_camera_yaml(tmp_path / "cam1_mei.yaml", EUROC_CAM1, 752, 480)
+    est = write_estimator_yaml(tmp_path / "est.yaml", 150, 30, 1, show_track=1)
+    n = 6
+    with open(tmp_path / "frames.bin", "wb") as f:
+        for t, l, r in euroc_frames[:n]:
+            f.write(struct.pack("<d", t)); f.write(l.tobytes()); f.write(r.tobytes())
+    res = subprocess.run([exe, "run", str(est), str(tmp_path / "cam0_mei.yaml"), str(tmp_path / "cam1_mei.yaml"),
+                          str(tmp_path / "frames.bin"), "752", "480", str(n), str(tmp_path / "out.bin")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    buf = open(tmp_path / "out.bin", "rb").read()
+    off = 0
+    from oracle.cv2_oracle import Cv2FeatureTracker
+    ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
+    for k, (t, l, r) in enumerate(euroc_frames[:n]):
+        want = Cv2FeatureTracker.feature_frame(ref.track_image(t, l, r))
+        (n_ids,) = struct.unpack_from("<i", buf, off); off += 4
+        assert n_ids == len(want)
+        for fid in sorted(want):                                   # std::map iterates in key order
+            gid, n_obs = struct.unpack_from("<ii", buf, off); off += 8
+            assert gid == fid and n_obs == len(want[fid])
+            for cam_id, vec in want[fid]:
+                (gcam,) = struct.unpack_from("<i", buf, off); off += 4
+                v = np.frombuffer(buf, np.float64, 7, off); off += 56
+                assert gcam == cam_id and v.tobytes() == vec.tobytes(), f"frame {k} id {fid} cam {cam_id}"
+    assert off == len(buf)

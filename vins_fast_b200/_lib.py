@@ -45,7 +45,7 @@ assert FEATURE_DTYPE.itemsize == C.sizeof(VfFeature) == 60
 
 # every symbol include/vins_fast_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "vf_config_default", "vf_config_load_yaml", "vf_camera_load_yaml", "vf_last_global_error",
+    "vf_config_default", "vf_config_load_yaml", "vf_camera_load_yaml", "vf_yaml_get", "vf_last_global_error",
     "vf_tracker_create", "vf_tracker_destroy", "vf_tracker_reset", "vf_tracker_track", "vf_tracker_track_device",
     "vf_last_error",
     "vf_batch_create", "vf_batch_destroy", "vf_batch_reset", "vf_batch_size", "vf_batch_track", "vf_batch_track_device",
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
         "vf_config_default": (None, [P]),
         "vf_config_load_yaml": (I32, [C.c_char_p, P]),
         "vf_camera_load_yaml": (I32, [C.c_char_p, P]),
+        "vf_yaml_get": (I32, [C.c_char_p, C.c_char_p, P, SZ]),
         "vf_last_global_error": (C.c_char_p, []),
         "vf_tracker_create": (I32, [P, P]),
         "vf_tracker_destroy": (None, [P]),

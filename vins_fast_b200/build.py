@@ -1,4 +1,4 @@
-"""Builds libvinsfast_b200.so (CUDA kernels + C ABI + C++ FeatureTracker) in-tree for sm_100a with nvcc.
+"""Builds libvinsfast_b200.so (CUDA kernels + C ABI; the C++ FeatureTracker of include/vins_fast_b200/ is header-only over that ABI) in-tree for sm_100a with nvcc.
 
     python -m vins_fast_b200.build [--force] [--verbose]
 
@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libvinsfast_b200.so")
 
-SOURCES = ["vf_api.cu", "vf_pyramid.cu", "vf_lk.cu", "vf_corners.cu", "vf_select.cu", "vf_yaml.cpp", "feature_tracker.cpp"]
+SOURCES = ["vf_api.cu", "vf_pyramid.cu", "vf_lk.cu", "vf_corners.cu", "vf_select.cu", "vf_yaml.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # parity: no FMA contraction anywhere (critical expressions also use _rn intrinsics)

@@ -168,3 +168,17 @@ extern "C" vf_status vf_config_load_yaml(const char* estimator_yaml, vf_config* 
     }
     return VF_OK;
 }
+
+// common::Setting::Get<T>(key) (vins/common/parameter.hpp:36-53): raw scalar text of a top-level key, or of
+// "section.key" for one level of nesting.  The C++ mirror (include/vins_fast_b200/parameter.hpp) converts it to T.
+extern "C" vf_status vf_yaml_get(const char* yaml_path, const char* key, char* value_out, size_t cap) {
+    if (!yaml_path || !key || !value_out || cap == 0) { g_yaml_error = "null argument"; return VF_ERR_INVALID_ARG; }
+    std::map<std::string, std::string> m;
+    if (!parse_yaml(yaml_path, m, g_yaml_error)) return VF_ERR_IO;
+    auto it = m.find(key);
+    if (it == m.end()) { g_yaml_error = std::string("key '") + key + "' not found in " + yaml_path; return VF_ERR_PARSE; }
+    if (it->second.size() + 1 > cap) { g_yaml_error = "value buffer too small"; return VF_ERR_INVALID_ARG; }
+    std::copy(it->second.begin(), it->second.end(), value_out);
+    value_out[it->second.size()] = 0;
+    return VF_OK;
+}
