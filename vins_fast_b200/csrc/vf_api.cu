@@ -50,7 +50,8 @@ struct vf_batch {
     int S = 0, device = 0;
     cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr;
     bool own_main = false;
-    cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr,
+                ev_sel = nullptr, ev_un = nullptr;
     DevBatch h;               // host copy of the device descriptor
     DevBatch* d = nullptr;    // device copy
     std::vector<void*> allocs;
@@ -72,10 +73,10 @@ struct vf_batch {
 };
 
 enum Stage { ST_H2D_LEFT = 0, ST_PYR_LEFT, ST_LK_TEMPORAL, ST_SELECT_TRACKED, ST_RESPONSE_NMS, ST_BUCKET_SCAN, ST_BUCKET_SCATTER,
-             ST_MASK_AND_MAX, ST_GFTT_SELECT, ST_H2D_RIGHT, ST_PYR_RIGHT, ST_LK_STEREO, ST_D2H, ST_CLEAR, ST_COUNT };
+             ST_MASK_AND_MAX, ST_GFTT_SELECT, ST_H2D_RIGHT, ST_PYR_RIGHT, ST_LK_STEREO, ST_D2H, ST_CLEAR, ST_UNDISTORT_LEFT, ST_COUNT };
 static const char* kStageNames[ST_COUNT] = {"h2d_left", "pyrdown_left", "lk_temporal", "select_tracked", "response_nms", "bucket_scan",
                                             "bucket_scatter", "mask_and_max", "gftt_select", "h2d_right", "pyrdown_right", "lk_stereo",
-                                            "d2h", "clear_frame"};
+                                            "d2h", "clear_frame", "undistort_left"};
 
 struct StageTimer {   // records begin/end events on `st` around a scope when profiling is on
     vf_batch* b; int id; cudaStream_t st;
@@ -199,6 +200,8 @@ void destroy_batch(vf_batch* b) {
     if (b->ev_resp) cudaEventDestroy(b->ev_resp);
     if (b->ev_right) cudaEventDestroy(b->ev_right);
     if (b->ev_img) cudaEventDestroy(b->ev_img);
+    if (b->ev_sel) cudaEventDestroy(b->ev_sel);
+    if (b->ev_un) cudaEventDestroy(b->ev_un);
     for (int k = 0; k < 16; ++k) { if (b->st_beg[k]) cudaEventDestroy(b->st_beg[k]); if (b->st_end[k]) cudaEventDestroy(b->st_end[k]); }
     if (b->side_a) cudaStreamDestroy(b->side_a);
     if (b->side_b) cudaStreamDestroy(b->side_b);
@@ -326,8 +329,14 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         if (st != VF_OK) return st;
     }
     n_launch += b->chain_launches;
+    // left camera undistortion + velocity beside the stereo LK (it needs current_kps_ / ids_ only)
+    VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_sel, 0));
+    { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_a); launch_undistort_left(b->d, h, parity, b->side_a); ++n_launch; }
+    VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_a));
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
     { StageTimer t(b, ST_LK_STEREO, b->main); launch_lk_stereo(b->d, h, parity, b->main); ++n_launch; }
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_un, 0));
     VF_CUDA(b, cudaGetLastError());
     {
         StageTimer t(b, ST_D2H, b->main);
@@ -426,6 +435,8 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRYC(cudaEventCreateWithFlags(&b->ev_resp, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_right, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_img, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_un, cudaEventDisableTiming));
     for (int p = 0; p < 2; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_done[p], cudaEventDisableTiming));
 
     DevBatch& h = b->h;
@@ -464,6 +475,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     }
     TRYC(cudaMallocHost(&b->pin_times, sizeof(double) * (size_t)S * 2));
     TRYC(select_tracked_prepare(cap));
+    TRYC(lk_prepare());
     TRYC(cudaDeviceSynchronize());
     b->views.resize(S);
     for (int s = 0; s < S; ++s) { b->views[s].batch = b; b->views[s].stream_index = s; b->views[s].owns_batch = false; }
@@ -761,6 +773,7 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
     VF_CUDA((vf_batch*)nullptr, cudaMalloc(&di, sizeof(int) * n)); a.allocs.push_back(di);
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(dp, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(dn, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    VF_CUDA((vf_batch*)nullptr, lk_prepare());
     launch_lk_op(a.pv, c.pv, dp, dn, ds, di, n, max_level, use_initial_flow, 0);
     VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(next_pts, dn, sizeof(float2) * n, cudaMemcpyDeviceToHost));

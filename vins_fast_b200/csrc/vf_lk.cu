@@ -3,18 +3,25 @@
 //
 // Replaces the four cv::calcOpticalFlowPyrLK calls of the reference
 // (vins/estimator/feature_tracker.cpp:41-42, 50-53, 117-119, 125-127) and the status logic around them
-// (:55-67, :128-133), plus RemoveDistortion / ComputeKpsVelocity (:310-363) in the stereo epilogue.
+// (:55-67, :128-133), plus the right camera's RemoveDistortion / ComputeKpsVelocity (:310-363) in the stereo epilogue.
 //
 // Arithmetic = OpenCV's LKTrackerInvoker (modules/video/src/lkpyramid.cpp), restated in oracle/vf_oracle.c:
 //   * 21x21 bilinear patch of I and of its Scharr derivative in W_BITS=14 fixed point (integers);
 //   * A11,A12,A22 and b1,b2 are FLOAT sums accumulated in the exact order OpenCV's 128-bit SIMD loop uses
 //     (4 / 8 interleaved lane accumulators over columns 0..15, a scalar tail over columns 16..20, then the
-//     v_reduce_sum tree), so positions and status flags are bit-identical to the OpenCV CPU path instead of
-//     "within 0.01 px".  The terms of those sums are produced by all 128 threads; one warp then runs the
-//     order-dependent chains (<= 105 dependent FADDs), which is the latency floor of an iteration.
-//   * the Scharr derivative is never materialised in HBM: each level stages a 24x24 uint8 tile of I in shared
-//     memory and derives the 22x22 (Ix,Iy) tile from it (zero outside the image, reflect-101 inside), so the
-//     kernel reads only the uint8 pyramids.
+//     v_reduce_sum tree), so positions and status flags are bit-identical to the OpenCV CPU path.
+//
+// The path is a dependent chain (levels x Gauss-Newton iterations), so the kernel is organised around latency:
+//   * everything that depends only on the source point -- the 24x24 uint8 tiles of I on EVERY level, their Scharr
+//     tiles, the interpolated patches Iw / dI and the 2x2 matrix A -- is computed in one prologue for all levels at
+//     once (4 block barriers in total); the level loop is left with the J tile and the iterations;
+//   * the float sums are integer-valued.  A chain whose terms satisfy sum|t| < 2^24 has only exactly representable
+//     partial sums, so its value is the integer sum and the order of the additions is irrelevant: such chains are
+//     reduced with REDUX (one instruction per warp) instead of 84..105 dependent FADDs.  One iteration then costs ONE
+//     block barrier: every thread contributes two pixels, each warp publishes (sum_x, sum_y, sum|.|) and every
+//     thread folds the 8 partials itself.  Only when the bound fails are the terms spilled to shared memory and
+//     each chain examined on its own (exact integer value if ITS bound holds, else the ordered float chain);
+//   * the Scharr derivative is never materialised in HBM: the kernel reads only the uint8 pyramids.
 // All float expressions use explicit round-to-nearest intrinsics (no FMA contraction).
 #include <float.h>
 
@@ -25,49 +32,67 @@
 namespace vf {
 
 constexpr int kLkThreads = 256;
+constexpr int kLkWarps = kLkThreads / 32;
 constexpr int kTileI = 24;                   // staged I tile (window + bilinear tap + Scharr ring)
 constexpr int kTileD = 22;                   // derivative tile (window + bilinear tap)
 constexpr int kJMargin = 5;                  // staged J tile = 22x22 taps + this margin on every side
 constexpr int kTileJ = 22 + 2 * kJMargin;    // 32
 constexpr int kTail = 105;                   // 21 rows x 5 tail columns
-constexpr int kChain = 108;                  // every summation chain is padded with zeros to 27 float4
-constexpr int kChainsA = 15;                 // 3 x 4 SIMD-lane accumulators (84 terms) + 3 scalar tails (105 terms)
-constexpr int kChainsB = 10;                 // 8 SIMD-lane accumulators (42 terms) + 2 scalar tails (105 terms)
+constexpr int kSimdB = 42;                   // terms of one SIMD-lane chain of b (21 rows x 2 groups of 8 columns)
+constexpr int kTermsB = 8 * kSimdB + 2 * kTail;   // 546
+constexpr int kExact = 1 << 24;              // below this every integer is a float
 
 struct LevelRef {
     const uint8_t* p;
     int w, h, pitch;
 };
 
+// Per-level geometry of the source window (depends on the source point only).
+struct LevelGeo {
+    int ipx, ipy;            // top-left tap of the window
+    int valid;               // window intersects the padded level (lkpyramid.cpp bounds test)
+    int w00, w01, w10, w11;  // bilinear weights of the source point
+    int pad;
+};
+
+struct LevelPatch {
+    short Iw[kWinPx + 3];            // interpolated I, 2^5 fixed point
+    short2 dI[kWinPx];               // interpolated (Ix, Iy)
+    float A[16];                     // chain values: A11 lanes 0..3, tail | A12 ... | A22 ...  (index m*5 + c)
+};
+
 struct LkSmem {
-    alignas(16) float termsA[kChainsA * kChain];
-    alignas(16) float termsB[kChainsB * kChain];
-    uint8_t tileIs[kMaxLevels][kTileI * kTileI];   // I tiles of every level of the current pass (prefetched together)
-    uint8_t tileJ[kTileJ * kTileJ];
-    short2 dtile[kTileD * kTileD];
-    short Iw[kWinPx + 1];
-    short2 dI[kWinPx];
     LevelRef pyr[2][kMaxLevels];
-    float bcast[4];
+    LevelGeo geo[kMaxLevels];
+    LevelPatch patch[kMaxLevels];
+    alignas(16) uint8_t tileI[kMaxLevels][kTileI * kTileI];
+    alignas(16) short2 dtile[kMaxLevels][kTileD * kTileD];
+    alignas(16) uint8_t tileJ[kTileJ * kTileJ];
+    alignas(16) int4 part[2][kLkWarps];   // per-warp (sum tx, sum ty, sum |t|) of an iteration, double-buffered
+    alignas(16) int termsB[kTermsB + 2];  // terms of b, spilled only when the global exactness bound fails
+    float chainB[12];
     int found[2];
-    int part[8][10];     // per-warp exact integer partial sums of the 10 chains of b
-    int bound[8];        // per-warp sum |term|
-    int fast_iters;      // iterations whose chains were provably exact integers (statistics)
+    int fast_iters;
+#ifdef VF_LK_TIMING
+    unsigned long long tacc[16], tcnt[16];
+    int tbase;
+#endif
 };
 
 #define VF_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
 
-// Optional phase timing (build with -DVF_LK_TIMING): thread 0 of every CTA accumulates clock64() deltas per phase and
-// adds them to vf_lk_timing[k] (cycles) / vf_lk_timing[16 + k] (visits).  Measurement aid only; the marks split lane 0
-// from its warp, which inflates whatever follows a mark until the next reconvergence.
+// Optional phase timing (build with -DVF_LK_TIMING): every thread reads the clock at a mark (no divergence), thread 0
+// accumulates per-phase cycles in shared memory and flushes them to vf_lk_timing[k] / vf_lk_timing[16 + k] at the end.
 #ifdef VF_LK_TIMING
 __device__ unsigned long long vf_lk_timing[32];
 #define LK_T_DECL long long lk_t_last = clock64();
-#define LK_T(k) do { if (threadIdx.x == 0) { const long long t__ = clock64(); atomicAdd(&vf_lk_timing[k], (unsigned long long)(t__ - lk_t_last)); \
-                     atomicAdd(&vf_lk_timing[16 + (k)], 1ull); lk_t_last = t__; } } while (0)
+#define LK_T(k) do { const long long t__ = clock64(); if (threadIdx.x == 0) { sm.tacc[sm.tbase + (k)] += (unsigned long long)(t__ - lk_t_last); sm.tcnt[sm.tbase + (k)] += 1; } \
+                     lk_t_last = t__; } while (0)
+#define LK_T_RESET() do { lk_t_last = clock64(); } while (0)
 #else
 #define LK_T_DECL
 #define LK_T(k) do { } while (0)
+#define LK_T_RESET() do { } while (0)
 #endif
 
 __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
@@ -78,32 +103,8 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
     w11 = 16384 - w00 - w01 - w10;
 }
 
-// Zero the padding slots of the summation chains once per kernel: the terms never overwrite them, and adding +0.0f
-// to a chain value is an exact identity (a chain of integer-valued floats can never be -0.0f).
-__device__ __forceinline__ void lk_smem_init(LkSmem& sm) {
-    for (int i = threadIdx.x; i < kChainsA * kChain; i += kLkThreads) sm.termsA[i] = 0.f;
-    for (int i = threadIdx.x; i < kChainsB * kChain; i += kLkThreads) sm.termsB[i] = 0.f;
-    if (threadIdx.x < 80) (&sm.part[0][0])[threadIdx.x] = 0;
-    if (threadIdx.x == 0) sm.fast_iters = 0;
-}
-
-// Sequential float chain acc = (((0 + t0) + t1) + ...) in the order OpenCV's accumulators see the terms: 27 vector
-// loads, 108 dependent FADDs (the latency floor of one LK iteration).
-// Not inlined: one copy serves A and b, which keeps the per-iteration code inside the instruction cache.
-__device__ __noinline__ float chain_sum(const float* src) {
-    const float4* p = reinterpret_cast<const float4*>(src);
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < kChain / 4; ++i) {
-        const float4 v = p[i];
-        acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
-    }
-    return acc;
-}
-
-// Stage a TS x TS tile of `img` with origin (x0, y0), reflect-101 outside the image.
 // Reflect-101 for tile coordinates: two branch-free folds cover every index within 2n-2 of the image
-// (tiles reach at most 26 pixels outside a level, levels are at least 22 pixels wide).
+// (tiles reach at most 27 pixels outside a level, levels are at least 22 pixels wide).
 __device__ __forceinline__ int refl101_tile(int i, int n) {
     i = i < 0 ? -i : i;
     i = i >= n ? 2 * n - 2 - i : i;
@@ -112,159 +113,227 @@ __device__ __forceinline__ int refl101_tile(int i, int n) {
     return i;
 }
 
-// Stage a TS x TS tile of a level with origin (x0, y0), reflect-101 outside the image.  All loads of a thread are
-// issued before its first store (one memory round trip per tile).  Not inlined (code size, see lk_track_point).
-template <int TS>
-__device__ __noinline__ void stage_tile(uint8_t* tile, const LevelRef& L, int x0, int y0) {
-    constexpr int PER = (TS * TS + kLkThreads - 1) / kLkThreads;
-    uint8_t v[PER];
+// Stage the 32x32 tile of J with origin (x0, y0), reflect-101 outside the image: 4 bytes per thread, all loads
+// before the first store (one memory round trip).
+__device__ __forceinline__ void stage_tile_j(uint8_t* tile, const LevelRef& L, int x0, int y0) {
+    const int tid = threadIdx.x;
+    const int ty = tid >> 3, tx = (tid & 7) * 4;
+    const uint8_t* row = L.p + (size_t)refl101_tile(y0 + ty, L.h) * L.pitch;
+    uint32_t v = 0;
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int i = threadIdx.x + k * kLkThreads;
-        const int ty = i / TS, tx = i - ty * TS;
-        const int gx = refl101_tile(x0 + tx, L.w), gy = refl101_tile(min(y0 + ty, y0 + TS - 1), L.h);
-        v[k] = __ldg(L.p + (size_t)gy * L.pitch + gx);
+    for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + refl101_tile(x0 + tx + k, L.w)) << (8 * k);
+    *reinterpret_cast<uint32_t*>(tile + ty * kTileJ + tx) = v;
+}
+
+struct LkResult {
+    float x, y;
+    int status;
+};
+
+// Warp-level value of one summation chain whose `n` integer terms are produced by term(k), k = 0..n-1 in OpenCV's
+// accumulation order.  Exact integer path when sum|t| < 2^24, else the ordered float chain (all lanes run it
+// redundantly; they are in lock-step anyway).  Terms are |t| < 2^27, n <= 105: no int32 overflow.
+template <typename F>
+__device__ __forceinline__ float chain_value(int n, F term, bool nonneg) {
+    const int lane = threadIdx.x & 31;
+    int s = 0;
+    unsigned int a = 0u;     // sum|t| <= 105 * 2^25 < 2^32: unsigned, so it cannot wrap into a small value
+    for (int k = lane; k < n; k += 32) {
+        const int t = term(k);
+        s += t;
+        a += nonneg ? 0u : (unsigned int)abs(t);
     }
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int i = threadIdx.x + k * kLkThreads;
-        if (i < TS * TS) tile[i] = v[k];
-    }
+    s = __reduce_add_sync(0xffffffffu, s);
+    a = nonneg ? (unsigned int)s : __reduce_add_sync(0xffffffffu, a);
+    if (a < (unsigned int)kExact) return (float)s;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) acc = __fadd_rn(acc, (float)term(k));
+    return acc;
 }
 
 // One calcOpticalFlowPyrLK for one point, executed cooperatively by the CTA (all threads pass identical
 // arguments and return identical results).  ia / ja select the source and target pyramids in sm.pyr.
-// Not inlined: the forward and the reverse pass of a kernel share one copy of this code (the kernel is latency-bound with
-// one CTA per SM, so instruction-cache misses are fully exposed; the body must stay well under the 32 KB L1.5 I-cache).
-__device__ __noinline__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init,
-                                            int max_level, float2& out_pt, int& out_status, int& iters) {
-    const int tid = threadIdx.x;
+// Not inlined: the two passes of a kernel share one copy of this code.
+__device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init,
+                                                int max_level, int* iters_io) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (1 << 20);
-    int status = 1;
+    const int nlv = max_level + 1;
+    int status = 1, iters = 0, fast = 0;
     float outx = init_pt.x, outy = init_pt.y;
     LK_T_DECL
 
-    // The I tiles depend on prev_pt only: fetch them for every level of this pass now, in one burst of loads.
+    // ================= prologue: everything that depends on the source point only, all levels at once =================
     __syncthreads();   // the previous pass may still be reading the shared buffers
-#pragma unroll 1
-    for (int level = max_level; level >= 0; --level) {
+    if (tid < nlv) {
+        const int level = tid;
         const LevelRef LI = sm.pyr[ia][level];
         const float scale = 1.f / (float)(1 << level);
-        const int ipx = __float2int_rd(__fsub_rn(__fmul_rn(prev_pt.x, scale), half));
-        const int ipy = __float2int_rd(__fsub_rn(__fmul_rn(prev_pt.y, scale), half));
-        if (ipx < -kWin || ipx >= LI.w || ipy < -kWin || ipy >= LI.h) continue;
-        stage_tile<kTileI>(sm.tileIs[level], LI, ipx - 1, ipy - 1);
+        const float ppx = __fsub_rn(__fmul_rn(prev_pt.x, scale), half), ppy = __fsub_rn(__fmul_rn(prev_pt.y, scale), half);
+        LevelGeo g;
+        g.ipx = __float2int_rd(ppx); g.ipy = __float2int_rd(ppy);
+        g.valid = !(g.ipx < -kWin || g.ipx >= LI.w || g.ipy < -kWin || g.ipy >= LI.h);
+        bilinear_weights(__fsub_rn(ppx, (float)g.ipx), __fsub_rn(ppy, (float)g.ipy), g.w00, g.w01, g.w10, g.w11);
+        g.pad = 0;
+        sm.geo[level] = g;
     }
-    LK_T(7);
+    // the J tile of the top level only depends on the start point: fetch it together with the I tiles
+    int jx0, jy0;
+    {
+        const float scale = 1.f / (float)(1 << max_level);
+        const float sx = use_init ? init_pt.x : prev_pt.x, sy = use_init ? init_pt.y : prev_pt.y;
+        jx0 = __float2int_rd(__fsub_rn(__fmul_rn(sx, scale), half)) - kJMargin;
+        jy0 = __float2int_rd(__fsub_rn(__fmul_rn(sy, scale), half)) - kJMargin;
+    }
+    __syncthreads();
+    // ---- P1: 24x24 tiles of I on every level (9 bytes per thread for 4 levels), all loads before the first store ----
+    {
+        constexpr int PER = (kMaxLevels * kTileI * kTileI + kLkThreads - 1) / kLkThreads;   // 18
+        const int total = nlv * kTileI * kTileI;
+        uint8_t v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * kLkThreads;
+            v[k] = 0;
+            if (i < total) {
+                const int level = i / (kTileI * kTileI), e = i - level * (kTileI * kTileI);
+                const int ty = e / kTileI, tx = e - ty * kTileI;
+                const LevelRef LI = sm.pyr[ia][level];
+                const LevelGeo& g = sm.geo[level];
+                if (g.valid)
+                    v[k] = __ldg(LI.p + (size_t)refl101_tile(g.ipy - 1 + ty, LI.h) * LI.pitch + refl101_tile(g.ipx - 1 + tx, LI.w));
+            }
+        }
+        stage_tile_j(sm.tileJ, sm.pyr[ja][max_level], jx0, jy0);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const int i = tid + k * kLkThreads;
+            if (i < total) (&sm.tileI[0][0])[i] = v[k];
+        }
+    }
+    __syncthreads();
+    LK_T(0);
+    // ---- P2: Scharr (Ix,Iy) on the 22x22 tap positions of every level; zero outside the image ----
+    for (int i = tid; i < nlv * (kTileD * kTileD); i += kLkThreads) {
+        const int level = i / (kTileD * kTileD), e = i - level * (kTileD * kTileD);
+        const int ty = e / kTileD, tx = e - ty * kTileD;
+        const LevelGeo& g = sm.geo[level];
+        const int x = g.ipx + tx, y = g.ipy + ty;
+        short2 d = make_short2(0, 0);
+        if (x >= 0 && x < sm.pyr[ia][level].w && y >= 0 && y < sm.pyr[ia][level].h) {
+            const uint8_t* p = &sm.tileI[level][(ty + 1) * kTileI + (tx + 1)];
+            const int a00 = p[-kTileI - 1], a01 = p[-kTileI], a02 = p[-kTileI + 1];
+            const int a10 = p[-1], a12 = p[1];
+            const int a20 = p[kTileI - 1], a21 = p[kTileI], a22 = p[kTileI + 1];
+            const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
+            const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
+            d = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
+        }
+        sm.dtile[level][e] = d;
+    }
+    __syncthreads();
+    LK_T(1);
+    // ---- P3: 21x21 bilinear patches (I in 2^5, derivatives in Scharr units) of every level ----
+    for (int i = tid; i < nlv * kWinPx; i += kLkThreads) {
+        const int level = i / kWinPx, e = i - level * kWinPx;
+        const int y = e / kWin, x = e - y * kWin;
+        const LevelGeo& g = sm.geo[level];
+        const int w00 = g.w00, w01 = g.w01, w10 = g.w10, w11 = g.w11;
+        const uint8_t* s = &sm.tileI[level][(y + 1) * kTileI + (x + 1)];
+        const int ival = VF_DESCALE(s[0] * w00 + s[1] * w01 + s[kTileI] * w10 + s[kTileI + 1] * w11, 9);
+        const short2* dt = &sm.dtile[level][y * kTileD + x];
+        const short2 d00 = dt[0], d01 = dt[1], d10 = dt[kTileD], d11 = dt[kTileD + 1];
+        const int ixval = VF_DESCALE(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14);
+        const int iyval = VF_DESCALE(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14);
+        sm.patch[level].Iw[e] = (short)ival;
+        sm.patch[level].dI[e] = make_short2((short)ixval, (short)iyval);
+    }
+    __syncthreads();
+    LK_T(2);
+    // ---- P4: the 15 summation chains of A on every level; unit = (level, SIMD lane class c = 0..3 | tail c = 4) ----
+    for (int u = wid; u < nlv * 5; u += kLkWarps) {
+        const int level = u / 5, c = u - level * 5;
+        const short2* dI = sm.patch[level].dI;
+        float* A = sm.patch[level].A;
+        // OpenCV's order: lane c sees columns c, 4+c, 8+c, 12+c of every row in turn; the tail sees columns 16..20
+        auto at = [&](int k) -> short2 {
+            return c < 4 ? dI[(k >> 2) * kWin + 4 * (k & 3) + c] : dI[(k / 5) * kWin + 16 + (k - (k / 5) * 5)];
+        };
+        const int n = c < 4 ? 84 : kTail;
+        const float a11 = chain_value(n, [&](int k) { const short2 d = at(k); return (int)d.x * d.x; }, true);
+        const float a12 = chain_value(n, [&](int k) { const short2 d = at(k); return (int)d.x * d.y; }, false);
+        const float a22 = chain_value(n, [&](int k) { const short2 d = at(k); return (int)d.y * d.y; }, true);
+        if (lane == 0) { A[c] = a11; A[5 + c] = a12; A[10 + c] = a22; }
+    }
+    __syncthreads();
+    LK_T(3);
+
+    // ================= level loop: J tile + iterations =================
+    // the two pixels this thread owns in every iteration: threads 0..167 take the 168 column pairs (c, c+4) of the two
+    // 8-wide SIMD groups of every row (pmaddwd pair sums), threads 192..244 take 53 pairs of consecutive tail pixels.
+    int e0 = -1, e1 = -1;
+    if (tid < 168) {
+        const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3;
+        e0 = y * kWin + 8 * g + c; e1 = e0 + 4;
+    } else if (tid >= 192 && tid < 192 + 53) {
+        const int t = 2 * (tid - 192);
+        e0 = (t / 5) * kWin + 16 + (t - (t / 5) * 5);
+        if (t + 1 < kTail) e1 = ((t + 1) / 5) * kWin + 16 + ((t + 1) - ((t + 1) / 5) * 5);
+    }
+    const int o0 = e0 < 0 ? 0 : (e0 / kWin) * kTileJ + (e0 - (e0 / kWin) * kWin);
+    const int o1 = e1 < 0 ? 0 : (e1 / kWin) * kTileJ + (e1 - (e1 / kWin) * kWin);
+    bool tile_ready = true;      // the top level's J tile was staged by the prologue
+    int pbuf = 0;
 
 #pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
-        const LevelRef LI = sm.pyr[ia][level], LJ = sm.pyr[ja][level];
-        const int cols = LI.w, rows = LI.h, jcols = LJ.w, jrows = LJ.h;
+        const LevelRef LJ = sm.pyr[ja][level];
+        const int jcols = LJ.w, jrows = LJ.h;
         const float scale = 1.f / (float)(1 << level);
-        float ppx = __fmul_rn(prev_pt.x, scale), ppy = __fmul_rn(prev_pt.y, scale);
         float nx, ny;
         if (level == max_level) {
             if (use_init) { nx = __fmul_rn(outx, scale); ny = __fmul_rn(outy, scale); }
-            else { nx = ppx; ny = ppy; }
+            else { nx = __fmul_rn(prev_pt.x, scale); ny = __fmul_rn(prev_pt.y, scale); }
         } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
         outx = nx; outy = ny;
-
-        ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
-        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
-        if (ipx < -kWin || ipx >= cols || ipy < -kWin || ipy >= rows) {
+        const LevelGeo& geo = sm.geo[level];
+        if (!geo.valid) {
             if (level == 0) status = 0;
+            tile_ready = false;
             continue;
         }
-        int w00, w01, w10, w11;
-        bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
-
-        // ---- stage a 32x32 tile of J around the start of the search (the 24x24 tile of I is already resident) ----
-        int jx0 = __float2int_rd(__fsub_rn(nx, half)) - kJMargin, jy0 = __float2int_rd(__fsub_rn(ny, half)) - kJMargin;
-        const uint8_t* tileI = sm.tileIs[level];
-        __syncthreads();   // the previous level may still be reading tileJ / the patch buffers
-        stage_tile<kTileJ>(sm.tileJ, LJ, jx0, jy0);
-        __syncthreads();
-        LK_T(0);
-        // ---- Scharr (Ix,Iy) on the 22x22 tap positions; zero outside the image ----
-#pragma unroll 1
-        for (int i = tid; i < kTileD * kTileD; i += kLkThreads) {
-            const int ty = i / kTileD, tx = i - ty * kTileD;
-            const int x = ipx + tx, y = ipy + ty;
-            short2 d = make_short2(0, 0);
-            if (x >= 0 && x < cols && y >= 0 && y < rows) {
-                const uint8_t* p = &tileI[(ty + 1) * kTileI + (tx + 1)];
-                const int a00 = p[-kTileI - 1], a01 = p[-kTileI], a02 = p[-kTileI + 1];
-                const int a10 = p[-1], a12 = p[1];
-                const int a20 = p[kTileI - 1], a21 = p[kTileI], a22 = p[kTileI + 1];
-                const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
-                const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
-                d = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
-            }
-            sm.dtile[i] = d;
-        }
-        __syncthreads();
-        LK_T(1);
-        // ---- 21x21 bilinear patch (I in 2^5, derivatives in Scharr units) + terms of A ----
-#pragma unroll 1
-        for (int i = tid; i < kWinPx; i += kLkThreads) {
-            const int y = i / kWin, x = i - y * kWin;
-            const uint8_t* s = &tileI[(y + 1) * kTileI + (x + 1)];
-            const int ival = VF_DESCALE(s[0] * w00 + s[1] * w01 + s[kTileI] * w10 + s[kTileI + 1] * w11, 9);
-            const short2 d00 = sm.dtile[y * kTileD + x], d01 = sm.dtile[y * kTileD + x + 1];
-            const short2 d10 = sm.dtile[(y + 1) * kTileD + x], d11 = sm.dtile[(y + 1) * kTileD + x + 1];
-            const int ixval = VF_DESCALE(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14);
-            const int iyval = VF_DESCALE(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14);
-            sm.Iw[i] = (short)ival;
-            sm.dI[i] = make_short2((short)ixval, (short)iyval);
-            const float fx = (float)ixval, fy = (float)iyval;   // products are < 2^24: exact in float
-            const float t11 = __fmul_rn(fx, fx), t12 = __fmul_rn(fx, fy), t22 = __fmul_rn(fy, fy);
-            if (x < 16) {   // SIMD lane l = x & 3 sees columns l, 4+l, 8+l, 12+l of every row in turn
-                const int l = x & 3, slot = y * 4 + (x >> 2);
-                sm.termsA[(0 + l) * kChain + slot] = t11;
-                sm.termsA[(4 + l) * kChain + slot] = t12;
-                sm.termsA[(8 + l) * kChain + slot] = t22;
-            } else {        // scalar tail: columns 16..20 of every row in turn
-                const int slot = y * 5 + (x - 16);
-                sm.termsA[12 * kChain + slot] = t11;
-                sm.termsA[13 * kChain + slot] = t12;
-                sm.termsA[14 * kChain + slot] = t22;
-            }
-        }
-        __syncthreads();
-        LK_T(2);
-        if (tid < 32) {
-            const int lane = tid;
-            // Converge the warp before the chain and before the shuffles: a warp that arrives split (e.g. lane 0 after the
-            // timing marks) would run the chain once per group and take the WARPSYNC.COLLECTIVE path on every shuffle.
-            __syncwarp();
-            const float acc = chain_sum(&sm.termsA[min(lane, kChainsA - 1) * kChain]);
-            __syncwarp();
-            float r[3];
+        const float* Ac = sm.patch[level].A;
+        float r[3];
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const float q0 = __shfl_sync(0xffffffffu, acc, m * 4 + 0), q1 = __shfl_sync(0xffffffffu, acc, m * 4 + 1);
-                const float q2 = __shfl_sync(0xffffffffu, acc, m * 4 + 2), q3 = __shfl_sync(0xffffffffu, acc, m * 4 + 3);
-                const float tail = __shfl_sync(0xffffffffu, acc, 12 + m);
-                r[m] = __fadd_rn(tail, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));   // iA += v_reduce_sum(qA)
-            }
-            if (lane == 0) { sm.bcast[0] = r[0]; sm.bcast[1] = r[1]; sm.bcast[2] = r[2]; }
-        }
-        __syncthreads();
-        LK_T(3);
-        const float A11 = __fmul_rn(sm.bcast[0], FLT_SCALE), A12 = __fmul_rn(sm.bcast[1], FLT_SCALE),
-                    A22 = __fmul_rn(sm.bcast[2], FLT_SCALE);
+        for (int m = 0; m < 3; ++m)   // iA += v_reduce_sum(qA): tail + ((q0 + q2) + (q1 + q3))
+            r[m] = __fadd_rn(Ac[5 * m + 4], __fadd_rn(__fadd_rn(Ac[5 * m + 0], Ac[5 * m + 2]), __fadd_rn(Ac[5 * m + 1], Ac[5 * m + 3])));
+        const float A11 = __fmul_rn(r[0], FLT_SCALE), A12 = __fmul_rn(r[1], FLT_SCALE), A22 = __fmul_rn(r[2], FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
         const float dA = __fsub_rn(A11, A22);
         const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
         const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * kWin * kWin));
         if (minEig < 1e-4f || D < FLT_EPSILON) {
             if (level == 0) status = 0;
+            tile_ready = false;
             continue;
         }
         D = __fdiv_rn(1.f, D);
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
+        // this thread's two source pixels stay in registers for the whole level
+        const short* Iw = sm.patch[level].Iw;
+        const short2* dI = sm.patch[level].dI;
+        const int I0 = e0 >= 0 ? Iw[e0] : 0, I1 = e1 >= 0 ? Iw[e1] : 0;
+        const short2 g0 = e0 >= 0 ? dI[e0] : make_short2(0, 0), g1 = e1 >= 0 ? dI[e1] : make_short2(0, 0);
+        if (!tile_ready) {
+            jx0 = __float2int_rd(nx) - kJMargin; jy0 = __float2int_rd(ny) - kJMargin;
+            __syncthreads();   // the previous level may still be reading tileJ
+            stage_tile_j(sm.tileJ, LJ, jx0, jy0);
+            __syncthreads();
+        }
+        tile_ready = false;
+        LK_T(4);
         float pdx = 0.f, pdy = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 30; ++j) {
@@ -278,99 +347,66 @@ __device__ __noinline__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 p
                 // the window left the staged tile: re-centre it (uniform branch)
                 jx0 = inx - kJMargin; jy0 = iny - kJMargin;
                 __syncthreads();
-                stage_tile<kTileJ>(sm.tileJ, LJ, jx0, jy0);
+                stage_tile_j(sm.tileJ, LJ, jx0, jy0);
                 __syncthreads();
             }
+            int w00, w01, w10, w11;
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            LK_T(4);
             const uint8_t* jt = &sm.tileJ[(iny - jy0) * kTileJ + (inx - jx0)];
-            auto jdiff = [&](int y, int x) -> int {
-                const uint8_t* p = jt + y * kTileJ + x;
-                const int v = p[0] * w00 + p[1] * w01 + p[kTileJ] * w10 + p[kTileJ + 1] * w11;
-                return VF_DESCALE(v, 9) - (int)sm.Iw[y * kWin + x];
-            };
-            // terms of b, one work item per thread: threads 0..167 take the 168 column pairs (c, c+4) of the two 8-wide
-            // SIMD groups of every row (pmaddwd pair sums), threads 192..244 take 53 pairs of tail pixels (columns 16..20).
-            // Besides the float terms of the ordered chains, every chain is also summed as an exact integer together with
-            // a bound on sum|term|: when the bound is below 2^24 every partial sum of every float chain is an exactly
-            // representable integer, the order of the additions cannot matter, and the chain value IS the integer sum --
-            // the 105-deep dependent FADD chain is skipped (bit-identical result).
-            int tx = 0, ty = 0, ab = 0;
-            if (tid < 168) {
-                const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3;
-                const int xa = 8 * g + c, xb = xa + 4;
-                const int da = jdiff(y, xa), db = jdiff(y, xb);
-                const short2 pa = sm.dI[y * kWin + xa], pb = sm.dI[y * kWin + xb];
-                const int slot = y * 2 + g;
-                tx = da * pa.x + db * pb.x; ty = da * pa.y + db * pb.y;             // exact int32 pair sums
-                ab = abs(tx) + abs(ty);
-                sm.termsB[(2 * c + 0) * kChain + slot] = (float)tx;
-                sm.termsB[(2 * c + 1) * kChain + slot] = (float)ty;
-            } else if (tid >= 192 && tid < 192 + 53) {
-#pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
-                    const int t = 2 * (tid - 192) + h2;
-                    if (t < kTail) {
-                        const int y = t / 5, x = 16 + (t - y * 5);
-                        const int d = jdiff(y, x);
-                        const short2 pd = sm.dI[y * kWin + x];
-                        const int ex = d * pd.x, ey = d * pd.y;
-                        tx += ex; ty += ey; ab += abs(ex) + abs(ey);
-                        sm.termsB[8 * kChain + t] = (float)ex;
-                        sm.termsB[9 * kChain + t] = (float)ey;
-                    }
-                }
-            }
-            {
-                const int wid = tid >> 5, lane = tid & 31;
-                ab = __reduce_add_sync(0xffffffffu, ab);
-                if (wid < 6) {          // pair warps: lanes with equal (lane & 3) feed the same two chains
-#pragma unroll
-                    for (int o = 4; o < 32; o <<= 1) {
-                        tx += __shfl_xor_sync(0xffffffffu, tx, o);
-                        ty += __shfl_xor_sync(0xffffffffu, ty, o);
-                    }
-                    if (lane < 4) { sm.part[wid][2 * lane] = tx; sm.part[wid][2 * lane + 1] = ty; }
-                } else {                // tail warps
-                    tx = __reduce_add_sync(0xffffffffu, tx);
-                    ty = __reduce_add_sync(0xffffffffu, ty);
-                    if (lane == 0) { sm.part[wid][8] = tx; sm.part[wid][9] = ty; }
-                }
-                if (lane == 0) sm.bound[wid] = ab;
-            }
+            const uint8_t* p0 = jt + o0;
+            const uint8_t* p1 = jt + o1;
+            const int d0 = VF_DESCALE(p0[0] * w00 + p0[1] * w01 + p0[kTileJ] * w10 + p0[kTileJ + 1] * w11, 9) - I0;
+            const int d1 = VF_DESCALE(p1[0] * w00 + p1[1] * w01 + p1[kTileJ] * w10 + p1[kTileJ + 1] * w11, 9) - I1;
+            // exact int32 products; pair threads form OpenCV's pmaddwd pair sums, tail threads keep single terms
+            const int ex0 = e0 >= 0 ? d0 * g0.x : 0, ey0 = e0 >= 0 ? d0 * g0.y : 0;
+            const int ex1 = e1 >= 0 ? d1 * g1.x : 0, ey1 = e1 >= 0 ? d1 * g1.y : 0;
+            const int tx = ex0 + ex1, ty = ey0 + ey1;
+            // clamped so that the sum over the 221 contributing threads stays below 2^32 (compared unsigned)
+            const int ab = min(tid < 168 ? abs(tx) + abs(ty) : abs(ex0) + abs(ey0) + abs(ex1) + abs(ey1), kExact);
+            const int sx = __reduce_add_sync(0xffffffffu, tx);
+            const int sy = __reduce_add_sync(0xffffffffu, ty);
+            const int sa = (int)__reduce_add_sync(0xffffffffu, (unsigned int)ab);
+            if (lane == 0) sm.part[pbuf][wid] = make_int4(sx, sy, sa, 0);
             __syncthreads();
-            LK_T(5);
-            if (tid < 32) {
-                const int lane = tid;
-                __syncwarp();
-                int isum = 0, bnd = 0;
-                if (lane < 8) {
+            int bx = 0, by = 0;
+            unsigned int bnd = 0u;
 #pragma unroll
-                    for (int w = 0; w < 6; ++w) isum += sm.part[w][lane];
-                } else if (lane < 10) {
-                    isum = sm.part[6][lane] + sm.part[7][lane];
+            for (int w = 0; w < kLkWarps; ++w) {
+                const int4 q = sm.part[pbuf][w];
+                bx += q.x; by += q.y; bnd += (unsigned int)q.z;
+            }
+            pbuf ^= 1;
+            float ib1, ib2;
+            if (bnd < (unsigned int)kExact) {
+                // every partial sum of every chain and of their combination is an exactly representable integer
+                ib1 = (float)bx; ib2 = (float)by;
+                ++fast;
+            } else {
+                // spill the terms; examine each of the 10 chains on its own
+                if (tid < 168) {
+                    const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3, slot = y * 2 + g;
+                    sm.termsB[(2 * c + 0) * kSimdB + slot] = tx;
+                    sm.termsB[(2 * c + 1) * kSimdB + slot] = ty;
+                } else if (tid >= 192 && tid < 192 + 53) {
+                    const int t = 2 * (tid - 192);
+                    sm.termsB[8 * kSimdB + t] = ex0; sm.termsB[8 * kSimdB + kTail + t] = ey0;
+                    if (t + 1 < kTail) { sm.termsB[8 * kSimdB + t + 1] = ex1; sm.termsB[8 * kSimdB + kTail + t + 1] = ey1; }
                 }
-#pragma unroll
-                for (int w = 0; w < 8; ++w) bnd += sm.bound[w];
-                float acc;
-                if (bnd < (1 << 24)) acc = (float)isum;                                   // exact: order-independent
-                else acc = chain_sum(&sm.termsB[min(lane, kChainsB - 1) * kChain]);       // OpenCV's summation order
-                __syncwarp();
-                float k[10];
-#pragma unroll
-                for (int q = 0; q < 10; ++q) k[q] = __shfl_sync(0xffffffffu, acc, q);
+                __syncthreads();
+                for (int ch = wid; ch < 10; ch += kLkWarps) {
+                    const int* src = ch < 8 ? &sm.termsB[ch * kSimdB] : &sm.termsB[8 * kSimdB + (ch - 8) * kTail];
+                    const float v = chain_value(ch < 8 ? kSimdB : kTail, [&](int k) { return src[k]; }, false);
+                    if (lane == 0) sm.chainB[ch] = v;
+                }
+                __syncthreads();
+                const float* k = sm.chainB;
                 // qb0+qb1 -> (s0,s1,s2,s3); ib1 += (s0+0)+(s2+0); ib2 += (s1+0)+(s3+0)
                 const float s0 = __fadd_rn(k[0], k[4]), s1 = __fadd_rn(k[1], k[5]);
                 const float s2 = __fadd_rn(k[2], k[6]), s3 = __fadd_rn(k[3], k[7]);
-                if (lane == 0) {
-                    sm.bcast[0] = __fadd_rn(k[8], __fadd_rn(s0, s2));
-                    sm.bcast[1] = __fadd_rn(k[9], __fadd_rn(s1, s3));
-                    if (bnd < (1 << 24)) ++sm.fast_iters;
-                }
+                ib1 = __fadd_rn(k[8], __fadd_rn(s0, s2));
+                ib2 = __fadd_rn(k[9], __fadd_rn(s1, s3));
             }
-            __syncthreads();
-            LK_T(6);
-            const float b1 = __fmul_rn(sm.bcast[0], FLT_SCALE), b2 = __fmul_rn(sm.bcast[1], FLT_SCALE);
+            const float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
@@ -383,13 +419,19 @@ __device__ __noinline__ void lk_track_point(LkSmem& sm, int ia, int ja, float2 p
             }
             pdx = dx; pdy = dy;
         }
+        LK_T(5);
         if (status && level == 0) {   // the caller passes an err vector: final window test (lkpyramid.cpp)
             const int ix = __float2int_rd(__fsub_rn(outx, half)), iy = __float2int_rd(__fsub_rn(outy, half));
             if (ix < -kWin || ix >= jcols || iy < -kWin || iy >= jrows) status = 0;
         }
     }
-    out_pt = make_float2(outx, outy);
-    out_status = status;
+    if (tid == 0) {
+        iters_io[0] += iters;
+        iters_io[1] += fast;
+    }
+    LkResult res;
+    res.x = outx; res.y = outy; res.status = status;
+    return res;
 }
 
 // Fill sm.pyr[slot] with stream s of a pyramid (threads 0..kMaxLevels-1 of the given quarter).
@@ -404,6 +446,27 @@ __device__ __forceinline__ void load_pyr(LkSmem& sm, int slot, const PyrView& pv
     }
 }
 
+__device__ __forceinline__ void lk_smem_init(LkSmem& sm, int* counters2) {
+    if (threadIdx.x == 0) { counters2[0] = 0; counters2[1] = 0; }
+#ifdef VF_LK_TIMING
+    if (threadIdx.x < 16) { sm.tacc[threadIdx.x] = 0; sm.tcnt[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) sm.tbase = 0;
+#endif
+    (void)sm;
+}
+
+__device__ __forceinline__ void lk_timing_flush(LkSmem& sm) {
+#ifdef VF_LK_TIMING
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        atomicAdd(&vf_lk_timing[threadIdx.x], sm.tacc[threadIdx.x]);
+        atomicAdd(&vf_lk_timing[16 + threadIdx.x], sm.tcnt[threadIdx.x]);
+    }
+#else
+    (void)sm;
+#endif
+}
+
 __device__ __forceinline__ bool in_border(float2 p, int rows, int cols) {   // feature_tracker.cpp:20-25
     const int x = __float2int_rn(p.x), y = __float2int_rn(p.y);
     return 1 <= x && x < cols - 1 && 1 <= y && y < rows - 1;
@@ -413,37 +476,59 @@ __device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // f
     return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
+extern __shared__ __align__(16) unsigned char lk_smem_raw[];
+
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
 __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch* __restrict__ bp, int parity) {
-    __shared__ LkSmem sm;
+    LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
+    __shared__ int stat[2];
     const DevBatch& b = *bp;
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
     if (i >= n_prev) return;
-    lk_smem_init(sm);
+    lk_smem_init(sm, stat);
     load_pyr(sm, 0, b.left[parity ^ 1], b.lvl_stream_stride, s);   // 0 = previous left
     load_pyr(sm, 1, b.left[parity], b.lvl_stream_stride, s);       // 1 = current left
     __syncthreads();
     const float2 p0 = b.kps[parity ^ 1][(size_t)s * cap + i];
-    float2 fwd, rev = p0;
-    int st = 0, rst = 0, iters = 0;
     const int L = min(b.lk_max_level, b.left[parity].n_levels - 1);
-    lk_track_point(sm, 0, 1, p0, p0, false, L, fwd, st, iters);
+#ifdef VF_LK_TIMING_REPEAT
+    {   // cold-vs-warm experiment: the same forward pass twice, the second one is accounted under phases 8..13
+        lk_track_point(sm, 0, 1, p0, p0, false, L, stat);
+        __syncthreads();
+        if (threadIdx.x == 0) { sm.tbase = 8; stat[0] = 0; stat[1] = 0; }
+        __syncthreads();
+    }
+#endif
+    const LkResult f = lk_track_point(sm, 0, 1, p0, p0, false, L, stat);
+#ifdef VF_LK_TIMING_REPEAT
+    __syncthreads();
+    if (threadIdx.x == 0) sm.tbase = 0;
+    __syncthreads();
+#endif
+    const float2 fwd = make_float2(f.x, f.y);
+    float2 rev = p0;
+    int st = f.status, rst = 0;
     int ok = st;
     if (b.flow_back) {
         // the reference also runs the reverse pass on points whose forward status is already 0 and then
         // discards the result (:55-59); the device skips that work, the outcome is the same.
-        if (st) lk_track_point(sm, 1, 0, fwd, p0, true, min(1, L), rev, rst, iters);
+        if (st) {
+            const LkResult r = lk_track_point(sm, 1, 0, fwd, p0, true, min(1, L), stat);
+            rev = make_float2(r.x, r.y); rst = r.status;
+        }
         ok = st && rst && pt_distance(p0, rev) <= 0.5;
     }
     if (ok && !in_border(fwd, b.H, b.W)) ok = 0;
+    __syncthreads();
     if (threadIdx.x == 0) {
         const size_t o = (size_t)s * cap + i;
         b.fwd_pts[o] = fwd; b.fwd_st[o] = (uint8_t)st;
         b.rev_pts[o] = rev; b.rev_st[o] = (uint8_t)rst;
         b.temporal_st[o] = (uint8_t)ok;
-        b.lk_iters[o] = iters | (sm.fast_iters << 16);   // low 16 bits: iterations, high: of which on the exact-integer path
+        b.lk_iters[o] = stat[0] | (stat[1] << 16);   // low 16 bits: iterations, high: of which on the exact-integer path
     }
+    lk_timing_flush(sm);
 }
 
 // velocity of ComputeKpsVelocity (:323-363): (cur - prev) as float, / dt as double, stored as float.
@@ -452,83 +537,114 @@ __device__ __forceinline__ float2 velocity(float2 cur, float2 prev, double dt) {
 }
 
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
-//      RemoveDistortion + ComputeKpsVelocity for both cameras and the packed featureFrame record ----
+//      RemoveDistortion + ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
 __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* __restrict__ bp, int parity) {
-    __shared__ LkSmem sm;
+    LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
+    __shared__ int stat[2];
     const DevBatch& b = *bp;
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
     const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
     if (i >= n) return;
     const size_t o = (size_t)s * cap + i;
-    lk_smem_init(sm);
+    lk_smem_init(sm, stat);
     load_pyr(sm, 0, b.left[parity], b.lvl_stream_stride, s);   // 0 = current left
     load_pyr(sm, 1, b.right, b.lvl_stream_stride, s);          // 1 = current right
+    if (tid == 0) sm.found[1] = -1;
     __syncthreads();
     const float2 p0 = b.kps[parity][o];
     const int id = b.ids[parity][o];
-    float2 rp, back = p0;
-    int st = 0, rst = 0, iters = 0;
+    // id lookup in the previous frame's right map (previous_right_un_distortion_ids_kps_map_); independent of the LK
+    {
+        const int n_prev = cnt_prev[C_N_TOTAL];
+        const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
+        for (int j = tid; j < n_prev; j += kLkThreads)
+            if (prev_ids[j] == id && b.right_ok[parity ^ 1][(size_t)s * cap + j]) sm.found[1] = j;
+    }
     const int L = min(b.lk_max_level, b.right.n_levels - 1);
-    lk_track_point(sm, 0, 1, p0, p0, false, L, rp, st, iters);
+    const LkResult f = lk_track_point(sm, 0, 1, p0, p0, false, L, stat);
+    const float2 rp = make_float2(f.x, f.y);
+    float2 back = p0;
+    int st = f.status, rst = 0;
     int ok = st;
     if (b.flow_back) {
-        if (st) lk_track_point(sm, 1, 0, rp, rp, false, L, back, rst, iters);
+        if (st) {
+            const LkResult r = lk_track_point(sm, 1, 0, rp, rp, false, L, stat);
+            back = make_float2(r.x, r.y); rst = r.status;
+        }
         ok = st && rst && in_border(rp, b.H, b.W) && pt_distance(p0, back) <= 0.5;
     }
-    // id lookup in the previous frame's maps (previous_left/right_un_distortion_ids_kps_map_)
-    if (tid < 2) sm.found[tid] = -1;
-    __syncthreads();
-    const int n_prev = cnt_prev[C_N_TOTAL];
-    const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
-    for (int j = tid; j < n_prev; j += kLkThreads)
-        if (prev_ids[j] == id) { sm.found[0] = j; if (b.right_ok[parity ^ 1][(size_t)s * cap + j]) sm.found[1] = j; }
     __syncthreads();
     if (tid == 0) {
         const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
-        vf_feature rec;
-        rec.id = id; rec.track_cnt = b.cnt[parity][o]; rec.has_right = ok;
-        const float2 un = undistort_point(b.cam[0], p0);
-        float2 v = make_float2(0.f, 0.f);
-        if (sm.found[0] >= 0) v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + sm.found[0]], dt);
-        rec.x = un.x; rec.y = un.y; rec.u = p0.x; rec.v = p0.y; rec.vx = v.x; rec.vy = v.y;
-        rec.xr = rec.yr = rec.ur = rec.vr = rec.vxr = rec.vyr = 0.f;
-        float2 unr = make_float2(0.f, 0.f);
+        vf_feature* rec = &b.out[o];
+        rec->has_right = ok;
+        float2 unr = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
         if (ok) {
             unr = undistort_point(b.cam[1], rp);
-            float2 vr = make_float2(0.f, 0.f);
             if (sm.found[1] >= 0) vr = velocity(unr, b.un_right[parity ^ 1][(size_t)s * cap + sm.found[1]], dt);
-            rec.xr = unr.x; rec.yr = unr.y; rec.ur = rp.x; rec.vr = rp.y; rec.vxr = vr.x; rec.vyr = vr.y;
         }
-        b.out[o] = rec;
-        b.un_left[parity][o] = un;
+        rec->xr = unr.x; rec->yr = unr.y; rec->ur = ok ? rp.x : 0.f; rec->vr = ok ? rp.y : 0.f; rec->vxr = vr.x; rec->vyr = vr.y;
         b.un_right[parity][o] = unr;
         b.right_ok[parity][o] = (uint8_t)ok;
         b.lr_pts[o] = rp; b.lr_st[o] = (uint8_t)st; b.rl_pts[o] = back; b.rl_st[o] = (uint8_t)rst;
-        b.lk_iters_stereo[o] = iters | (sm.fast_iters << 16);
+        b.lk_iters_stereo[o] = stat[0] | (stat[1] << 16);
         if (ok) atomicAdd(&b.counters[parity][s * C_COUNT + C_N_RIGHT], 1);
     }
+    lk_timing_flush(sm);
+}
+
+// ---- left camera: RemoveDistortion + ComputeKpsVelocity (:103-104, :310-363) and the left half of the record.
+//      Depends on current_kps_ / ids_ only, so it runs beside the stereo LK on the side stream. ----
+__global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity) {
+    const DevBatch& b = *bp;
+    const int s = blockIdx.y, cap = b.cap;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
+    if (i >= n) return;
+    const size_t o = (size_t)s * cap + i;
+    const float2 p0 = b.kps[parity][o];
+    const int id = b.ids[parity][o];
+    const float2 un = undistort_point(b.cam[0], p0);
+    // previous_left_un_distortion_ids_kps_map_.find(id): tracked features keep their relative order, so the match is
+    // found among the previous frame's ids by a short scan
+    const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
+    const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
+    int found = -1;
+    if (b.cnt[parity][o] > 1)
+        for (int j = 0; j < n_prev; ++j)
+            if (prev_ids[j] == id) { found = j; break; }
+    float2 v = make_float2(0.f, 0.f);
+    if (found >= 0) {
+        const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
+        v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + found], dt);
+    }
+    vf_feature* rec = &b.out[o];
+    rec->id = id; rec->track_cnt = b.cnt[parity][o];
+    rec->x = un.x; rec->y = un.y; rec->u = p0.x; rec->v = p0.y; rec->vx = v.x; rec->vy = v.y;
+    b.un_left[parity][o] = un;
 }
 
 // ---- stand-alone calcOpticalFlowPyrLK (vf_op_lk) ----
 __global__ void __launch_bounds__(kLkThreads) lk_op_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts,
                                                            float2* __restrict__ next_pts, uint8_t* __restrict__ status,
                                                            int* __restrict__ iters_out, int n, int max_level, int use_init) {
-    __shared__ LkSmem sm;
+    LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
+    __shared__ int stat[2];
     const int i = blockIdx.x;
     if (i >= n) return;
-    lk_smem_init(sm);
+    lk_smem_init(sm, stat);
     load_pyr(sm, 0, prev, nullptr, 0);
     load_pyr(sm, 1, next, nullptr, 0);
     __syncthreads();
-    float2 out;
-    int st = 0, iters = 0;
     const int L = min(max_level, min(prev.n_levels, next.n_levels) - 1);
-    lk_track_point(sm, 0, 1, prev_pts[i], next_pts[i], use_init != 0, L, out, st, iters);
+    const LkResult r = lk_track_point(sm, 0, 1, prev_pts[i], next_pts[i], use_init != 0, L, stat);
+    __syncthreads();
     if (threadIdx.x == 0) {
-        next_pts[i] = out; status[i] = (uint8_t)st;
-        if (iters_out) iters_out[i] = iters;
+        next_pts[i] = make_float2(r.x, r.y); status[i] = (uint8_t)r.status;
+        if (iters_out) iters_out[i] = stat[0];
     }
+    lk_timing_flush(sm);
 }
 
 __global__ void undistort_kernel(CamParams cam, const float2* __restrict__ uv, float2* __restrict__ out, int n) {
@@ -540,27 +656,40 @@ void launch_undistort(const CamParams& cam, const float2* uv, float2* out, int n
     undistort_kernel<<<(n + 127) / 128, 128, 0, stream>>>(cam, uv, out, n);
 }
 
+// The LK kernels keep all per-level state of a pass in (dynamic) shared memory: opt in above 48 KB once per device.
+cudaError_t lk_prepare() {
+    cudaError_t e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
+}
+
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_temporal_kernel<<<grid, kLkThreads, 0, stream>>>(d_batch, parity);
+    lk_temporal_kernel<<<grid, kLkThreads, sizeof(LkSmem), stream>>>(d_batch, parity);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_stereo_kernel<<<grid, kLkThreads, 0, stream>>>(d_batch, parity);
+    lk_stereo_kernel<<<grid, kLkThreads, sizeof(LkSmem), stream>>>(d_batch, parity);
+}
+void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
+    dim3 grid((h.cap + 127) / 128, h.n_streams);
+    undistort_left_kernel<<<grid, 128, 0, stream>>>(d_batch, parity);
 }
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {
     if (n <= 0) return;
-    lk_op_kernel<<<n, kLkThreads, 0, stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow);
+    lk_op_kernel<<<n, kLkThreads, sizeof(LkSmem), stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow);
 }
 
 }  // namespace vf
 
 #ifdef VF_LK_TIMING
 // measurement aid (timing build only): read and clear the per-phase cycle counters
-extern "C" int vf_debug_lk_timing(unsigned long long* out16) {
+extern "C" int vf_debug_lk_timing(unsigned long long* out32) {
     unsigned long long zero[32] = {0};
-    if (cudaMemcpyFromSymbol(out16, vf::vf_lk_timing, sizeof(zero)) != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(out32, vf::vf_lk_timing, sizeof(zero)) != cudaSuccess) return 1;
     return cudaMemcpyToSymbol(vf::vf_lk_timing, zero, sizeof(zero)) != cudaSuccess;
 }
 #endif
