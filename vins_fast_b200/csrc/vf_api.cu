@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -49,7 +50,7 @@ struct vf_batch {
     vf_config cfg;
     int S = 0, device = 0;
     cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr;
-    bool own_main = false;
+    bool own_main = false, serialized = false;
     cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr,
                 ev_sel = nullptr, ev_un = nullptr;
     DevBatch h;               // host copy of the device descriptor
@@ -146,10 +147,12 @@ vf_status alloc_pyramid(vf_batch* b, PyrView& pv, int W, int H, int n_levels, in
     pv.n_levels = n_levels;
     int w = W, h = H;
     for (int l = 0; l < n_levels; ++l) {
-        pv.w[l] = w; pv.h[l] = h; pv.pitch[l] = align_up(w, 16);
-        b->h.lvl_stream_stride[l] = (size_t)pv.pitch[l] * h;
-        vf_status st = dalloc(b, &pv.lvl[l], (size_t)pv.pitch[l] * h * S);
+        pv.w[l] = w; pv.h[l] = h; pv.pitch[l] = align_up(w + 2 * kPyrPad, 16);
+        b->h.lvl_stream_stride[l] = (size_t)pv.pitch[l] * (h + 2 * kPyrPad);
+        uint8_t* base = nullptr;
+        vf_status st = dalloc(b, &base, b->h.lvl_stream_stride[l] * S);
         if (st != VF_OK) return st;
+        pv.lvl[l] = base + (size_t)kPyrPad * pv.pitch[l] + kPyrPad;   // interior origin of stream 0
         w = (w + 1) / 2; h = (h + 1) / 2;
     }
     return VF_OK;
@@ -203,8 +206,8 @@ void destroy_batch(vf_batch* b) {
     if (b->ev_sel) cudaEventDestroy(b->ev_sel);
     if (b->ev_un) cudaEventDestroy(b->ev_un);
     for (int k = 0; k < 16; ++k) { if (b->st_beg[k]) cudaEventDestroy(b->st_beg[k]); if (b->st_end[k]) cudaEventDestroy(b->st_end[k]); }
-    if (b->side_a) cudaStreamDestroy(b->side_a);
-    if (b->side_b) cudaStreamDestroy(b->side_b);
+    if (b->side_a && !b->serialized) cudaStreamDestroy(b->side_a);
+    if (b->side_b && !b->serialized) cudaStreamDestroy(b->side_b);
     if (b->own_main && b->main) cudaStreamDestroy(b->main);
     delete b;
 }
@@ -294,10 +297,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         for (int s = 0; s < S; ++s) {
             const uint8_t* a = base0 ? base0 + (size_t)s * image_stride : img0[s];
             uint8_t* dst = h.left[parity].lvl[0] + (size_t)s * h.lvl_stream_stride[0];
-            if (stride0 == (size_t)h.left[parity].pitch[0])   // contiguous on both sides: one linear DMA
-                VF_CUDA(b, cudaMemcpyAsync(dst, a, stride0 * (size_t)H, kind, b->main));
-            else
-                VF_CUDA(b, cudaMemcpy2DAsync(dst, h.left[parity].pitch[0], a, stride0, W, H, kind, b->main));
+            VF_CUDA(b, cudaMemcpy2DAsync(dst, h.left[parity].pitch[0], a, stride0, W, H, kind, b->main));
         }
     }
     {
@@ -305,10 +305,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         for (int s = 0; s < S; ++s) {
             const uint8_t* c = base1 ? base1 + (size_t)s * image_stride : img1[s];
             uint8_t* dst = h.right.lvl[0] + (size_t)s * h.lvl_stream_stride[0];
-            if (stride1 == (size_t)h.right.pitch[0])
-                VF_CUDA(b, cudaMemcpyAsync(dst, c, stride1 * (size_t)H, kind, b->side_b));
-            else
-                VF_CUDA(b, cudaMemcpy2DAsync(dst, h.right.pitch[0], c, stride1, W, H, kind, b->side_b));
+            VF_CUDA(b, cudaMemcpy2DAsync(dst, h.right.pitch[0], c, stride1, W, H, kind, b->side_b));
         }
     }
     int n_launch = 0;
@@ -429,8 +426,12 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
 
     if (cfg->cuda_stream) { b->main = (cudaStream_t)cfg->cuda_stream; b->own_main = false; }
     else { TRYC(cudaStreamCreateWithFlags(&b->main, cudaStreamNonBlocking)); b->own_main = true; }
-    TRYC(cudaStreamCreateWithFlags(&b->side_a, cudaStreamNonBlocking));
-    TRYC(cudaStreamCreateWithFlags(&b->side_b, cudaStreamNonBlocking));
+    if (getenv("VF_SERIALIZE")) {   // measurement aid: one stream, no overlap between the stages of a frame
+        b->side_a = b->main; b->side_b = b->main; b->serialized = true;
+    } else {
+        TRYC(cudaStreamCreateWithFlags(&b->side_a, cudaStreamNonBlocking));
+        TRYC(cudaStreamCreateWithFlags(&b->side_b, cudaStreamNonBlocking));
+    }
     TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_resp, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_right, cudaEventDisableTiming));
@@ -596,10 +597,8 @@ vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* b
     VF_CUDA(b, cudaStreamSynchronize(b->main));
     const DevBatch& h = b->h;
     const int s = t->stream_index, p = b->last_parity, cap = h.cap;
-    const int* cn = b->pin_counters[p] + s * C_COUNT;
     int cnt_now[C_COUNT];
     VF_CUDA(b, cudaMemcpy(cnt_now, h.counters[p] + s * C_COUNT, sizeof(cnt_now), cudaMemcpyDeviceToHost));
-    (void)cn;
     const size_t so = (size_t)s * cap;
     const void* src = nullptr;
     size_t bytes = 0;
@@ -666,11 +665,11 @@ vf_status temp_pyramid(TempPyr& tp, const uint8_t* img, int w, int h, int max_le
     tp.pv.n_levels = n;
     int lw = w, lh = h;
     for (int l = 0; l < n; ++l) {
-        tp.pv.w[l] = lw; tp.pv.h[l] = lh; tp.pv.pitch[l] = align_up(lw, 16);
+        tp.pv.w[l] = lw; tp.pv.h[l] = lh; tp.pv.pitch[l] = align_up(lw + 2 * kPyrPad, 16);
         void* p = nullptr;
-        VF_CUDA((vf_batch*)nullptr, cudaMalloc(&p, (size_t)tp.pv.pitch[l] * lh));
+        VF_CUDA((vf_batch*)nullptr, cudaMalloc(&p, (size_t)tp.pv.pitch[l] * (lh + 2 * kPyrPad)));
         tp.allocs.push_back(p);
-        tp.pv.lvl[l] = (uint8_t*)p;
+        tp.pv.lvl[l] = (uint8_t*)p + (size_t)kPyrPad * tp.pv.pitch[l] + kPyrPad;
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy2DAsync(tp.pv.lvl[0], tp.pv.pitch[0], img, w, w, h, cudaMemcpyHostToDevice, st));

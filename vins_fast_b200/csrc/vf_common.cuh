@@ -13,8 +13,13 @@ constexpr int kWin = 21;             // LK window (reference: cv::Size(21,21), f
 constexpr int kWinPx = kWin * kWin;  // 441
 constexpr int kNumSms = 148;         // B200
 
-// One image pyramid resident in HBM: unpadded levels, rows padded to a 16-byte pitch so 16-byte vector
-// loads/stores are always aligned (a 752-wide level 0 has pitch 752: the upload is one linear DMA).
+// One image pyramid resident in HBM.  Every level is stored with a REFLECT_101 border of kPyrPad pixels on all four
+// sides (what cv::buildOpticalFlowPyramid keeps around each level for the LK window, lkpyramid.cpp), so the LK kernels
+// fetch window tiles with plain aligned 32-bit loads wherever the window lies.  lvl[l] points at pixel (0,0) of the
+// level (interior origin, 16-byte aligned); pitch[l] is the padded row pitch (multiple of 16).  The innermost
+// kPyrPadFill border pixels are filled (pad_levels_kernel); an LK tile reaches at most 26 pixels outside a level.
+constexpr int kPyrPad = 32;
+constexpr int kPyrPadFill = 28;
 struct PyrView {
     uint8_t* lvl[kMaxLevels];
     int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];

@@ -47,37 +47,44 @@ struct LevelRef {
     int w, h, pitch;
 };
 
-// Per-level geometry of the source window (depends on the source point only).
-struct LevelGeo {
-    int ipx, ipy;            // top-left tap of the window
-    int valid;               // window intersects the padded level (lkpyramid.cpp bounds test)
-    int w00, w01, w10, w11;  // bilinear weights of the source point
-    int pad;
+// Per-level quantities that depend on the source point only (computed once per pass by the prologue).
+struct alignas(16) LevelGeo {
+    int w00, w01, w10, w11;        // bilinear weights of the source point
+    int ipx, ipy, w, h;            // top-left tap of the window; level size
+    float A11, A12, A22, Dinv;     // spatial gradient matrix (scaled by 2^-20) and 1 / det
+    int valid;                     // window intersects the padded level (lkpyramid.cpp bounds test)
+    int skip;                      // minEig < 1e-4 or det < FLT_EPSILON: the level is skipped (status 0 on level 0)
+    int pad[2];
 };
 
-struct LevelPatch {
-    short Iw[kWinPx + 3];            // interpolated I, 2^5 fixed point
-    short2 dI[kWinPx];               // interpolated (Ix, Iy)
-    float A[16];                     // chain values: A11 lanes 0..3, tail | A12 ... | A22 ...  (index m*5 + c)
+constexpr int kChainA = 108;                 // slots of one summation chain of A (84 / 105 terms, zero padded)
+constexpr int kChainsA = 15;                 // 3 matrices x (4 SIMD-lane accumulators + 1 scalar tail)
+
+// Per-level state of one pass, in dynamic shared memory (one block per pyramid level the pass uses).
+struct LevelBlock {
+    alignas(16) float termsA[kChainsA * kChainA];   // terms of A in accumulation order, chain-major
+    alignas(16) short2 dI[kWinPx + 3];               // interpolated (Ix, Iy)
+    alignas(16) short Iw[kWinPx + 7];                // interpolated I, 2^5 fixed point
+    alignas(16) short2 dtile[kTileD * kTileD];       // Scharr (Ix, Iy) at the 22x22 tap positions
+    alignas(16) uint8_t tileI[kTileI * kTileI];      // 24x24 source pixels
+    LevelGeo geo;
 };
 
 struct LkSmem {
     LevelRef pyr[2][kMaxLevels];
-    LevelGeo geo[kMaxLevels];
-    LevelPatch patch[kMaxLevels];
-    alignas(16) uint8_t tileI[kMaxLevels][kTileI * kTileI];
-    alignas(16) short2 dtile[kMaxLevels][kTileD * kTileD];
-    alignas(16) uint8_t tileJ[kTileJ * kTileJ];
+    alignas(16) uint8_t tileJ[2][kTileJ * kTileJ];
     alignas(16) int4 part[2][kLkWarps];   // per-warp (sum tx, sum ty, sum |t|) of an iteration, double-buffered
     alignas(16) int termsB[kTermsB + 2];  // terms of b, spilled only when the global exactness bound fails
     float chainB[12];
     int found[2];
-    int fast_iters;
 #ifdef VF_LK_TIMING
     unsigned long long tacc[16], tcnt[16];
     int tbase;
 #endif
+    alignas(16) LevelBlock lv[1];         // [n_levels of the launch]
 };
+
+static size_t lk_smem_bytes(int n_levels) { return sizeof(LkSmem) + sizeof(LevelBlock) * (size_t)(n_levels > 1 ? n_levels - 1 : 0); }
 
 #define VF_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
 
@@ -85,14 +92,20 @@ struct LkSmem {
 // accumulates per-phase cycles in shared memory and flushes them to vf_lk_timing[k] / vf_lk_timing[16 + k] at the end.
 #ifdef VF_LK_TIMING
 __device__ unsigned long long vf_lk_timing[32];
+__device__ unsigned long long vf_lk_cta_times[2][256][4];   // [kernel][cta]{start ns, end ns, smid, iters}
+__device__ __forceinline__ unsigned long long vf_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int vf_smid() { unsigned int r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 #define LK_T_DECL long long lk_t_last = clock64();
 #define LK_T(k) do { const long long t__ = clock64(); if (threadIdx.x == 0) { sm.tacc[sm.tbase + (k)] += (unsigned long long)(t__ - lk_t_last); sm.tcnt[sm.tbase + (k)] += 1; } \
                      lk_t_last = t__; } while (0)
-#define LK_T_RESET() do { lk_t_last = clock64(); } while (0)
 #else
 #define LK_T_DECL
 #define LK_T(k) do { } while (0)
-#define LK_T_RESET() do { } while (0)
+#endif
+#ifdef VF_LK_TIMING_FINE
+#define LK_TF(k) LK_T(k)
+#else
+#define LK_TF(k) do { } while (0)
 #endif
 
 __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
@@ -103,27 +116,25 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int
     w11 = 16384 - w00 - w01 - w10;
 }
 
-// Reflect-101 for tile coordinates: two branch-free folds cover every index within 2n-2 of the image
-// (tiles reach at most 27 pixels outside a level, levels are at least 22 pixels wide).
-__device__ __forceinline__ int refl101_tile(int i, int n) {
-    i = i < 0 ? -i : i;
-    i = i >= n ? 2 * n - 2 - i : i;
-    i = i < 0 ? -i : i;
-    i = i >= n ? 2 * n - 2 - i : i;
-    return i;
+// One row of NW*4 pixels of a level starting at column x0 of row y, as NW packed words.  The levels carry a REFLECT_101
+// border in HBM (vf_common.cuh: kPyrPad), so any row a window can touch is fetched with NW (+1 when unaligned) aligned
+// 32-bit loads and realigned with funnel shifts.  Callers keep -26 <= x0, x0 + 4*NW <= w + 26 (+-3 for the alignment)
+// and -26 <= y < h + 26.
+template <int NW>
+__device__ __forceinline__ void load_row_words(const LevelRef& L, int x0, int y, uint32_t (&out)[NW]) {
+    const uint8_t* row = L.p + (ptrdiff_t)y * L.pitch;
+    const int m = x0 & 3;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row + (x0 - m));   // level origin and pitch are 16-byte aligned
+    uint32_t w[NW + 1];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) w[k] = __ldg(wp + k);
+    w[NW] = m ? __ldg(wp + NW) : 0u;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], 8 * m);
 }
 
-// Stage the 32x32 tile of J with origin (x0, y0), reflect-101 outside the image: 4 bytes per thread, all loads
-// before the first store (one memory round trip).
-__device__ __forceinline__ void stage_tile_j(uint8_t* tile, const LevelRef& L, int x0, int y0) {
-    const int tid = threadIdx.x;
-    const int ty = tid >> 3, tx = (tid & 7) * 4;
-    const uint8_t* row = L.p + (size_t)refl101_tile(y0 + ty, L.h) * L.pitch;
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v |= (uint32_t)__ldg(row + refl101_tile(x0 + tx + k, L.w)) << (8 * k);
-    *reinterpret_cast<uint32_t*>(tile + ty * kTileJ + tx) = v;
-}
+// Origin of a speculative (prefetched) J tile, clamped so that the 32x32 tile stays inside the filled border.
+__device__ __forceinline__ int clamp_tile_origin(int o, int n) { return min(max(o, -(kPyrPadFill - 2)), n + kPyrPadFill - 2 - kTileJ); }
 
 struct LkResult {
     float x, y;
@@ -132,19 +143,19 @@ struct LkResult {
 
 // Warp-level value of one summation chain whose `n` integer terms are produced by term(k), k = 0..n-1 in OpenCV's
 // accumulation order.  Exact integer path when sum|t| < 2^24, else the ordered float chain (all lanes run it
-// redundantly; they are in lock-step anyway).  Terms are |t| < 2^27, n <= 105: no int32 overflow.
+// redundantly; they are in lock-step anyway).
 template <typename F>
-__device__ __forceinline__ float chain_value(int n, F term, bool nonneg) {
+__device__ __forceinline__ float chain_value(int n, F term) {
     const int lane = threadIdx.x & 31;
     int s = 0;
     unsigned int a = 0u;     // sum|t| <= 105 * 2^25 < 2^32: unsigned, so it cannot wrap into a small value
     for (int k = lane; k < n; k += 32) {
         const int t = term(k);
         s += t;
-        a += nonneg ? 0u : (unsigned int)abs(t);
+        a += (unsigned int)abs(t);
     }
     s = __reduce_add_sync(0xffffffffu, s);
-    a = nonneg ? (unsigned int)s : __reduce_add_sync(0xffffffffu, a);
+    a = __reduce_add_sync(0xffffffffu, a);
     if (a < (unsigned int)kExact) return (float)s;
     float acc = 0.f;
 #pragma unroll 4
@@ -167,105 +178,132 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
 
     // ================= prologue: everything that depends on the source point only, all levels at once =================
     __syncthreads();   // the previous pass may still be reading the shared buffers
-    if (tid < nlv) {
-        const int level = tid;
-        const LevelRef LI = sm.pyr[ia][level];
-        const float scale = 1.f / (float)(1 << level);
-        const float ppx = __fsub_rn(__fmul_rn(prev_pt.x, scale), half), ppy = __fsub_rn(__fmul_rn(prev_pt.y, scale), half);
-        LevelGeo g;
-        g.ipx = __float2int_rd(ppx); g.ipy = __float2int_rd(ppy);
-        g.valid = !(g.ipx < -kWin || g.ipx >= LI.w || g.ipy < -kWin || g.ipy >= LI.h);
-        bilinear_weights(__fsub_rn(ppx, (float)g.ipx), __fsub_rn(ppy, (float)g.ipy), g.w00, g.w01, g.w10, g.w11);
-        g.pad = 0;
-        sm.geo[level] = g;
-    }
-    // the J tile of the top level only depends on the start point: fetch it together with the I tiles
-    int jx0, jy0;
+    // ---- P1: one thread per tile row.  Threads 0..24*nlv-1: rows of the 24x24 tiles of I (level = tid / 24);
+    //      warp 6: rows of the top level's 32x32 tile of J (it only depends on the start point) ----
+    int jx0, jy0, jbuf = 0;
     {
         const float scale = 1.f / (float)(1 << max_level);
         const float sx = use_init ? init_pt.x : prev_pt.x, sy = use_init ? init_pt.y : prev_pt.y;
-        jx0 = __float2int_rd(__fsub_rn(__fmul_rn(sx, scale), half)) - kJMargin;
-        jy0 = __float2int_rd(__fsub_rn(__fmul_rn(sy, scale), half)) - kJMargin;
+        const LevelRef LT = sm.pyr[ja][max_level];
+        jx0 = clamp_tile_origin(__float2int_rd(__fsub_rn(__fmul_rn(sx, scale), half)) - kJMargin, LT.w);
+        jy0 = clamp_tile_origin(__float2int_rd(__fsub_rn(__fmul_rn(sy, scale), half)) - kJMargin, LT.h);
     }
-    __syncthreads();
-    // ---- P1: 24x24 tiles of I on every level (9 bytes per thread for 4 levels), all loads before the first store ----
-    {
-        constexpr int PER = (kMaxLevels * kTileI * kTileI + kLkThreads - 1) / kLkThreads;   // 18
-        const int total = nlv * kTileI * kTileI;
-        uint8_t v[PER];
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int i = tid + k * kLkThreads;
-            v[k] = 0;
-            if (i < total) {
-                const int level = i / (kTileI * kTileI), e = i - level * (kTileI * kTileI);
-                const int ty = e / kTileI, tx = e - ty * kTileI;
-                const LevelRef LI = sm.pyr[ia][level];
-                const LevelGeo& g = sm.geo[level];
-                if (g.valid)
-                    v[k] = __ldg(LI.p + (size_t)refl101_tile(g.ipy - 1 + ty, LI.h) * LI.pitch + refl101_tile(g.ipx - 1 + tx, LI.w));
-            }
+    if (tid < kTileI * nlv) {
+        const int level = tid / kTileI, row = tid - level * kTileI;
+        const LevelRef LI = sm.pyr[ia][level];
+        const float scale = 1.f / (float)(1 << level);
+        const float ppx = __fsub_rn(__fmul_rn(prev_pt.x, scale), half), ppy = __fsub_rn(__fmul_rn(prev_pt.y, scale), half);
+        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+        const int valid = !(ipx < -kWin || ipx >= LI.w || ipy < -kWin || ipy >= LI.h);
+        if (row == 0) {
+            LevelGeo& g = sm.lv[level].geo;
+            g.ipx = ipx; g.ipy = ipy; g.w = LI.w; g.h = LI.h; g.valid = valid;
+            bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), g.w00, g.w01, g.w10, g.w11);
         }
-        stage_tile_j(sm.tileJ, sm.pyr[ja][max_level], jx0, jy0);
+        if (valid) {
+            uint32_t v[kTileI / 4];
+            load_row_words<kTileI / 4>(LI, ipx - 1, ipy - 1 + row, v);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(sm.lv[level].tileI + row * kTileI);
 #pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int i = tid + k * kLkThreads;
-            if (i < total) (&sm.tileI[0][0])[i] = v[k];
+            for (int k = 0; k < kTileI / 4; ++k) dst[k] = v[k];
         }
+    } else if (wid == 6) {
+        uint32_t v[kTileJ / 4];
+        load_row_words<kTileJ / 4>(sm.pyr[ja][max_level], jx0, jy0 + lane, v);
+        uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[0] + lane * kTileJ);
+        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
     LK_T(0);
-    // ---- P2: Scharr (Ix,Iy) on the 22x22 tap positions of every level; zero outside the image ----
-    for (int i = tid; i < nlv * (kTileD * kTileD); i += kLkThreads) {
-        const int level = i / (kTileD * kTileD), e = i - level * (kTileD * kTileD);
-        const int ty = e / kTileD, tx = e - ty * kTileD;
-        const LevelGeo& g = sm.geo[level];
-        const int x = g.ipx + tx, y = g.ipy + ty;
-        short2 d = make_short2(0, 0);
-        if (x >= 0 && x < sm.pyr[ia][level].w && y >= 0 && y < sm.pyr[ia][level].h) {
-            const uint8_t* p = &sm.tileI[level][(ty + 1) * kTileI + (tx + 1)];
-            const int a00 = p[-kTileI - 1], a01 = p[-kTileI], a02 = p[-kTileI + 1];
-            const int a10 = p[-1], a12 = p[1];
-            const int a20 = p[kTileI - 1], a21 = p[kTileI], a22 = p[kTileI + 1];
-            const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
-            const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
-            d = make_short2((short)(t0p - t0m), (short)((t1m + t1p) * 3 + t1c * 10));
+    // ---- P2: Scharr (Ix,Iy) on the 22x22 tap positions of every level; zero outside the image.
+    //      A thread owns the same (at most two) tile positions on every level: the index arithmetic is level-invariant ----
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int e = tid + r * kLkThreads;
+        if (e < kTileD * kTileD) {
+            const int ty = e / kTileD, tx = e - ty * kTileD;
+            const int toff = (ty + 1) * kTileI + (tx + 1);
+#pragma unroll 1
+            for (int level = 0; level < nlv; ++level) {
+                LevelBlock& B = sm.lv[level];
+                const int4 q = *reinterpret_cast<const int4*>(&B.geo.ipx);     // ipx, ipy, w, h
+                const int x = q.x + tx, y = q.y + ty;
+                const bool inside = (unsigned)x < (unsigned)q.z && (unsigned)y < (unsigned)q.w;
+                const uint8_t* p = B.tileI + toff;                             // always readable; stale for skipped levels
+                const int a00 = p[-kTileI - 1], a01 = p[-kTileI], a02 = p[-kTileI + 1];
+                const int a10 = p[-1], a12 = p[1];
+                const int a20 = p[kTileI - 1], a21 = p[kTileI], a22 = p[kTileI + 1];
+                const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
+                const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
+                const int ix = inside ? t0p - t0m : 0, iy = inside ? (t1m + t1p) * 3 + t1c * 10 : 0;
+                B.dtile[e] = make_short2((short)ix, (short)iy);
+            }
         }
-        sm.dtile[level][e] = d;
     }
     __syncthreads();
     LK_T(1);
-    // ---- P3: 21x21 bilinear patches (I in 2^5, derivatives in Scharr units) of every level ----
-    for (int i = tid; i < nlv * kWinPx; i += kLkThreads) {
-        const int level = i / kWinPx, e = i - level * kWinPx;
-        const int y = e / kWin, x = e - y * kWin;
-        const LevelGeo& g = sm.geo[level];
-        const int w00 = g.w00, w01 = g.w01, w10 = g.w10, w11 = g.w11;
-        const uint8_t* s = &sm.tileI[level][(y + 1) * kTileI + (x + 1)];
-        const int ival = VF_DESCALE(s[0] * w00 + s[1] * w01 + s[kTileI] * w10 + s[kTileI + 1] * w11, 9);
-        const short2* dt = &sm.dtile[level][y * kTileD + x];
-        const short2 d00 = dt[0], d01 = dt[1], d10 = dt[kTileD], d11 = dt[kTileD + 1];
-        const int ixval = VF_DESCALE(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14);
-        const int iyval = VF_DESCALE(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14);
-        sm.patch[level].Iw[e] = (short)ival;
-        sm.patch[level].dI[e] = make_short2((short)ixval, (short)iyval);
+    // ---- P3: 21x21 bilinear patches (I in 2^5, derivatives in Scharr units) of every level + the terms of A, stored
+    //      in OpenCV's accumulation order: SIMD lane l = x & 3 sees columns l, 4+l, 8+l, 12+l of every row in turn
+    //      (slot y*4 + x/4 of chain l), the scalar tail sees columns 16..20 of every row (slot y*5 + x-16 of chain 4) ----
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int e = tid + r * kLkThreads;
+        if (e < kWinPx) {
+            const int y = e / kWin, x = e - y * kWin;
+            const int ioff = (y + 1) * kTileI + (x + 1), doff = y * kTileD + x;
+            const int aoff = x < 16 ? (x & 3) * kChainA + y * 4 + (x >> 2) : 4 * kChainA + y * 5 + (x - 16);
+#pragma unroll 1
+            for (int level = 0; level < nlv; ++level) {
+                LevelBlock& B = sm.lv[level];
+                const int4 w = *reinterpret_cast<const int4*>(&B.geo.w00);
+                const uint8_t* s = B.tileI + ioff;
+                const int ival = VF_DESCALE(s[0] * w.x + s[1] * w.y + s[kTileI] * w.z + s[kTileI + 1] * w.w, 9);
+                const short2* dt = B.dtile + doff;
+                const short2 d00 = dt[0], d01 = dt[1], d10 = dt[kTileD], d11 = dt[kTileD + 1];
+                const int ixval = VF_DESCALE(d00.x * w.x + d01.x * w.y + d10.x * w.z + d11.x * w.w, 14);
+                const int iyval = VF_DESCALE(d00.y * w.x + d01.y * w.y + d10.y * w.z + d11.y * w.w, 14);
+                B.Iw[e] = (short)ival;
+                B.dI[e] = make_short2((short)ixval, (short)iyval);
+                float* ta = B.termsA + aoff;                       // |ixval|, |iyval| <= 4080: products < 2^24, exact in float
+                ta[0] = (float)(ixval * ixval);
+                ta[5 * kChainA] = (float)(ixval * iyval);
+                ta[10 * kChainA] = (float)(iyval * iyval);
+            }
+        }
     }
     __syncthreads();
     LK_T(2);
-    // ---- P4: the 15 summation chains of A on every level; unit = (level, SIMD lane class c = 0..3 | tail c = 4) ----
-    for (int u = wid; u < nlv * 5; u += kLkWarps) {
-        const int level = u / 5, c = u - level * 5;
-        const short2* dI = sm.patch[level].dI;
-        float* A = sm.patch[level].A;
-        // OpenCV's order: lane c sees columns c, 4+c, 8+c, 12+c of every row in turn; the tail sees columns 16..20
-        auto at = [&](int k) -> short2 {
-            return c < 4 ? dI[(k >> 2) * kWin + 4 * (k & 3) + c] : dI[(k / 5) * kWin + 16 + (k - (k / 5) * 5)];
-        };
-        const int n = c < 4 ? 84 : kTail;
-        const float a11 = chain_value(n, [&](int k) { const short2 d = at(k); return (int)d.x * d.x; }, true);
-        const float a12 = chain_value(n, [&](int k) { const short2 d = at(k); return (int)d.x * d.y; }, false);
-        const float a22 = chain_value(n, [&](int k) { const short2 d = at(k); return (int)d.y * d.y; }, true);
-        if (lane == 0) { A[c] = a11; A[5 + c] = a12; A[10 + c] = a22; }
+    // ---- P4: the 15 ordered float chains of A on every level, one LANE per chain (acc = ((0 + t0) + t1) + ...):
+    //      27 vector loads and 108 dependent FADDs per lane, all chains of all levels side by side ----
+    for (int level = wid; level < nlv; level += kLkWarps) {
+        LevelBlock& B = sm.lv[level];
+        const float4* src = reinterpret_cast<const float4*>(B.termsA + min(lane, kChainsA - 1) * kChainA);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kChainA / 4; ++i) {
+            const float4 v = src[i];
+            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+        }
+        // iA += v_reduce_sum(qA): tail + ((q0 + q2) + (q1 + q3)); then the 2x2 system of the level
+        float r[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const float q0 = __shfl_sync(0xffffffffu, acc, 5 * m + 0), q1 = __shfl_sync(0xffffffffu, acc, 5 * m + 1);
+            const float q2 = __shfl_sync(0xffffffffu, acc, 5 * m + 2), q3 = __shfl_sync(0xffffffffu, acc, 5 * m + 3);
+            const float tl = __shfl_sync(0xffffffffu, acc, 5 * m + 4);
+            r[m] = __fadd_rn(tl, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+        }
+        if (lane == 0) {
+            const float A11 = __fmul_rn(r[0], FLT_SCALE), A12 = __fmul_rn(r[1], FLT_SCALE), A22 = __fmul_rn(r[2], FLT_SCALE);
+            const float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+            const float dA = __fsub_rn(A11, A22);
+            const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+            const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * kWin * kWin));
+            LevelGeo& g = B.geo;
+            g.A11 = A11; g.A12 = A12; g.A22 = A22; g.Dinv = __fdiv_rn(1.f, D);
+            g.skip = (minEig < 1e-4f || D < FLT_EPSILON) ? 1 : 0;
+        }
     }
     __syncthreads();
     LK_T(3);
@@ -290,6 +328,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
 #pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
         const LevelRef LJ = sm.pyr[ja][level];
+        const LevelBlock& B = sm.lv[level];
         const int jcols = LJ.w, jrows = LJ.h;
         const float scale = 1.f / (float)(1 << level);
         float nx, ny;
@@ -298,42 +337,46 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             else { nx = __fmul_rn(prev_pt.x, scale); ny = __fmul_rn(prev_pt.y, scale); }
         } else { nx = __fmul_rn(outx, 2.f); ny = __fmul_rn(outy, 2.f); }
         outx = nx; outy = ny;
-        const LevelGeo& geo = sm.geo[level];
-        if (!geo.valid) {
+        const int4 gflags = *reinterpret_cast<const int4*>(&B.geo.valid);     // valid, skip
+        if (!gflags.x || gflags.y) {   // window outside the level, or minEig / det below threshold (lkpyramid.cpp)
             if (level == 0) status = 0;
             tile_ready = false;
             continue;
         }
-        const float* Ac = sm.patch[level].A;
-        float r[3];
-#pragma unroll
-        for (int m = 0; m < 3; ++m)   // iA += v_reduce_sum(qA): tail + ((q0 + q2) + (q1 + q3))
-            r[m] = __fadd_rn(Ac[5 * m + 4], __fadd_rn(__fadd_rn(Ac[5 * m + 0], Ac[5 * m + 2]), __fadd_rn(Ac[5 * m + 1], Ac[5 * m + 3])));
-        const float A11 = __fmul_rn(r[0], FLT_SCALE), A12 = __fmul_rn(r[1], FLT_SCALE), A22 = __fmul_rn(r[2], FLT_SCALE);
-        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
-        const float dA = __fsub_rn(A11, A22);
-        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
-        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * kWin * kWin));
-        if (minEig < 1e-4f || D < FLT_EPSILON) {
-            if (level == 0) status = 0;
-            tile_ready = false;
-            continue;
-        }
-        D = __fdiv_rn(1.f, D);
+        const float4 gA = *reinterpret_cast<const float4*>(&B.geo.A11);
+        const float A11 = gA.x, A12 = gA.y, A22 = gA.z, D = gA.w;
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         // this thread's two source pixels stay in registers for the whole level
-        const short* Iw = sm.patch[level].Iw;
-        const short2* dI = sm.patch[level].dI;
-        const int I0 = e0 >= 0 ? Iw[e0] : 0, I1 = e1 >= 0 ? Iw[e1] : 0;
-        const short2 g0 = e0 >= 0 ? dI[e0] : make_short2(0, 0), g1 = e1 >= 0 ? dI[e1] : make_short2(0, 0);
-        if (!tile_ready) {
-            jx0 = __float2int_rd(nx) - kJMargin; jy0 = __float2int_rd(ny) - kJMargin;
-            __syncthreads();   // the previous level may still be reading tileJ
-            stage_tile_j(sm.tileJ, LJ, jx0, jy0);
-            __syncthreads();
+        const int I0 = e0 >= 0 ? B.Iw[e0] : 0, I1 = e1 >= 0 ? B.Iw[e1] : 0;
+        const short2 g0 = e0 >= 0 ? B.dI[e0] : make_short2(0, 0), g1 = e1 >= 0 ? B.dI[e1] : make_short2(0, 0);
+        {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (!tile_ready || inx < jx0 || iny < jy0 || inx + kTileD > jx0 + kTileJ || iny + kTileD > jy0 + kTileJ) {
+                // no usable prefetched tile: stage it now (one warp, one row per lane)
+                jx0 = clamp_tile_origin(inx - kJMargin, jcols); jy0 = clamp_tile_origin(iny - kJMargin, jrows);
+                jbuf ^= 1;
+                if (wid == 7) {
+                    uint32_t v[kTileJ / 4];
+                    load_row_words<kTileJ / 4>(LJ, jx0, jy0 + lane, v);
+                    uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
+                    dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                }
+                __syncthreads();
+            }
         }
-        tile_ready = false;
+        // prefetch the next level's J tile around the current estimate: warp 7 issues the loads now and parks the
+        // words in registers until the iterations of this level are done
+        uint32_t pf[kTileJ / 4];
+        int px0 = 0, py0 = 0;
+        if (level > 0) {
+            const LevelRef LN = sm.pyr[ja][level - 1];
+            px0 = clamp_tile_origin(__float2int_rd(__fadd_rn(__fmul_rn(nx, 2.f), half)) - kJMargin, LN.w);   // 2*(nx + half) - half
+            py0 = clamp_tile_origin(__float2int_rd(__fadd_rn(__fmul_rn(ny, 2.f), half)) - kJMargin, LN.h);
+            if (wid == 7) load_row_words<kTileJ / 4>(sm.pyr[ja][level - 1], px0, py0 + lane, pf);
+        }
         LK_T(4);
+        const uint8_t* tj = sm.tileJ[jbuf];
         float pdx = 0.f, pdy = 0.f;
 #pragma unroll 1
         for (int j = 0; j < 30; ++j) {
@@ -346,13 +389,19 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             if (inx < jx0 || iny < jy0 || inx + kTileD > jx0 + kTileJ || iny + kTileD > jy0 + kTileJ) {
                 // the window left the staged tile: re-centre it (uniform branch)
                 jx0 = inx - kJMargin; jy0 = iny - kJMargin;
-                __syncthreads();
-                stage_tile_j(sm.tileJ, LJ, jx0, jy0);
+                __syncthreads();    // everybody is done with the current tile
+                if (wid == 6) {
+                    uint32_t v[kTileJ / 4];
+                    load_row_words<kTileJ / 4>(LJ, jx0, jy0 + lane, v);
+                    uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
+                    dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                }
                 __syncthreads();
             }
             int w00, w01, w10, w11;
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            const uint8_t* jt = &sm.tileJ[(iny - jy0) * kTileJ + (inx - jx0)];
+            const uint8_t* jt = tj + (iny - jy0) * kTileJ + (inx - jx0);
             const uint8_t* p0 = jt + o0;
             const uint8_t* p1 = jt + o1;
             const int d0 = VF_DESCALE(p0[0] * w00 + p0[1] * w01 + p0[kTileJ] * w10 + p0[kTileJ + 1] * w11, 9) - I0;
@@ -361,6 +410,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             const int ex0 = e0 >= 0 ? d0 * g0.x : 0, ey0 = e0 >= 0 ? d0 * g0.y : 0;
             const int ex1 = e1 >= 0 ? d1 * g1.x : 0, ey1 = e1 >= 0 ? d1 * g1.y : 0;
             const int tx = ex0 + ex1, ty = ey0 + ey1;
+            LK_TF(6);
             // clamped so that the sum over the 221 contributing threads stays below 2^32 (compared unsigned)
             const int ab = min(tid < 168 ? abs(tx) + abs(ty) : abs(ex0) + abs(ey0) + abs(ex1) + abs(ey1), kExact);
             const int sx = __reduce_add_sync(0xffffffffu, tx);
@@ -376,6 +426,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 bx += q.x; by += q.y; bnd += (unsigned int)q.z;
             }
             pbuf ^= 1;
+            LK_TF(7);
             float ib1, ib2;
             if (bnd < (unsigned int)kExact) {
                 // every partial sum of every chain and of their combination is an exactly representable integer
@@ -395,7 +446,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 __syncthreads();
                 for (int ch = wid; ch < 10; ch += kLkWarps) {
                     const int* src = ch < 8 ? &sm.termsB[ch * kSimdB] : &sm.termsB[8 * kSimdB + (ch - 8) * kTail];
-                    const float v = chain_value(ch < 8 ? kSimdB : kTail, [&](int k) { return src[k]; }, false);
+                    const float v = chain_value(ch < 8 ? kSimdB : kTail, [&](int k) { return src[k]; });
                     if (lane == 0) sm.chainB[ch] = v;
                 }
                 __syncthreads();
@@ -405,21 +456,40 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 const float s2 = __fadd_rn(k[2], k[6]), s3 = __fadd_rn(k[3], k[7]);
                 ib1 = __fadd_rn(k[8], __fadd_rn(s0, s2));
                 ib2 = __fadd_rn(k[9], __fadd_rn(s1, s3));
+                LK_TF(8);
             }
             const float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             outx = __fadd_rn(nx, half); outy = __fadd_rn(ny, half);
-            const double dd = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy));
-            if (dd <= 0.01 * 0.01) break;
-            if (j > 0 && fabs((double)__fadd_rn(dx, pdx)) < 0.01 && fabs((double)__fadd_rn(dy, pdy)) < 0.01) {
+            // delta.ddot(delta) <= eps^2 in double (lkpyramid.cpp); a float estimate settles all but borderline cases
+            const float ff = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+            bool conv = ff < 0.9999e-4f;
+            if (!conv && ff < 1.0001e-4f)
+                conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= 0.01 * 0.01;
+            if (conv) break;
+            // std::abs(x) < 0.01 on a float widened to double  <=>  |x| <= 0.01f (0.01f is the largest float below 0.01)
+            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
                 outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
                 break;
             }
             pdx = dx; pdy = dy;
+            LK_TF(9);
         }
         LK_T(5);
+        tile_ready = false;
+        if (level > 0) {   // publish the prefetched tile of the next level
+            jbuf ^= 1;
+            if (wid == 7) {
+                uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
+                dst[0] = make_uint4(pf[0], pf[1], pf[2], pf[3]);
+                dst[1] = make_uint4(pf[4], pf[5], pf[6], pf[7]);
+            }
+            jx0 = px0; jy0 = py0;
+            tile_ready = true;
+            __syncthreads();
+        }
         if (status && level == 0) {   // the caller passes an err vector: final window test (lkpyramid.cpp)
             const int ix = __float2int_rd(__fsub_rn(outx, half)), iy = __float2int_rd(__fsub_rn(outy, half));
             if (ix < -kWin || ix >= jcols || iy < -kWin || iy >= jrows) status = 0;
@@ -446,7 +516,14 @@ __device__ __forceinline__ void load_pyr(LkSmem& sm, int slot, const PyrView& pv
     }
 }
 
-__device__ __forceinline__ void lk_smem_init(LkSmem& sm, int* counters2) {
+// Zero the padding slots of the A chains once per kernel: the terms never overwrite them, and adding +0.0f to a chain
+// value is an exact identity (a chain of non-negative-zero integer-valued floats can never be -0.0f).
+__device__ __forceinline__ void lk_smem_init(LkSmem& sm, int* counters2, int n_levels) {
+    constexpr int kPad = kChainA - 84;   // slots 84..107 (the tails' real terms 84..104 are written later, every pass)
+    for (int i = threadIdx.x; i < n_levels * kChainsA * kPad; i += kLkThreads) {
+        const int level = i / (kChainsA * kPad), r = i - level * (kChainsA * kPad);
+        sm.lv[level].termsA[(r / kPad) * kChainA + 84 + (r % kPad)] = 0.f;
+    }
     if (threadIdx.x == 0) { counters2[0] = 0; counters2[1] = 0; }
 #ifdef VF_LK_TIMING
     if (threadIdx.x < 16) { sm.tacc[threadIdx.x] = 0; sm.tcnt[threadIdx.x] = 0; }
@@ -485,8 +562,11 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch*
     const DevBatch& b = *bp;
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
+#ifdef VF_LK_TIMING
+    const unsigned long long cta_t0 = vf_globaltimer();
+#endif
     if (i >= n_prev) return;
-    lk_smem_init(sm, stat);
+    lk_smem_init(sm, stat, b.n_levels);
     load_pyr(sm, 0, b.left[parity ^ 1], b.lvl_stream_stride, s);   // 0 = previous left
     load_pyr(sm, 1, b.left[parity], b.lvl_stream_stride, s);       // 1 = current left
     __syncthreads();
@@ -527,6 +607,9 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch*
         b.rev_pts[o] = rev; b.rev_st[o] = (uint8_t)rst;
         b.temporal_st[o] = (uint8_t)ok;
         b.lk_iters[o] = stat[0] | (stat[1] << 16);   // low 16 bits: iterations, high: of which on the exact-integer path
+#ifdef VF_LK_TIMING
+        if (i < 256) { vf_lk_cta_times[0][i][0] = cta_t0; vf_lk_cta_times[0][i][1] = vf_globaltimer(); vf_lk_cta_times[0][i][2] = vf_smid(); vf_lk_cta_times[0][i][3] = stat[0]; }
+#endif
     }
     lk_timing_flush(sm);
 }
@@ -545,9 +628,12 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
     const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
+#ifdef VF_LK_TIMING
+    const unsigned long long cta_t0 = vf_globaltimer();
+#endif
     if (i >= n) return;
     const size_t o = (size_t)s * cap + i;
-    lk_smem_init(sm, stat);
+    lk_smem_init(sm, stat, b.n_levels);
     load_pyr(sm, 0, b.left[parity], b.lvl_stream_stride, s);   // 0 = current left
     load_pyr(sm, 1, b.right, b.lvl_stream_stride, s);          // 1 = current right
     if (tid == 0) sm.found[1] = -1;
@@ -590,6 +676,9 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
         b.lr_pts[o] = rp; b.lr_st[o] = (uint8_t)st; b.rl_pts[o] = back; b.rl_st[o] = (uint8_t)rst;
         b.lk_iters_stereo[o] = stat[0] | (stat[1] << 16);
         if (ok) atomicAdd(&b.counters[parity][s * C_COUNT + C_N_RIGHT], 1);
+#ifdef VF_LK_TIMING
+        if (i < 256) { vf_lk_cta_times[1][i][0] = cta_t0; vf_lk_cta_times[1][i][1] = vf_globaltimer(); vf_lk_cta_times[1][i][2] = vf_smid(); vf_lk_cta_times[1][i][3] = stat[0]; }
+#endif
     }
     lk_timing_flush(sm);
 }
@@ -633,11 +722,11 @@ __global__ void __launch_bounds__(kLkThreads) lk_op_kernel(PyrView prev, PyrView
     __shared__ int stat[2];
     const int i = blockIdx.x;
     if (i >= n) return;
-    lk_smem_init(sm, stat);
+    const int L = min(max_level, min(prev.n_levels, next.n_levels) - 1);
+    lk_smem_init(sm, stat, L + 1);
     load_pyr(sm, 0, prev, nullptr, 0);
     load_pyr(sm, 1, next, nullptr, 0);
     __syncthreads();
-    const int L = min(max_level, min(prev.n_levels, next.n_levels) - 1);
     const LkResult r = lk_track_point(sm, 0, 1, prev_pts[i], next_pts[i], use_init != 0, L, stat);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -658,20 +747,21 @@ void launch_undistort(const CamParams& cam, const float2* uv, float2* out, int n
 
 // The LK kernels keep all per-level state of a pass in (dynamic) shared memory: opt in above 48 KB once per device.
 cudaError_t lk_prepare() {
-    cudaError_t e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
+    const int bytes = (int)lk_smem_bytes(kMaxLevels);
+    cudaError_t e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
+    e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
+    return cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_temporal_kernel<<<grid, kLkThreads, sizeof(LkSmem), stream>>>(d_batch, parity);
+    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_stereo_kernel<<<grid, kLkThreads, sizeof(LkSmem), stream>>>(d_batch, parity);
+    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity);
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);
@@ -680,7 +770,8 @@ void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parit
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {
     if (n <= 0) return;
-    lk_op_kernel<<<n, kLkThreads, sizeof(LkSmem), stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow);
+    const int nlv = (max_level < prev.n_levels - 1 ? max_level : prev.n_levels - 1) + 1;
+    lk_op_kernel<<<n, kLkThreads, lk_smem_bytes(nlv > 1 ? nlv : 1), stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow);
 }
 
 }  // namespace vf
@@ -691,5 +782,8 @@ extern "C" int vf_debug_lk_timing(unsigned long long* out32) {
     unsigned long long zero[32] = {0};
     if (cudaMemcpyFromSymbol(out32, vf::vf_lk_timing, sizeof(zero)) != cudaSuccess) return 1;
     return cudaMemcpyToSymbol(vf::vf_lk_timing, zero, sizeof(zero)) != cudaSuccess;
+}
+extern "C" int vf_debug_lk_cta_times(unsigned long long* out) {   // [2][256][4]
+    return cudaMemcpyFromSymbol(out, vf::vf_lk_cta_times, sizeof(unsigned long long) * 2 * 256 * 4) != cudaSuccess;
 }
 #endif

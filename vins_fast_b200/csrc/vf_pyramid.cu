@@ -136,7 +136,70 @@ static void launch_pyr_fused(const PyrView& pv, const size_t* stride, int first,
     }
 }
 
-// All levels 1..n_levels-1 of a pyramid from its level 0, in ceil((n_levels-1)/3) launches.  Returns the launch count.
+// ------------------------------------------------------------------------------------------------------
+// REFLECT_101 border of every level (kPyrPadFill pixels on each side), one 32-bit word per thread:
+//   rows -F .. h+F-1 :  the left strip (columns -32 .. -1) and the right strip (from the last aligned column to w+31)
+//   rows -F .. -1 and h .. h+F-1 :  the words in between.
+// Runs after the level interiors are complete (level 0: the uploaded image; levels 1..: pyr_fused_kernel).
+// ------------------------------------------------------------------------------------------------------
+struct PadArgs {
+    uint8_t* lvl[kMaxLevels]; int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels]; size_t stride[kMaxLevels];
+    int first_item[kMaxLevels + 1];   // prefix sum of work items (words) per level
+    int n_levels;
+};
+
+__host__ __device__ inline int pad_items(int w, int h, int* strip_words) {
+    const int c0 = w & ~3, n_right = (w + kPyrPad - c0) / 4;
+    *strip_words = kPyrPad / 4 + n_right;
+    return (h + 2 * kPyrPadFill) * (*strip_words) + 2 * kPyrPadFill * (c0 / 4);
+}
+
+__global__ void __launch_bounds__(256) pad_levels_kernel(PadArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
+    if (idx >= a.first_item[a.n_levels]) return;
+    int l = 0;
+    while (idx >= a.first_item[l + 1]) ++l;
+    int j = idx - a.first_item[l];
+    const int w = a.w[l], h = a.h[l], pitch = a.pitch[l], F = kPyrPadFill;
+    uint8_t* base = a.lvl[l] + (size_t)img * a.stride[l];
+    const int c0 = w & ~3;
+    int strip;
+    pad_items(w, h, &strip);
+    int row, col;
+    if (j < (h + 2 * F) * strip) {
+        row = j / strip - F;
+        const int k = j - (row + F) * strip;
+        col = k < kPyrPad / 4 ? -kPyrPad + 4 * k : c0 + 4 * (k - kPyrPad / 4);
+    } else {
+        j -= (h + 2 * F) * strip;
+        const int per = c0 / 4, rr = j / per;
+        col = 4 * (j - rr * per);
+        row = rr < F ? rr - F : h + (rr - F);
+    }
+    const uint8_t* src = base + (size_t)refl101(row, h) * pitch;
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v |= (uint32_t)src[refl101(col + q, w)] << (8 * q);
+    *reinterpret_cast<uint32_t*>(base + (ptrdiff_t)row * pitch + col) = v;   // interior origin and pitch are 16-byte aligned
+}
+
+static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream) {
+    PadArgs a;
+    a.n_levels = pv.n_levels;
+    a.first_item[0] = 0;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        const bool ok = l < pv.n_levels;
+        a.lvl[l] = ok ? pv.lvl[l] : nullptr; a.w[l] = ok ? pv.w[l] : 0; a.h[l] = ok ? pv.h[l] : 0; a.pitch[l] = ok ? pv.pitch[l] : 0;
+        a.stride[l] = (ok && stride) ? stride[l] : 0;
+        int strip;
+        a.first_item[l + 1] = a.first_item[l] + (ok ? pad_items(pv.w[l], pv.h[l], &strip) : 0);
+    }
+    dim3 grid((a.first_item[pv.n_levels] + 255) / 256, n_images);
+    pad_levels_kernel<<<grid, 256, 0, stream>>>(a);
+}
+
+// All levels 1..n_levels-1 of a pyramid from its level 0, in ceil((n_levels-1)/3) launches, then the REFLECT_101
+// borders of all levels in one more.  Returns the launch count.
 int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream) {
     int first = 0, left = pv.n_levels - 1, n = 0;
     while (left > 0) {
@@ -144,7 +207,8 @@ int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaSt
         launch_pyr_fused(pv, stride, first, cnt, n_images, stream);
         first += cnt; left -= cnt; ++n;
     }
-    return n;
+    launch_pad_levels(pv, stride, n_images, stream);
+    return n + 1;
 }
 
 // calcScharrDeriv (video/lkpyramid.cpp) as a stand-alone plane kernel: int16 interleaved (Ix, Iy).
