@@ -53,6 +53,8 @@ struct vf_batch {
     bool own_main = false, serialized = false;
     cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr,
                 ev_sel = nullptr, ev_un = nullptr;
+    uint8_t* stage[2] = {nullptr, nullptr};   // unpadded upload targets (left, right): [S][H][stage_pitch]
+    int stage_pitch = 0;
     DevBatch h;               // host copy of the device descriptor
     DevBatch* d = nullptr;    // device copy
     std::vector<void*> allocs;
@@ -241,7 +243,8 @@ vf_status issue_left_chain(vf_batch* b, int parity) {
     const PyrView& pv = h.left[parity];
     {
         StageTimer t(b, ST_PYR_LEFT, b->main);
-        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main);
+        const Level0Src src = {b->stage[0], b->stage_pitch, (size_t)b->stage_pitch * h.H};
+        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main, &src);
     }
     { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, b->main); ++n; }
     { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); ++n; }
@@ -292,26 +295,26 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     VF_CUDA(b, cudaEventRecord(b->ev_img, b->main));            // orders side B after the previous frame's lk_stereo
     VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_img, 0));
     for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
-    {
-        StageTimer t(b, ST_H2D_LEFT, b->main);
+    // the images go up as ONE linear copy each into unpadded staging buffers (a pitched 2-D copy of 480 short rows is
+    // several times slower over PCIe); the pyramid launches read them there and move level 0 into its padded home
+    const size_t SP = (size_t)b->stage_pitch, simg = SP * H;
+    auto upload = [&](int cam, const uint8_t* const* imgs, const uint8_t* base, size_t stride, cudaStream_t st) -> cudaError_t {
         for (int s = 0; s < S; ++s) {
-            const uint8_t* a = base0 ? base0 + (size_t)s * image_stride : img0[s];
-            uint8_t* dst = h.left[parity].lvl[0] + (size_t)s * h.lvl_stream_stride[0];
-            VF_CUDA(b, cudaMemcpy2DAsync(dst, h.left[parity].pitch[0], a, stride0, W, H, kind, b->main));
+            const uint8_t* a = base ? base + (size_t)s * image_stride : imgs[s];
+            uint8_t* dst = b->stage[cam] + (size_t)s * simg;
+            cudaError_t e = (stride == SP) ? cudaMemcpyAsync(dst, a, simg, kind, st)
+                                           : cudaMemcpy2DAsync(dst, SP, a, stride, W, H, kind, st);
+            if (e != cudaSuccess) return e;
         }
-    }
-    {
-        StageTimer t(b, ST_H2D_RIGHT, b->side_b);
-        for (int s = 0; s < S; ++s) {
-            const uint8_t* c = base1 ? base1 + (size_t)s * image_stride : img1[s];
-            uint8_t* dst = h.right.lvl[0] + (size_t)s * h.lvl_stream_stride[0];
-            VF_CUDA(b, cudaMemcpy2DAsync(dst, h.right.pitch[0], c, stride1, W, H, kind, b->side_b));
-        }
-    }
+        return cudaSuccess;
+    };
+    { StageTimer t(b, ST_H2D_LEFT, b->main); VF_CUDA(b, upload(0, img0, base0, stride0, b->main)); }
+    { StageTimer t(b, ST_H2D_RIGHT, b->side_b); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_b)); }
     int n_launch = 0;
     {
         StageTimer t(b, ST_PYR_RIGHT, b->side_b);
-        n_launch += launch_pyramid(h.right, h.lvl_stream_stride, S, b->side_b);
+        const Level0Src src = {b->stage[1], b->stage_pitch, simg};
+        n_launch += launch_pyramid(h.right, h.lvl_stream_stride, S, b->side_b, &src);
     }
     VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
     // left chain
@@ -453,6 +456,9 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     h.cam[0] = to_cam(cfg->cam[0]); h.cam[1] = to_cam(cfg->cam[1]);
     for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.left[p], W, H, h.n_levels, S));
     TRY(alloc_pyramid(b, h.right, W, H, h.n_levels, S));
+    b->stage_pitch = align_up(W, 16);
+    for (int c = 0; c < 2; ++c) TRY(dalloc(b, &b->stage[c], (size_t)S * b->stage_pitch * H));
+    h.stage_left = b->stage[0]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
     const size_t SC = (size_t)S * cap, SP = (size_t)S * W * H;
     for (int p = 0; p < 2; ++p) {
         TRY(dalloc(b, &h.kps[p], SC)); TRY(dalloc(b, &h.ids[p], SC)); TRY(dalloc(b, &h.cnt[p], SC));
@@ -788,7 +794,7 @@ vf_status vf_op_min_eigen(const uint8_t* img, int32_t w, int32_t h, int32_t devi
     if (st != VF_OK) return st;
     vf_batch* b = bh.b;
     DeviceGuard g(b->device);
-    VF_CUDA(b, cudaMemcpy2DAsync(b->h.left[0].lvl[0], b->h.left[0].pitch[0], img, w, w, h, cudaMemcpyHostToDevice, b->main));
+    VF_CUDA(b, cudaMemcpy2DAsync(b->stage[0], b->stage_pitch, img, w, w, h, cudaMemcpyHostToDevice, b->main));
     launch_clear_frame(b->d, b->h, 0, b->main);
     launch_response_nms(b->d, b->h, 0, b->main);
     VF_CUDA(b, cudaGetLastError());
@@ -807,7 +813,7 @@ vf_status vf_op_good_features(const uint8_t* img, int32_t w, int32_t h, int32_t 
     vf_batch* b = bh.b;
     DeviceGuard g(b->device);
     const size_t npx = (size_t)w * h;
-    VF_CUDA(b, cudaMemcpy2DAsync(b->h.left[0].lvl[0], b->h.left[0].pitch[0], img, w, w, h, cudaMemcpyHostToDevice, b->main));
+    VF_CUDA(b, cudaMemcpy2DAsync(b->stage[0], b->stage_pitch, img, w, w, h, cudaMemcpyHostToDevice, b->main));
     launch_clear_frame(b->d, b->h, 0, b->main);
     launch_response_nms(b->d, b->h, 0, b->main);
     launch_bucket_scan(b->d, b->h, 0, b->main);

@@ -19,6 +19,9 @@ struct DevBatch {
     PyrView left[2];                 // left pyramids, slot = frame parity (cur) / parity^1 (prev); stream 0 base
     PyrView right;                   // right pyramid of the current frame
     size_t lvl_stream_stride[kMaxLevels];   // bytes between consecutive streams of one level
+    const uint8_t* stage_left;       // [S][H][stage_pitch] the uploaded left image, unpadded (read by the corner response)
+    int stage_pitch;
+    size_t stage_stride;
 
     float2* kps[2];                  // [parity][S][cap] current_kps_ at the end of the frame
     int* ids[2];                     // [parity][S][cap] ids_
@@ -51,7 +54,10 @@ struct DevBatch {
 };
 
 // ---- vf_pyramid.cu ----
-int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream);
+struct Level0Src {   // unpadded staging image(s): rows 16-byte aligned
+    const uint8_t* p; int pitch; size_t stride;
+};
+int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0 = nullptr);
 void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cudaStream_t stream);
 
 // ---- vf_lk.cu ----

@@ -38,8 +38,6 @@ constexpr int kTileD = 22;                   // derivative tile (window + biline
 constexpr int kJMargin = 5;                  // staged J tile = 22x22 taps + this margin on every side
 constexpr int kTileJ = 22 + 2 * kJMargin;    // 32
 constexpr int kTail = 105;                   // 21 rows x 5 tail columns
-constexpr int kSimdB = 42;                   // terms of one SIMD-lane chain of b (21 rows x 2 groups of 8 columns)
-constexpr int kTermsB = 8 * kSimdB + 2 * kTail;   // 546
 constexpr int kExact = 1 << 24;              // below this every integer is a float
 
 struct LevelRef {
@@ -73,9 +71,11 @@ struct LevelBlock {
 struct LkSmem {
     LevelRef pyr[2][kMaxLevels];
     alignas(16) uint8_t tileJ[2][kTileJ * kTileJ];
-    alignas(16) int4 part[2][kLkWarps];   // per-warp (sum tx, sum ty, sum |t|) of an iteration, double-buffered
-    alignas(16) int termsB[kTermsB + 2];  // terms of b, spilled only when the global exactness bound fails
-    float chainB[12];
+    alignas(16) int tot[3][4];            // (sum tx, sum ty, sum |t|) of an iteration, accumulated with shared atomics;
+                                          // triple-buffered: slot j%3 is used by iteration j and re-zeroed during j+1
+    alignas(16) float termsB[10 * kChainA];   // terms of b in accumulation order (chain-major, zero padded), spilled
+                                              // only when the global exactness bound fails
+    alignas(16) float chainB[12];
     int found[2];
 #ifdef VF_LK_TIMING
     unsigned long long tacc[16], tcnt[16];
@@ -86,6 +86,9 @@ struct LkSmem {
 
 static size_t lk_smem_bytes(int n_levels) { return sizeof(LkSmem) + sizeof(LevelBlock) * (size_t)(n_levels > 1 ? n_levels - 1 : 0); }
 
+#ifndef VF_LK_ABLATE
+#define VF_LK_ABLATE 0
+#endif
 #define VF_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
 
 // Optional phase timing (build with -DVF_LK_TIMING): every thread reads the clock at a mark (no divergence), thread 0
@@ -178,6 +181,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
 
     // ================= prologue: everything that depends on the source point only, all levels at once =================
     __syncthreads();   // the previous pass may still be reading the shared buffers
+    if (tid >= 224 && tid < 236) (&sm.tot[0][0])[tid - 224] = 0;   // all three slots of the iteration totals start at zero
     // ---- P1: one thread per tile row.  Threads 0..24*nlv-1: rows of the 24x24 tiles of I (level = tid / 24);
     //      warp 6: rows of the top level's 32x32 tile of J (it only depends on the start point) ----
     int jx0, jy0, jbuf = 0;
@@ -322,8 +326,11 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     }
     const int o0 = e0 < 0 ? 0 : (e0 / kWin) * kTileJ + (e0 - (e0 / kWin) * kWin);
     const int o1 = e1 < 0 ? 0 : (e1 / kWin) * kTileJ + (e1 - (e1 / kWin) * kWin);
+    const bool is_pair = tid < 168;
     bool tile_ready = true;      // the top level's J tile was staged by the prologue
-    int pbuf = 0;
+    // shared-memory addresses of the three iteration-total slots, rotated every iteration (j, j+1, j+2)
+    unsigned int slot_cur = (unsigned int)__cvta_generic_to_shared(sm.tot[0]);
+    unsigned int slot_next = slot_cur + 16, slot_nn = slot_cur + 32;
 
 #pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
@@ -347,7 +354,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         const float A11 = gA.x, A12 = gA.y, A22 = gA.z, D = gA.w;
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         // this thread's two source pixels stay in registers for the whole level
-        const int I0 = e0 >= 0 ? B.Iw[e0] : 0, I1 = e1 >= 0 ? B.Iw[e1] : 0;
+        const int I0 = B.Iw[max(e0, 0)], I1 = B.Iw[max(e1, 0)];
         const short2 g0 = e0 >= 0 ? B.dI[e0] : make_short2(0, 0), g1 = e1 >= 0 ? B.dI[e1] : make_short2(0, 0);
         {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
@@ -378,15 +385,18 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         LK_T(4);
         const uint8_t* tj = sm.tileJ[jbuf];
         float pdx = 0.f, pdy = 0.f;
+        // window origins for which the iteration needs no special handling: inside the level's search range
+        // (lkpyramid.cpp bounds test) AND covered by the staged tile.  Everything else takes the cold branch.
+        int lox = max(-kWin, jx0), hix = min(jcols - 1, jx0 + kTileJ - kTileD);
+        int loy = max(-kWin, jy0), hiy = min(jrows - 1, jy0 + kTileJ - kTileD);
 #pragma unroll 1
-        for (int j = 0; j < 30; ++j) {
+        for (int j = 0; ; ++j) {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
-            if (inx < -kWin || inx >= jcols || iny < -kWin || iny >= jrows) {
-                if (level == 0) status = 0;
-                break;
-            }
-            ++iters;
-            if (inx < jx0 || iny < jy0 || inx + kTileD > jx0 + kTileJ || iny + kTileD > jy0 + kTileJ) {
+            if (inx < lox || inx > hix || iny < loy || iny > hiy) {
+                if (inx < -kWin || inx >= jcols || iny < -kWin || iny >= jrows) {
+                    if (level == 0) status = 0;
+                    break;
+                }
                 // the window left the staged tile: re-centre it (uniform branch)
                 jx0 = inx - kJMargin; jy0 = iny - kJMargin;
                 __syncthreads();    // everybody is done with the current tile
@@ -398,7 +408,10 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                     dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
                 }
                 __syncthreads();
+                lox = max(-kWin, jx0); hix = min(jcols - 1, jx0 + kTileJ - kTileD);
+                loy = max(-kWin, jy0); hiy = min(jrows - 1, jy0 + kTileJ - kTileD);
             }
+            ++iters;
             int w00, w01, w10, w11;
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             const uint8_t* jt = tj + (iny - jy0) * kTileJ + (inx - jx0);
@@ -406,26 +419,39 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             const uint8_t* p1 = jt + o1;
             const int d0 = VF_DESCALE(p0[0] * w00 + p0[1] * w01 + p0[kTileJ] * w10 + p0[kTileJ + 1] * w11, 9) - I0;
             const int d1 = VF_DESCALE(p1[0] * w00 + p1[1] * w01 + p1[kTileJ] * w10 + p1[kTileJ + 1] * w11, 9) - I1;
-            // exact int32 products; pair threads form OpenCV's pmaddwd pair sums, tail threads keep single terms
-            const int ex0 = e0 >= 0 ? d0 * g0.x : 0, ey0 = e0 >= 0 ? d0 * g0.y : 0;
-            const int ex1 = e1 >= 0 ? d1 * g1.x : 0, ey1 = e1 >= 0 ? d1 * g1.y : 0;
+            // exact int32 products (idle threads own zero gradients); pair threads form OpenCV's pmaddwd pair sums,
+            // tail threads keep single terms
+            const int ex0 = d0 * g0.x, ey0 = d0 * g0.y, ex1 = d1 * g1.x, ey1 = d1 * g1.y;
             const int tx = ex0 + ex1, ty = ey0 + ey1;
             LK_TF(6);
-            // clamped so that the sum over the 221 contributing threads stays below 2^32 (compared unsigned)
-            const int ab = min(tid < 168 ? abs(tx) + abs(ty) : abs(ex0) + abs(ey0) + abs(ex1) + abs(ey1), kExact);
+            // sum |term| of this thread, clamped so that the total over the 221 contributing threads stays below 2^32
+            const int ab = min(is_pair ? abs(tx) + abs(ty) : abs(ex0) + abs(ey0) + abs(ex1) + abs(ey1), kExact);
+#if VF_LK_ABLATE == 1
+            int bx = tx, by = ty, bz = ab & 0xffff, bw = 0;
+#elif VF_LK_ABLATE == 2
+            const int sx = tx, sy = ty, sa = ab & 0xff;
+#else
             const int sx = __reduce_add_sync(0xffffffffu, tx);
             const int sy = __reduce_add_sync(0xffffffffu, ty);
-            const int sa = (int)__reduce_add_sync(0xffffffffu, (unsigned int)ab);
-            if (lane == 0) sm.part[pbuf][wid] = make_int4(sx, sy, sa, 0);
+            const int sa = __reduce_add_sync(0xffffffffu, ab);
+#endif
+#if VF_LK_ABLATE != 1
+            // lane 0 of every warp adds its three partial sums to the slot of this iteration (predicated, no branch)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, 0;\n\t"
+                         "@p red.shared.add.s32 [%1], %2;\n\t@p red.shared.add.s32 [%1+4], %3;\n\t@p red.shared.add.s32 [%1+8], %4;\n\t}"
+                         :: "r"(lane), "r"(slot_cur), "r"(sx), "r"(sy), "r"(sa) : "memory");
             __syncthreads();
-            int bx = 0, by = 0;
-            unsigned int bnd = 0u;
-#pragma unroll
-            for (int w = 0; w < kLkWarps; ++w) {
-                const int4 q = sm.part[pbuf][w];
-                bx += q.x; by += q.y; bnd += (unsigned int)q.z;
-            }
-            pbuf ^= 1;
+#if VF_LK_ABLATE == 3
+            int bx = tx, by = ty, bz = ab & 0xffff, bw = 0;
+#else
+            int bx, by, bz, bw;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(bx), "=r"(by), "=r"(bz), "=r"(bw) : "r"(slot_cur) : "memory");
+            asm volatile("st.shared.v4.s32 [%0], {%1, %1, %1, %1};" :: "r"(slot_nn), "r"(0) : "memory");   // slot of iteration j+2
+            { const unsigned int t3 = slot_cur; slot_cur = slot_next; slot_next = slot_nn; slot_nn = t3; }
+#endif
+#endif
+            const unsigned int bnd = (unsigned int)bz;
+            (void)bw;
             LK_TF(7);
             float ib1, ib2;
             if (bnd < (unsigned int)kExact) {
@@ -433,29 +459,43 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 ib1 = (float)bx; ib2 = (float)by;
                 ++fast;
             } else {
-                // spill the terms; examine each of the 10 chains on its own
+                // spill the terms in OpenCV's accumulation order and run the 10 ordered float chains, one lane per chain
                 if (tid < 168) {
                     const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3, slot = y * 2 + g;
-                    sm.termsB[(2 * c + 0) * kSimdB + slot] = tx;
-                    sm.termsB[(2 * c + 1) * kSimdB + slot] = ty;
+                    sm.termsB[(2 * c + 0) * kChainA + slot] = (float)tx;      // v_cvt_f32 of the pmaddwd pair sum
+                    sm.termsB[(2 * c + 1) * kChainA + slot] = (float)ty;
                 } else if (tid >= 192 && tid < 192 + 53) {
                     const int t = 2 * (tid - 192);
-                    sm.termsB[8 * kSimdB + t] = ex0; sm.termsB[8 * kSimdB + kTail + t] = ey0;
-                    if (t + 1 < kTail) { sm.termsB[8 * kSimdB + t + 1] = ex1; sm.termsB[8 * kSimdB + kTail + t + 1] = ey1; }
+                    sm.termsB[8 * kChainA + t] = (float)ex0; sm.termsB[9 * kChainA + t] = (float)ey0;
+                    if (t + 1 < kTail) { sm.termsB[8 * kChainA + t + 1] = (float)ex1; sm.termsB[9 * kChainA + t + 1] = (float)ey1; }
                 }
                 __syncthreads();
-                for (int ch = wid; ch < 10; ch += kLkWarps) {
-                    const int* src = ch < 8 ? &sm.termsB[ch * kSimdB] : &sm.termsB[8 * kSimdB + (ch - 8) * kTail];
-                    const float v = chain_value(ch < 8 ? kSimdB : kTail, [&](int k) { return src[k]; });
-                    if (lane == 0) sm.chainB[ch] = v;
+                if (wid == 0) {
+                    const float4* src = reinterpret_cast<const float4*>(sm.termsB + min(lane, 9) * kChainA);
+                    float acc = 0.f;
+                    if (lane < 8) {           // SIMD-lane chains: 42 terms (11 vector loads, zero padded)
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) {
+                            const float4 v = src[i];
+                            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+                        }
+                    } else {                  // scalar tails: 105 terms
+#pragma unroll
+                        for (int i = 0; i < kChainA / 4; ++i) {
+                            const float4 v = src[i];
+                            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+                        }
+                    }
+                    if (lane < 10) sm.chainB[lane] = acc;
                 }
                 __syncthreads();
-                const float* k = sm.chainB;
+                const float4 k0 = *reinterpret_cast<const float4*>(sm.chainB), k1 = *reinterpret_cast<const float4*>(sm.chainB + 4);
+                const float2 k2 = *reinterpret_cast<const float2*>(sm.chainB + 8);
                 // qb0+qb1 -> (s0,s1,s2,s3); ib1 += (s0+0)+(s2+0); ib2 += (s1+0)+(s3+0)
-                const float s0 = __fadd_rn(k[0], k[4]), s1 = __fadd_rn(k[1], k[5]);
-                const float s2 = __fadd_rn(k[2], k[6]), s3 = __fadd_rn(k[3], k[7]);
-                ib1 = __fadd_rn(k[8], __fadd_rn(s0, s2));
-                ib2 = __fadd_rn(k[9], __fadd_rn(s1, s3));
+                const float s0 = __fadd_rn(k0.x, k1.x), s1 = __fadd_rn(k0.y, k1.y);
+                const float s2 = __fadd_rn(k0.z, k1.z), s3 = __fadd_rn(k0.w, k1.w);
+                ib1 = __fadd_rn(k2.x, __fadd_rn(s0, s2));
+                ib2 = __fadd_rn(k2.y, __fadd_rn(s1, s3));
                 LK_TF(8);
             }
             const float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
@@ -463,16 +503,23 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, dx); ny = __fadd_rn(ny, dy);
             outx = __fadd_rn(nx, half); outy = __fadd_rn(ny, half);
-            // delta.ddot(delta) <= eps^2 in double (lkpyramid.cpp); a float estimate settles all but borderline cases
+            // The three ways out of the loop (lkpyramid.cpp, in this order), folded into ONE branch on the hot path:
+            //   delta.ddot(delta) <= eps^2 (in double; a float estimate settles all but borderline cases);
+            //   j > 0 and |delta + prevDelta| < 0.01 on both axes (std::abs on a float widened to double:
+            //       < 0.01  <=>  <= 0.01f, the largest float below 0.01) -> step back by delta/2;
+            //   maxCount = 30 iterations.
             const float ff = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-            bool conv = ff < 0.9999e-4f;
-            if (!conv && ff < 1.0001e-4f)
-                conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= 0.01 * 0.01;
-            if (conv) break;
-            // std::abs(x) < 0.01 on a float widened to double  <=>  |x| <= 0.01f (0.01f is the largest float below 0.01)
-            if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
-                outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
-                break;
+            const bool osc = j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f;
+            if (ff < 1.0001e-4f || osc || j == 29) {
+                bool conv = ff < 0.9999e-4f;
+                if (!conv && ff < 1.0001e-4f)
+                    conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= 0.01 * 0.01;
+                if (conv) break;
+                if (osc) {
+                    outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f)); outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+                    break;
+                }
+                if (j == 29) break;
             }
             pdx = dx; pdy = dy;
             LK_TF(9);
@@ -524,6 +571,8 @@ __device__ __forceinline__ void lk_smem_init(LkSmem& sm, int* counters2, int n_l
         const int level = i / (kChainsA * kPad), r = i - level * (kChainsA * kPad);
         sm.lv[level].termsA[(r / kPad) * kChainA + 84 + (r % kPad)] = 0.f;
     }
+    for (int i = threadIdx.x; i < 10 * kChainA; i += kLkThreads) sm.termsB[i] = 0.f;
+    if (threadIdx.x < 12) (&sm.tot[0][0])[threadIdx.x] = 0;
     if (threadIdx.x == 0) { counters2[0] = 0; counters2[1] = 0; }
 #ifdef VF_LK_TIMING
     if (threadIdx.x < 16) { sm.tacc[threadIdx.x] = 0; sm.tcnt[threadIdx.x] = 0; }
@@ -686,23 +735,25 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
 // ---- left camera: RemoveDistortion + ComputeKpsVelocity (:103-104, :310-363) and the left half of the record.
 //      Depends on current_kps_ / ids_ only, so it runs beside the stereo LK on the side stream. ----
 __global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity) {
+    extern __shared__ int prev_ids_sm[];   // [cap] ids_ of the previous frame
     const DevBatch& b = *bp;
     const int s = blockIdx.y, cap = b.cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
+    const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
+    const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
+    for (int j = threadIdx.x; j < n_prev; j += blockDim.x) prev_ids_sm[j] = prev_ids[j];
+    __syncthreads();
     if (i >= n) return;
     const size_t o = (size_t)s * cap + i;
     const float2 p0 = b.kps[parity][o];
     const int id = b.ids[parity][o];
     const float2 un = undistort_point(b.cam[0], p0);
-    // previous_left_un_distortion_ids_kps_map_.find(id): tracked features keep their relative order, so the match is
-    // found among the previous frame's ids by a short scan
-    const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
-    const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
+    // previous_left_un_distortion_ids_kps_map_.find(id): only features tracked from the previous frame (track count > 1)
+    // can be in it; ids are unique, so a branch-free scan of the staged id list finds the entry
     int found = -1;
     if (b.cnt[parity][o] > 1)
-        for (int j = 0; j < n_prev; ++j)
-            if (prev_ids[j] == id) { found = j; break; }
+        for (int j = 0; j < n_prev; ++j) found = prev_ids_sm[j] == id ? j : found;
     float2 v = make_float2(0.f, 0.f);
     if (found >= 0) {
         const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
@@ -765,7 +816,7 @@ void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cu
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);
-    undistort_left_kernel<<<grid, 128, 0, stream>>>(d_batch, parity);
+    undistort_left_kernel<<<grid, 128, sizeof(int) * (size_t)(h.cap > 0 ? h.cap : 1), stream>>>(d_batch, parity);
 }
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {

@@ -116,9 +116,11 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
 }
 
 // Builds levels first+1 .. first+count of a pyramid (count <= 3) in one launch.
-static void launch_pyr_fused(const PyrView& pv, const size_t* stride, int first, int count, int n_images, cudaStream_t stream) {
+static void launch_pyr_fused(const PyrView& pv, const size_t* stride, int first, int count, int n_images, cudaStream_t stream,
+                             const Level0Src* src0) {
     FusedPyrArgs a;
     a.src = pv.lvl[first]; a.sw = pv.w[first]; a.sh = pv.h[first]; a.spitch = pv.pitch[first]; a.s_stride = stride ? stride[first] : 0;
+    if (first == 0 && src0) { a.src = src0->p; a.spitch = src0->pitch; a.s_stride = src0->stride; }   // level 0 still sits in the staging buffer
     for (int k = 0; k < 3; ++k) {
         const int l = first + 1 + (k < count ? k : count - 1);
         a.dst[k] = pv.lvl[l]; a.dw[k] = pv.w[l]; a.dh[k] = pv.h[l]; a.dpitch[k] = pv.pitch[l]; a.d_stride[k] = stride ? stride[l] : 0;
@@ -146,6 +148,7 @@ struct PadArgs {
     uint8_t* lvl[kMaxLevels]; int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels]; size_t stride[kMaxLevels];
     int first_item[kMaxLevels + 1];   // prefix sum of work items (words) per level
     int n_levels;
+    Level0Src src0;                   // p != nullptr: level 0 (interior AND border) is written from this staging image
 };
 
 __host__ __device__ inline int pad_items(int w, int h, int* strip_words) {
@@ -162,6 +165,22 @@ __global__ void __launch_bounds__(256) pad_levels_kernel(PadArgs a) {
     int j = idx - a.first_item[l];
     const int w = a.w[l], h = a.h[l], pitch = a.pitch[l], F = kPyrPadFill;
     uint8_t* base = a.lvl[l] + (size_t)img * a.stride[l];
+    if (l == 0 && a.src0.p) {
+        // whole padded extent of level 0 from the staging image: rows -F..h+F-1, columns -32..w+31 (word granularity)
+        const int wpr = (w + 2 * kPyrPad + 3) / 4;
+        const int row = j / wpr - F, col = (j - (row + F) * wpr) * 4 - kPyrPad;
+        const uint8_t* srow = a.src0.p + (size_t)img * a.src0.stride + (size_t)refl101(row, h) * a.src0.pitch;
+        uint32_t v;
+        if (col >= 0 && col + 3 < w) {
+            v = *reinterpret_cast<const uint32_t*>(srow + col);      // staging rows are 16-byte aligned
+        } else {
+            v = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v |= (uint32_t)srow[refl101(col + q, w)] << (8 * q);
+        }
+        *reinterpret_cast<uint32_t*>(base + (ptrdiff_t)row * pitch + col) = v;
+        return;
+    }
     const int c0 = w & ~3;
     int strip;
     pad_items(w, h, &strip);
@@ -183,31 +202,37 @@ __global__ void __launch_bounds__(256) pad_levels_kernel(PadArgs a) {
     *reinterpret_cast<uint32_t*>(base + (ptrdiff_t)row * pitch + col) = v;   // interior origin and pitch are 16-byte aligned
 }
 
-static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream) {
+static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0) {
     PadArgs a;
     a.n_levels = pv.n_levels;
+    a.src0.p = nullptr; a.src0.pitch = 0; a.src0.stride = 0;
+    if (src0) a.src0 = *src0;
     a.first_item[0] = 0;
     for (int l = 0; l < kMaxLevels; ++l) {
         const bool ok = l < pv.n_levels;
         a.lvl[l] = ok ? pv.lvl[l] : nullptr; a.w[l] = ok ? pv.w[l] : 0; a.h[l] = ok ? pv.h[l] : 0; a.pitch[l] = ok ? pv.pitch[l] : 0;
         a.stride[l] = (ok && stride) ? stride[l] : 0;
         int strip;
-        a.first_item[l + 1] = a.first_item[l] + (ok ? pad_items(pv.w[l], pv.h[l], &strip) : 0);
+        int items = ok ? pad_items(pv.w[l], pv.h[l], &strip) : 0;
+        if (l == 0 && src0) items = (pv.h[0] + 2 * kPyrPadFill) * ((pv.w[0] + 2 * kPyrPad + 3) / 4);
+        a.first_item[l + 1] = a.first_item[l] + items;
     }
     dim3 grid((a.first_item[pv.n_levels] + 255) / 256, n_images);
     pad_levels_kernel<<<grid, 256, 0, stream>>>(a);
 }
 
 // All levels 1..n_levels-1 of a pyramid from its level 0, in ceil((n_levels-1)/3) launches, then the REFLECT_101
-// borders of all levels in one more.  Returns the launch count.
-int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream) {
+// borders of all levels in one more.  With src0 the image still sits in an unpadded staging buffer (one linear upload):
+// the first pyramid launch reads it there and the border launch also moves it into the padded level 0.
+// Returns the launch count.
+int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0) {
     int first = 0, left = pv.n_levels - 1, n = 0;
     while (left > 0) {
         const int cnt = (left == 4) ? 2 : (left < 3 ? left : 3);
-        launch_pyr_fused(pv, stride, first, cnt, n_images, stream);
+        launch_pyr_fused(pv, stride, first, cnt, n_images, stream, src0);
         first += cnt; left -= cnt; ++n;
     }
-    launch_pad_levels(pv, stride, n_images, stream);
+    launch_pad_levels(pv, stride, n_images, stream, src0);
     return n + 1;
 }
 
