@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -49,7 +50,7 @@ struct vf_tracker {
 struct vf_batch {
     vf_config cfg;
     int S = 0, device = 0;
-    cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr;
+    cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr;
     bool own_main = false, serialized = false;
     cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr,
                 ev_sel = nullptr, ev_un = nullptr;
@@ -188,10 +189,17 @@ CamParams to_cam(const vf_camera& c) {
     return p;
 }
 
+cudaError_t sync_all(vf_batch* b) {   // every stream a frame is spread over
+    cudaError_t e = cudaSuccess;
+    for (cudaStream_t st : {b->main, b->side_a, b->side_b, b->side_c})
+        if (st) { const cudaError_t r = cudaStreamSynchronize(st); if (r != cudaSuccess) e = r; }
+    return e;
+}
+
 void destroy_batch(vf_batch* b) {
     if (!b) return;
     DeviceGuard g(b->device);
-    if (b->main) cudaStreamSynchronize(b->main);
+    sync_all(b);
     for (int p = 0; p < 2; ++p) if (b->graph[p]) cudaGraphExecDestroy(b->graph[p]);
     for (void* p : b->allocs) cudaFree(p);
     if (b->d) cudaFree(b->d);
@@ -210,13 +218,14 @@ void destroy_batch(vf_batch* b) {
     for (int k = 0; k < 16; ++k) { if (b->st_beg[k]) cudaEventDestroy(b->st_beg[k]); if (b->st_end[k]) cudaEventDestroy(b->st_end[k]); }
     if (b->side_a && !b->serialized) cudaStreamDestroy(b->side_a);
     if (b->side_b && !b->serialized) cudaStreamDestroy(b->side_b);
+    if (b->side_c && !b->serialized) cudaStreamDestroy(b->side_c);
     if (b->own_main && b->main) cudaStreamDestroy(b->main);
     delete b;
 }
 
 vf_status reset_state(vf_batch* b) {
     DeviceGuard g(b->device);
-    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    VF_CUDA(b, sync_all(b));
     const size_t S = b->S;
     for (int p = 0; p < 2; ++p) {
         VF_CUDA(b, cudaMemsetAsync(b->h.counters[p], 0, sizeof(int) * S * C_COUNT, b->main));
@@ -291,9 +300,6 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     double* pt = b->pin_times + (size_t)parity * S;
     for (int s = 0; s < S; ++s) pt[s] = times[s];
     VF_CUDA(b, cudaMemcpyAsync(h.times[parity], pt, sizeof(double) * S, cudaMemcpyHostToDevice, b->main));
-    // right image + right pyramid on side B, overlapping the left chain
-    VF_CUDA(b, cudaEventRecord(b->ev_img, b->main));            // orders side B after the previous frame's lk_stereo
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_img, 0));
     for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
     // the images go up as ONE linear copy each into unpadded staging buffers (a pitched 2-D copy of 480 short rows is
     // several times slower over PCIe); the pyramid launches read them there and move level 0 into its padded home
@@ -309,12 +315,16 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         return cudaSuccess;
     };
     { StageTimer t(b, ST_H2D_LEFT, b->main); VF_CUDA(b, upload(0, img0, base0, stride0, b->main)); }
+    // right image + right pyramid on side B, overlapping the left chain; the right upload queues behind the left one so
+    // that the left image (which the frame's critical path waits for) has the link to itself
+    VF_CUDA(b, cudaEventRecord(b->ev_img, b->main));
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_img, 0));
     { StageTimer t(b, ST_H2D_RIGHT, b->side_b); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_b)); }
     int n_launch = 0;
     {
         StageTimer t(b, ST_PYR_RIGHT, b->side_b);
         const Level0Src src = {b->stage[1], b->stage_pitch, simg};
-        n_launch += launch_pyramid(h.right, h.lvl_stream_stride, S, b->side_b, &src);
+        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_b, &src);
     }
     VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
     // left chain
@@ -329,22 +339,25 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         if (st != VF_OK) return st;
     }
     n_launch += b->chain_launches;
-    // left camera undistortion + velocity beside the stereo LK (it needs current_kps_ / ids_ only)
+    // The stereo LK is not on the frame-to-frame dependency chain (frame k+1 only needs current_kps_ / ids_ of frame k),
+    // so it runs on its own stream: with asynchronous enqueues it overlaps the temporal chain of the next frame.
+    // Beside it, the left camera's undistortion + velocity (needs current_kps_ / ids_ only).
     VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_sel, 0));
     { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_a); launch_undistort_left(b->d, h, parity, b->side_a); ++n_launch; }
     VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_a));
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
-    { StageTimer t(b, ST_LK_STEREO, b->main); launch_lk_stereo(b->d, h, parity, b->main); ++n_launch; }
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_un, 0));
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
+    { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity, b->side_c); ++n_launch; }
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
     VF_CUDA(b, cudaGetLastError());
     {
-        StageTimer t(b, ST_D2H, b->main);
-        VF_CUDA(b, cudaMemcpyAsync(b->pin_out[parity], h.out, sizeof(vf_feature) * (size_t)S * h.cap, cudaMemcpyDeviceToHost, b->main));
+        StageTimer t(b, ST_D2H, b->side_c);
+        VF_CUDA(b, cudaMemcpyAsync(b->pin_out[parity], h.out[parity], sizeof(vf_feature) * (size_t)S * h.cap, cudaMemcpyDeviceToHost, b->side_c));
         VF_CUDA(b, cudaMemcpyAsync(b->pin_counters[parity], h.counters[parity], sizeof(int) * (size_t)S * C_COUNT,
-                                   cudaMemcpyDeviceToHost, b->main));
+                                   cudaMemcpyDeviceToHost, b->side_c));
     }
-    VF_CUDA(b, cudaEventRecord(b->ev_done[parity], b->main));
+    VF_CUDA(b, cudaEventRecord(b->ev_done[parity], b->side_c));
     b->launches = n_launch;
     b->last_parity = parity;
     b->frame++;
@@ -430,10 +443,11 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     if (cfg->cuda_stream) { b->main = (cudaStream_t)cfg->cuda_stream; b->own_main = false; }
     else { TRYC(cudaStreamCreateWithFlags(&b->main, cudaStreamNonBlocking)); b->own_main = true; }
     if (getenv("VF_SERIALIZE")) {   // measurement aid: one stream, no overlap between the stages of a frame
-        b->side_a = b->main; b->side_b = b->main; b->serialized = true;
+        b->side_a = b->main; b->side_b = b->main; b->side_c = b->main; b->serialized = true;
     } else {
         TRYC(cudaStreamCreateWithFlags(&b->side_a, cudaStreamNonBlocking));
         TRYC(cudaStreamCreateWithFlags(&b->side_b, cudaStreamNonBlocking));
+        TRYC(cudaStreamCreateWithFlags(&b->side_c, cudaStreamNonBlocking));
     }
     TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_resp, cudaEventDisableTiming));
@@ -455,7 +469,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     while (h.cand_cap < (size_t)W * H) h.cand_cap <<= 1;
     h.cam[0] = to_cam(cfg->cam[0]); h.cam[1] = to_cam(cfg->cam[1]);
     for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.left[p], W, H, h.n_levels, S));
-    TRY(alloc_pyramid(b, h.right, W, H, h.n_levels, S));
+    for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.right[p], W, H, h.n_levels, S));
     b->stage_pitch = align_up(W, 16);
     for (int c = 0; c < 2; ++c) TRY(dalloc(b, &b->stage[c], (size_t)S * b->stage_pitch * H));
     h.stage_left = b->stage[0]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
@@ -473,7 +487,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRY(dalloc(b, &h.hist, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start, (size_t)S * (h.n_buckets + 1)));
     TRY(dalloc(b, &h.bucket_fill, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz, (size_t)S * h.n_buckets));
     if (cap > 512) TRY(dalloc(b, &h.conflict, (size_t)S * cap * ((cap + 31) / 32)));
-    TRY(dalloc(b, &h.out, SC));
+    for (int p = 0; p < 2; ++p) TRY(dalloc(b, &h.out[p], SC));
     TRYC(cudaMalloc(&b->d, sizeof(DevBatch)));
     TRYC(cudaMemcpy(b->d, &h, sizeof(DevBatch), cudaMemcpyHostToDevice));
     for (int p = 0; p < 2; ++p) {
@@ -501,7 +515,7 @@ vf_status vf_batch_set_profiling(vf_batch* b, int32_t enable) {
     DeviceGuard g(b->device);
     if (enable && !b->st_beg[0])
         for (int k = 0; k < ST_COUNT; ++k) { VF_CUDA(b, cudaEventCreate(&b->st_beg[k])); VF_CUDA(b, cudaEventCreate(&b->st_end[k])); }
-    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    VF_CUDA(b, sync_all(b));
     b->profiling = enable != 0;
     return VF_OK;
 }
@@ -600,7 +614,7 @@ vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* b
     vf_batch* b = t->batch;
     if (b->last_parity < 0) return fail(b, VF_ERR_STATE, "debug getters are valid after the first frame");
     DeviceGuard g(b->device);
-    VF_CUDA(b, cudaStreamSynchronize(b->main));
+    VF_CUDA(b, sync_all(b));
     const DevBatch& h = b->h;
     const int s = t->stream_index, p = b->last_parity, cap = h.cap;
     int cnt_now[C_COUNT];
@@ -611,7 +625,7 @@ vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* b
     switch (what) {
         case VF_DBG_PYR_LEFT:
         case VF_DBG_PYR_RIGHT: {
-            const PyrView& pv = (what == VF_DBG_PYR_LEFT) ? h.left[p] : h.right;
+            const PyrView& pv = (what == VF_DBG_PYR_LEFT) ? h.left[p] : h.right[p];
             if (arg < 0 || arg >= pv.n_levels) return fail(b, VF_ERR_INVALID_ARG, "pyramid level out of range");
             bytes = (size_t)pv.w[arg] * pv.h[arg];
             *size_out = bytes;

@@ -17,7 +17,8 @@ struct DevBatch {
     CamParams cam[2];
 
     PyrView left[2];                 // left pyramids, slot = frame parity (cur) / parity^1 (prev); stream 0 base
-    PyrView right;                   // right pyramid of the current frame
+    PyrView right[2];                // right pyramids, slot = frame parity (the stereo LK of frame k may still read its
+                                     // pyramid while frame k+1 builds the next one)
     size_t lvl_stream_stride[kMaxLevels];   // bytes between consecutive streams of one level
     const uint8_t* stage_left;       // [S][H][stage_pitch] the uploaded left image, unpadded (read by the corner response)
     int stage_pitch;
@@ -50,7 +51,7 @@ struct DevBatch {
     int* bucket_nz;                  // [S][n_buckets] the non-empty d, ascending (counter C_N_NZ_BUCKETS)
     uint32_t* conflict;              // [S][cap][(cap+31)/32] min_dist conflict bit-matrix of select_tracked when cap > 512
 
-    vf_feature* out;                 // [S][cap] packed result records
+    vf_feature* out[2];              // [parity][S][cap] packed result records
 };
 
 // ---- vf_pyramid.cu ----

@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     const size_t o = (size_t)s * cap + i;
     lk_smem_init(sm, stat, b.n_levels);
     load_pyr(sm, 0, b.left[parity], b.lvl_stream_stride, s);   // 0 = current left
-    load_pyr(sm, 1, b.right, b.lvl_stream_stride, s);          // 1 = current right
+    load_pyr(sm, 1, b.right[parity], b.lvl_stream_stride, s);          // 1 = current right
     if (tid == 0) sm.found[1] = -1;
     __syncthreads();
     const float2 p0 = b.kps[parity][o];
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
         for (int j = tid; j < n_prev; j += kLkThreads)
             if (prev_ids[j] == id && b.right_ok[parity ^ 1][(size_t)s * cap + j]) sm.found[1] = j;
     }
-    const int L = min(b.lk_max_level, b.right.n_levels - 1);
+    const int L = min(b.lk_max_level, b.right[parity].n_levels - 1);
     const LkResult f = lk_track_point(sm, 0, 1, p0, p0, false, L, stat);
     const float2 rp = make_float2(f.x, f.y);
     float2 back = p0;
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     __syncthreads();
     if (tid == 0) {
         const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
-        vf_feature* rec = &b.out[o];
+        vf_feature* rec = &b.out[parity][o];
         rec->has_right = ok;
         float2 unr = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
         if (ok) {
@@ -759,7 +759,7 @@ __global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __r
         const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
         v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + found], dt);
     }
-    vf_feature* rec = &b.out[o];
+    vf_feature* rec = &b.out[parity][o];
     rec->id = id; rec->track_cnt = b.cnt[parity][o];
     rec->x = un.x; rec->y = un.y; rec->u = p0.x; rec->v = p0.y; rec->vx = v.x; rec->vy = v.y;
     b.un_left[parity][o] = un;
