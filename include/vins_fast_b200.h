@@ -124,6 +124,14 @@ vf_status vf_batch_track_device(vf_batch* b, const double* times, const uint8_t*
 vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
                                   size_t row_stride, size_t image_stride_bytes);
 vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out);
+/* Pipelined front-end (Estimator::FrontendTracker pushes results into feature_buf_ and the back-end consumes them later,
+ * estimator.cpp:143-158): vf_batch_enqueue starts frame k from HOST images and returns at once (at most two frames are
+ * in flight; the call blocks until frame k-2 has finished); vf_batch_fetch_lagged(b, 1, ...) then returns frame k-1 while
+ * frame k runs -- its stereo pass and download overlap the temporal chain of frame k+1.  lag 0 = vf_batch_fetch.
+ * The host images of a frame must stay valid until that frame has been fetched (or a later frame has). */
+vf_status vf_batch_enqueue(vf_batch* b, const double* times, const uint8_t* const* img0, size_t stride0,
+                           const uint8_t* const* img1, size_t stride1);
+vf_status vf_batch_fetch_lagged(vf_batch* b, int32_t lag, vf_feature* out, int32_t* n_out);
 const char* vf_batch_last_error(const vf_batch* b);
 void* vf_batch_cuda_stream(const vf_batch* b);        /* cudaStream_t the frame work is ordered on      */
 int32_t vf_batch_launches_per_frame(const vf_batch* b); /* kernels launched by the last frame            */

@@ -9,9 +9,21 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <stdexcept>
+#include <string>
 #include <vector>
+
+// Fatal errors of the host layer mirror the reference's assert / LOG(FATAL): message to stderr and std::abort();
+// define VINS_FAST_B200_THROW to get a std::runtime_error instead (used by this repository's tests).
+#ifdef VINS_FAST_B200_THROW
+#define VF_FATAL(msg) throw std::runtime_error(std::string(msg))
+#else
+#define VF_FATAL(msg) do { std::fprintf(stderr, "FATAL %s:%d: %s\n", __FILE__, __LINE__, std::string(msg).c_str()); std::abort(); } while (0)
+#endif
 
 #if !defined(VF_COMPAT_FORCE_SHIMS) && defined(__has_include)
 #if __has_include(<opencv2/core.hpp>)

@@ -31,7 +31,9 @@
 
 #include "../vins_fast_b200.h"
 #include "compat.hpp"
+#ifndef VF_USE_EXTERNAL_SETTING   // define it when the including project brings its own common::Setting (vins/common/parameter.hpp)
 #include "parameter.hpp"
+#endif
 
 namespace estimator {
 

@@ -16,12 +16,7 @@
 #include <string>
 
 #include "../vins_fast_b200.h"
-
-#ifdef VINS_FAST_B200_THROW
-#define VF_FATAL(msg) throw std::runtime_error(std::string(msg))
-#else
-#define VF_FATAL(msg) do { std::fprintf(stderr, "FATAL %s:%d: %s\n", __FILE__, __LINE__, std::string(msg).c_str()); std::abort(); } while (0)
-#endif
+#include "compat.hpp"
 
 namespace common {
 

@@ -194,3 +194,28 @@ def test_cpp_feature_tracker_drop_in(lib, oracle, euroc_frames, tmp_path):
                 v = np.frombuffer(buf, np.float64, 7, off); off += 56
                 assert gcam == cam_id and v.tobytes() == vec.tobytes(), f"frame {k} id {fid} cam {cam_id}"
     assert off == len(buf)
+
+
+def test_pipelined_enqueue_fetch_lagged(lib, oracle, euroc_frames):
+    """vf_batch_enqueue + vf_batch_fetch_lagged(1): frame k-1 is collected while frame k runs; results are the same
+    records the synchronous call returns (= the oracle's), frame after frame."""
+    import vins_fast_b200 as v
+    from vins_fast_b200 import _lib
+    cfg = v.make_config(752, 480, 150, 30, 1, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__)
+    batch = v.Batch(cfg, 1)
+    ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
+    with pytest.raises(v.VfError) as e:
+        batch.fetch(1)
+    assert e.value.status == _lib.VF_ERR_STATE
+    want = []
+    frames = euroc_frames[:10]
+    keep = []
+    for k, (t, l, r) in enumerate(frames):
+        want.append(ref.track_image(t, l, r))
+        pl, pr = (C.c_void_p * 1)(l.ctypes.data), (C.c_void_p * 1)(r.ctypes.data)
+        keep.append((pl, pr))
+        batch.enqueue_ptrs(t, pl, 752, pr, 752)
+        if k >= 1:
+            assert_frames_equal(oracle.records_to_frame(batch.fetch(1)[0]), want[k - 1], f"lagged frame {k - 1}")
+    assert_frames_equal(oracle.records_to_frame(batch.fetch(0)[0]), want[-1], "last frame")
+    batch.close()

@@ -263,3 +263,21 @@ def test_synthetic_sequence_is_deterministic_and_textured():
     t0, l0, r0 = a.frame(0)
     sha = hashlib.sha256(l0.tobytes()).hexdigest() + hashlib.sha256(r0.tobytes()).hexdigest()
     assert bytes.fromhex(sha) == g["in_sha_0"].tobytes()
+
+
+def test_cpp_header_compiles_against_the_reference_eigen(tmp_path):
+    """With the reference's vendored Eigen 3.3.7 on the include path compat.hpp uses the real Eigen::Matrix (this
+    container only: /root/reference does not exist on the GPU box)."""
+    eigen = "/root/reference/vins/thirdparty/eigen"
+    if not os.path.isdir(os.path.join(eigen, "Eigen")):
+        pytest.skip("reference tree not present")
+    cpp = tmp_path / "eig.cpp"
+    cpp.write_text('#define VINS_FAST_B200_THROW 1\n#include "vins_fast_b200/feature_tracker.hpp"\n'
+                   '#ifndef VF_HAVE_EIGEN\n#error real Eigen was not picked up\n#endif\n'
+                   'int main() { Eigen::Matrix<double, 7, 1> v; v << 1, 2, 3, 4, 5, 6, 7; estimator::FeatureTracker ft(150, 30, 1);\n'
+                   '  return v(6) == 7.0 && ft.MIN_DIST == 30 ? 0 : 1; }\n')
+    exe = tmp_path / "eig"
+    libdir = os.path.join(ROOT, "vins_fast_b200")
+    subprocess.check_call(["g++", "-std=c++14", "-w", "-I", os.path.join(ROOT, "include"), "-I", eigen, str(cpp), "-o", str(exe),
+                           "-L", libdir, "-lvinsfast_b200", "-Wl,-rpath," + libdir])
+    assert subprocess.run([str(exe)]).returncode == 0

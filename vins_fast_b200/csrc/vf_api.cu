@@ -364,10 +364,11 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     return VF_OK;
 }
 
-vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out) {
-    if (b->last_parity < 0) return fail(b, VF_ERR_STATE, "no frame has been enqueued");
+vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out, int lag = 0) {
+    if (lag < 0 || lag > 1) return fail(b, VF_ERR_INVALID_ARG, "lag must be 0 (last enqueued frame) or 1 (the one before)");
+    if (b->last_parity < 0 || b->frame <= lag) return fail(b, VF_ERR_STATE, "that frame has not been enqueued");
     DeviceGuard g(b->device);
-    const int p = b->last_parity, S = b->S, cap = b->h.cap;
+    const int p = b->last_parity ^ lag, S = b->S, cap = b->h.cap;
     VF_CUDA(b, cudaEventSynchronize(b->ev_done[p]));
     if (b->profiling) {
         VF_CUDA(b, cudaStreamSynchronize(b->side_a));
@@ -555,6 +556,18 @@ vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_
 vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out) {
     if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
     return fetch_frame(b, out, n_out);
+}
+
+vf_status vf_batch_fetch_lagged(vf_batch* b, int32_t lag, vf_feature* out, int32_t* n_out) {
+    if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
+    return fetch_frame(b, out, n_out, lag);
+}
+
+vf_status vf_batch_enqueue(vf_batch* b, const double* times, const uint8_t* const* img0, size_t stride0,
+                           const uint8_t* const* img1, size_t stride1) {
+    if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
+    if (!img0 || !img1) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
+    return enqueue_frame(b, times, img0, img1, nullptr, nullptr, 0, stride0, stride1, cudaMemcpyHostToDevice);
 }
 
 vf_status vf_batch_track_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,

@@ -223,9 +223,19 @@ class Batch:
         check(self._lib.vf_batch_enqueue_device(self._h, t.ctypes.data, d_img0, d_img1, row_stride, image_stride),
               self.last_error)
 
-    def fetch(self):
-        check(self._lib.vf_batch_fetch(self._h, self._out.ctypes.data, self._n.ctypes.data), self.last_error)
+    def fetch(self, lag: int = 0):
+        """Results of the last enqueued frame (lag 0) or of the one before it (lag 1, while the last one still runs)."""
+        check(self._lib.vf_batch_fetch_lagged(self._h, lag, self._out.ctypes.data, self._n.ctypes.data), self.last_error)
         return self._results()
+
+    def enqueue_ptrs(self, times, ptrs0, stride0: int, ptrs1, stride1: int):
+        """Starts a frame from HOST images (ctypes arrays of c_void_p) and returns at once; see vf_batch_enqueue."""
+        t = self._times(times)
+        check(self._lib.vf_batch_enqueue(self._h, t.ctypes.data, ptrs0, stride0, ptrs1, stride1), self.last_error)
+
+    def fetch_counts_lagged(self, lag: int) -> np.ndarray:
+        check(self._lib.vf_batch_fetch_lagged(self._h, lag, self._out.ctypes.data, self._n.ctypes.data), self.last_error)
+        return self._n
 
     def fetch_counts(self) -> np.ndarray:
         check(self._lib.vf_batch_fetch(self._h, self._out.ctypes.data, self._n.ctypes.data), self.last_error)
