@@ -142,6 +142,12 @@ vf_status vf_batch_set_profiling(vf_batch* b, int32_t enable);
 int32_t vf_batch_stage_count(void);
 const char* vf_batch_stage_name(int32_t i);
 vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap);
+/* Measurement aid (set VF_TRACE=1 in the environment before creating the batch): GPU-timer start / end stamps (ns) of every
+ * kernel launched since the previous call, out[2*k] = first start, out[2*k+1] = last end of kernel k (14 kernels, in
+ * the order clear, pyr_left, pad_left, lk_temporal, select_tracked, response, bucket_scan, bucket_scatter, mask_and_max,
+ * gftt_select, pyr_right, pad_right, lk_stereo, undistort_left); out[32..63] are ad-hoc phase stamps.  `cap` >= 64.
+ * Returns the kernel count, 0 when tracing is off. */
+int32_t vf_batch_trace_get(vf_batch* b, unsigned long long* out, int32_t cap);
 
 /* ---- stage-level debug getters (parity tests only; valid after a frame) --------------------------- */
 enum {

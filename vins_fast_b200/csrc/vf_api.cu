@@ -253,7 +253,7 @@ vf_status issue_left_chain(vf_batch* b, int parity) {
     {
         StageTimer t(b, ST_PYR_LEFT, b->main);
         const Level0Src src = {b->stage[0], b->stage_pitch, (size_t)b->stage_pitch * h.H};
-        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main, &src);
+        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT);
     }
     { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, b->main); ++n; }
     { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); ++n; }
@@ -324,7 +324,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     {
         StageTimer t(b, ST_PYR_RIGHT, b->side_b);
         const Level0Src src = {b->stage[1], b->stage_pitch, simg};
-        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_b, &src);
+        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_RIGHT);
     }
     VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
     // left chain
@@ -473,6 +473,12 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.right[p], W, H, h.n_levels, S));
     b->stage_pitch = align_up(W, 16);
     for (int c = 0; c < 2; ++c) TRY(dalloc(b, &b->stage[c], (size_t)S * b->stage_pitch * H));
+    if (getenv("VF_TRACE")) {   // measurement aid: per-kernel start / end stamps (read with vf_batch_trace_get)
+        TRY(dalloc(b, &h.trace, (size_t)64));
+        unsigned long long init[2 * TR_COUNT];
+        for (int k = 0; k < TR_COUNT; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+        TRYC(cudaMemcpy(h.trace, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
     h.stage_left = b->stage[0]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
     const size_t SC = (size_t)S * cap, SP = (size_t)S * W * H;
     for (int p = 0; p < 2; ++p) {
@@ -483,7 +489,8 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRY(dalloc(b, &h.fwd_pts, SC)); TRY(dalloc(b, &h.fwd_st, SC)); TRY(dalloc(b, &h.rev_pts, SC)); TRY(dalloc(b, &h.rev_st, SC));
     TRY(dalloc(b, &h.temporal_st, SC)); TRY(dalloc(b, &h.lr_pts, SC)); TRY(dalloc(b, &h.lr_st, SC)); TRY(dalloc(b, &h.rl_pts, SC));
     TRY(dalloc(b, &h.rl_st, SC)); TRY(dalloc(b, &h.sort_perm, SC)); TRY(dalloc(b, &h.lk_iters, SC)); TRY(dalloc(b, &h.lk_iters_stereo, SC));
-    TRY(dalloc(b, &h.eig, SP)); TRY(dalloc(b, &h.mask, SP));
+    TRY(dalloc(b, &h.eig, SP)); TRY(dalloc(b, &h.mask, SP)); TRY(dalloc(b, &h.lmflag, SP));
+    TRY(dalloc(b, &h.surv, (size_t)S * h.cand_cap));
     TRY(dalloc(b, &h.cand, (size_t)S * h.cand_cap)); TRY(dalloc(b, &h.cand_sorted, (size_t)S * h.cand_cap));
     TRY(dalloc(b, &h.hist, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start, (size_t)S * (h.n_buckets + 1)));
     TRY(dalloc(b, &h.bucket_fill, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz, (size_t)S * h.n_buckets));
@@ -527,6 +534,19 @@ vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap) {
     for (int k = 0; k < ST_COUNT; ++k) ms_out[k] = b->stage_ms[k];
     return VF_OK;
 }
+// Measurement aid (VF_TRACE=1 in the environment at creation): copies the [TR_COUNT][2] start / end stamps (ns) of the kernels
+// launched since the last call and re-arms the buffer.  Returns the number of kernels, 0 when tracing is off.
+int32_t vf_batch_trace_get(vf_batch* b, unsigned long long* out, int32_t cap) {
+    if (!b || !b->h.trace || !out || cap < 64) return 0;
+    DeviceGuard g(b->device);
+    if (sync_all(b) != cudaSuccess) return 0;
+    if (cudaMemcpy(out, b->h.trace, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    unsigned long long init[2 * TR_COUNT];
+    for (int k = 0; k < TR_COUNT; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+    cudaMemcpy(b->h.trace, init, sizeof(init), cudaMemcpyHostToDevice);
+    return TR_COUNT;
+}
+
 vf_status vf_batch_reset(vf_batch* b) { return b ? reset_state(b) : fail(nullptr, VF_ERR_INVALID_ARG, "batch is null"); }
 int32_t vf_batch_size(const vf_batch* b) { return b ? b->S : 0; }
 const char* vf_batch_last_error(const vf_batch* b) { return b ? b->err.c_str() : g_last_error.c_str(); }

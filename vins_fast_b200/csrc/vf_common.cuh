@@ -75,7 +75,27 @@ enum Counter {
     C_N_PREV_RIGHT_UN = 9,  // size of previous_right_un_distortion_ids_kps_map_
     C_MAXKEY = 10,      // masked max of the response, as sortable key (0 = no unmasked pixel)
     C_N_NZ_BUCKETS = 11,    // non-empty candidate buckets
+    C_N_SURV = 12,          // local maxima outside the mask (survivor list of mask_and_max)
     C_COUNT = 16
 };
+
+// Measurement aid: when a trace buffer is attached to the batch (vf_batch_set_trace), thread 0 of every CTA records the
+// kernel's first start and last end on the GPU's nanosecond timer: [id][0] = min start, [id][1] = max end.
+enum TraceId { TR_CLEAR = 0, TR_PYR_LEFT, TR_PAD_LEFT, TR_LK_TEMPORAL, TR_SELECT, TR_RESPONSE, TR_SCAN, TR_SCATTER, TR_MASK,
+               TR_GFTT, TR_PYR_RIGHT, TR_PAD_RIGHT, TR_LK_STEREO, TR_UNDISTORT_LEFT, TR_COUNT };
+#if defined(__CUDACC__)
+struct TraceScope {
+    unsigned long long* slot;
+    __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+    __device__ __forceinline__ TraceScope(unsigned long long* buf, int id) : slot(buf ? buf + 2 * id : nullptr) {
+        if (slot && threadIdx.x == 0) atomicMin(slot, now());
+    }
+    __device__ __forceinline__ ~TraceScope() { if (slot && threadIdx.x == 0) atomicMax(slot + 1, now()); }
+};
+// ad-hoc phase stamps inside a single-CTA kernel (slots 32..63 of the trace buffer)
+__device__ __forceinline__ void trace_phase(unsigned long long* buf, int k) {
+    if (buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) buf[32 + k] = TraceScope::now();
+}
+#endif
 
 }  // namespace vf

@@ -42,6 +42,8 @@ struct DevBatch {
 
     float* eig;                      // [S][H][W] cornerMinEigenVal of the current left image
     uint8_t* mask;                   // [S][H][W] SetFeatureExtractorMask
+    uint8_t* lmflag;                 // [S][H][W] 1 = 3x3 local maximum of the response (candidate of goodFeaturesToTrack)
+    unsigned long long* surv;        // [S][cand_cap] candidates outside the mask (unordered), written by mask_and_max
     unsigned long long* cand;        // [S][cand_cap] local maxima, key = float_key(eig) << 32 | raster index (unordered);
                                      //               reused as sort scratch by gftt_select once scattered
     unsigned long long* cand_sorted; // [S][cand_cap] same keys grouped by bucket, strongest bucket first
@@ -52,13 +54,15 @@ struct DevBatch {
     uint32_t* conflict;              // [S][cap][(cap+31)/32] min_dist conflict bit-matrix of select_tracked when cap > 512
 
     vf_feature* out[2];              // [parity][S][cap] packed result records
+    unsigned long long* trace;       // optional [TR_COUNT][2] kernel start / end stamps (measurement aid), else null
 };
 
 // ---- vf_pyramid.cu ----
 struct Level0Src {   // unpadded staging image(s): rows 16-byte aligned
     const uint8_t* p; int pitch; size_t stride;
 };
-int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0 = nullptr);
+int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0 = nullptr,
+                   unsigned long long* trace = nullptr, int trace_id = 0);
 void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cudaStream_t stream);
 
 // ---- vf_lk.cu ----

@@ -609,6 +609,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch*
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
     const DevBatch& b = *bp;
+    TraceScope trace(b.trace, TR_LK_TEMPORAL);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
 #ifdef VF_LK_TIMING
@@ -674,6 +675,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
     const DevBatch& b = *bp;
+    TraceScope trace(b.trace, TR_LK_STEREO);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
     const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
@@ -737,6 +739,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
 __global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity) {
     extern __shared__ int prev_ids_sm[];   // [cap] ids_ of the previous frame
     const DevBatch& b = *bp;
+    TraceScope trace(b.trace, TR_UNDISTORT_LEFT);
     const int s = blockIdx.y, cap = b.cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];

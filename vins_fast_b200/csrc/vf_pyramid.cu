@@ -21,11 +21,13 @@ namespace vf {
 struct FusedPyrArgs {
     const uint8_t* src; int sw, sh, spitch; size_t s_stride;          // input level
     uint8_t* dst[3]; int dw[3], dh[3], dpitch[3]; size_t d_stride[3];  // NL output levels
+    unsigned long long* trace; int trace_id;
 };
 
 template <int NL, int TW, int TH>
 __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
     constexpr int NT = 256;
+    TraceScope trace(a.trace, a.trace_id);
     // maximal region extents per relative level k (k = 0 input ... NL top)
     constexpr int RW3 = TW, RH3 = TH;
     constexpr int RW2 = 2 * RW3 + 3, RH2 = 2 * RH3 + 3;
@@ -117,8 +119,9 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
 
 // Builds levels first+1 .. first+count of a pyramid (count <= 3) in one launch.
 static void launch_pyr_fused(const PyrView& pv, const size_t* stride, int first, int count, int n_images, cudaStream_t stream,
-                             const Level0Src* src0) {
+                             const Level0Src* src0, unsigned long long* trace, int trace_id) {
     FusedPyrArgs a;
+    a.trace = trace; a.trace_id = trace_id;
     a.src = pv.lvl[first]; a.sw = pv.w[first]; a.sh = pv.h[first]; a.spitch = pv.pitch[first]; a.s_stride = stride ? stride[first] : 0;
     if (first == 0 && src0) { a.src = src0->p; a.spitch = src0->pitch; a.s_stride = src0->stride; }   // level 0 still sits in the staging buffer
     for (int k = 0; k < 3; ++k) {
@@ -149,6 +152,7 @@ struct PadArgs {
     int first_item[kMaxLevels + 1];   // prefix sum of work items (words) per level
     int n_levels;
     Level0Src src0;                   // p != nullptr: level 0 (interior AND border) is written from this staging image
+    unsigned long long* trace; int trace_id;
 };
 
 __host__ __device__ inline int pad_items(int w, int h, int* strip_words) {
@@ -158,6 +162,7 @@ __host__ __device__ inline int pad_items(int w, int h, int* strip_words) {
 }
 
 __global__ void __launch_bounds__(256) pad_levels_kernel(PadArgs a) {
+    TraceScope trace(a.trace, a.trace_id);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
     if (idx >= a.first_item[a.n_levels]) return;
     int l = 0;
@@ -202,8 +207,10 @@ __global__ void __launch_bounds__(256) pad_levels_kernel(PadArgs a) {
     *reinterpret_cast<uint32_t*>(base + (ptrdiff_t)row * pitch + col) = v;   // interior origin and pitch are 16-byte aligned
 }
 
-static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0) {
+static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0,
+                              unsigned long long* trace, int trace_id) {
     PadArgs a;
+    a.trace = trace; a.trace_id = trace_id;
     a.n_levels = pv.n_levels;
     a.src0.p = nullptr; a.src0.pitch = 0; a.src0.stride = 0;
     if (src0) a.src0 = *src0;
@@ -225,14 +232,15 @@ static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_ima
 // borders of all levels in one more.  With src0 the image still sits in an unpadded staging buffer (one linear upload):
 // the first pyramid launch reads it there and the border launch also moves it into the padded level 0.
 // Returns the launch count.
-int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0) {
+int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0,
+                   unsigned long long* trace, int trace_id) {
     int first = 0, left = pv.n_levels - 1, n = 0;
     while (left > 0) {
         const int cnt = (left == 4) ? 2 : (left < 3 ? left : 3);
-        launch_pyr_fused(pv, stride, first, cnt, n_images, stream, src0);
+        launch_pyr_fused(pv, stride, first, cnt, n_images, stream, src0, trace, trace_id);
         first += cnt; left -= cnt; ++n;
     }
-    launch_pad_levels(pv, stride, n_images, stream, src0);
+    launch_pad_levels(pv, stride, n_images, stream, src0, trace, trace_id + 1);
     return n + 1;
 }
 

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
     __shared__ int warp_cnt[ST_THREADS / 32];
     __shared__ int stack[3 * 40];
     const DevBatch& b = *bp;
+    TraceScope trace(b.trace, TR_SELECT);
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, cap = b.cap;
     const SelLayout L(cap);
     float2* pts = reinterpret_cast<float2*>(smem_raw + L.off_pts);
@@ -161,9 +162,11 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
         __syncthreads();
     }
 
+    trace_phase(b.trace, 8);
     // ---- 2. libstdc++ std::sort order: introsort loop (sequential replay) + stable rank (parallel) ----
     if (wid == 0) warp_introsort_loop(items, n_tr, stack, lists, lists + cap);
     __syncthreads();
+    trace_phase(b.trace, 9);
     for (int j = tid; j < n_tr; j += ST_THREADS) {
         const int kj = items[j].key;
         int r = 0;
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
     }
     __syncthreads();
 
+    trace_phase(b.trace, 10);
     // ---- 3. conflict bits: conf[r][w] bit k set iff feature 32w+k precedes r in sorted order and lies within min_dist ----
     const int R2 = b.min_dist * b.min_dist;
     for (int i = tid; i < n_tr * words; i += ST_THREADS) {
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
     }
     __syncthreads();
 
+    trace_phase(b.trace, 11);
     // ---- 4. rounds: reject if an earlier conflicting feature is accepted; accept if none is still undecided ----
     while (true) {
         bool any_undecided = false;
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
         if (!__syncthreads_or(any_undecided)) break;
     }
 
+    trace_phase(b.trace, 12);
     // ---- 5. write the kept features in sorted order ----
     int n_kept = 0;
     for (int base = 0; base < n_tr; base += ST_THREADS) {
