@@ -239,10 +239,12 @@ def main():
     n_frames = Wm + K
     times = np.arange(n_frames + 64) / 20.0
     fidx = [ping_pong(k, D) for k in range(n_frames + 64)]
-    stream = torch.cuda.Stream()
+    # the library owns its streams (the frame-to-frame chain runs on a high-priority one); the timing events are recorded
+    # on that stream, the one the kernels are launched on
     cfg = vf.make_config(W, H, MAX_CNT, MIN_DIST, FLOW_BACK, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__, lk_max_level=LEVEL,
-                         device=local, cuda_stream=stream.cuda_stream)
+                         device=local)
     batch = vf.Batch(cfg, 1)
+    stream = torch.cuda.ExternalStream(batch.cuda_stream, device=torch.device("cuda", local))
     base = d_frames.data_ptr()
 
     def barrier():
@@ -336,18 +338,19 @@ def main():
         if args.multi_streams > 0:
             S = args.multi_streams
             mb = vf.Batch(vf.make_config(W, H, MAX_CNT, MIN_DIST, FLOW_BACK, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__,
-                                         lk_max_level=LEVEL, device=local, cuda_stream=stream.cuda_stream), S)
+                                         lk_max_level=LEVEL, device=local), S)
+            mstream = torch.cuda.ExternalStream(mb.cuda_stream, device=torch.device("cuda", local))
             mt = lambda k: times[k] + np.zeros(S)
             steps_m, warm_m = 30, 5
             for k in range(warm_m):       # stream s sees frames k+s, k+s+1, ... : consecutive frames of the same sequence
                 mb.enqueue_device(mt(k), base + k * frame_bytes, base + k * frame_bytes + H * W, W, frame_bytes)
             mb.fetch_counts()
             barrier()
-            e0.record(stream)
+            e0.record(mstream)
             for k in range(warm_m, warm_m + steps_m):
                 mb.enqueue_device(mt(k), base + k * frame_bytes, base + k * frame_bytes + H * W, W, frame_bytes)
             mb.fetch_counts()
-            e1.record(stream)
+            e1.record(mstream)
             barrier()
             ms_m = max_over_ranks(e0.elapsed_time(e1))
             multi = {"streams_per_gpu": S, "steps": steps_m, "value": world * S * steps_m / (ms_m * 1e-3), "unit": "frames/s",

@@ -135,6 +135,8 @@ vf_status vf_batch_fetch_lagged(vf_batch* b, int32_t lag, vf_feature* out, int32
 const char* vf_batch_last_error(const vf_batch* b);
 void* vf_batch_cuda_stream(const vf_batch* b);        /* cudaStream_t the frame work is ordered on      */
 int32_t vf_batch_launches_per_frame(const vf_batch* b); /* kernels launched by the last frame            */
+/* Cumulative host microseconds inside the enqueue calls: out2[0] waiting for the frame two back, out2[1] issuing work. */
+void vf_batch_host_times(const vf_batch* b, double* out2);
 vf_tracker* vf_batch_stream(vf_batch* b, int32_t s);  /* borrowed view of stream s (for debug getters)  */
 /* Measurement aid: CUDA events around every kernel / copy of a frame (plain launches instead of the graph replay).
  * vf_batch_stage_times fills ms_out[vf_batch_stage_count()] with the device times of the last fetched frame. */
@@ -143,9 +145,10 @@ int32_t vf_batch_stage_count(void);
 const char* vf_batch_stage_name(int32_t i);
 vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap);
 /* Measurement aid (set VF_TRACE=1 in the environment before creating the batch): GPU-timer start / end stamps (ns) of every
- * kernel launched since the previous call, out[2*k] = first start, out[2*k+1] = last end of kernel k (14 kernels, in
- * the order clear, pyr_left, pad_left, lk_temporal, select_tracked, response, bucket_scan, bucket_scatter, mask_and_max,
- * gftt_select, pyr_right, pad_right, lk_stereo, undistort_left); out[32..63] are ad-hoc phase stamps.  `cap` >= 64.
+ * kernel launched since the previous call, out[2*(k + 16*parity)] = first start, out[.. + 1] = last end of kernel k of
+ * the frames of that parity (14 kernels, in the order clear, pyr_left, pad_left, lk_temporal, select_tracked, response,
+ * bucket_scan, bucket_scatter, mask_and_max, gftt_select, pyr_right, pad_right, lk_stereo, undistort_left);
+ * out[96..127] are ad-hoc phase stamps.  `cap` >= 128.
  * Returns the kernel count, 0 when tracing is off. */
 int32_t vf_batch_trace_get(vf_batch* b, unsigned long long* out, int32_t cap);
 

@@ -50,7 +50,7 @@ EXPORTS = [
     "vf_last_error",
     "vf_batch_create", "vf_batch_destroy", "vf_batch_reset", "vf_batch_size", "vf_batch_track", "vf_batch_track_device",
     "vf_batch_enqueue_device", "vf_batch_fetch", "vf_batch_enqueue", "vf_batch_fetch_lagged", "vf_batch_last_error", "vf_batch_cuda_stream",
-    "vf_batch_launches_per_frame", "vf_batch_stream",
+    "vf_batch_launches_per_frame", "vf_batch_host_times", "vf_batch_stream",
     "vf_batch_set_profiling", "vf_batch_stage_count", "vf_batch_stage_name", "vf_batch_stage_times", "vf_batch_trace_get",
     "vf_tracker_debug_get",
     "vf_op_build_pyramid", "vf_op_scharr", "vf_op_lk", "vf_op_min_eigen", "vf_op_good_features", "vf_op_set_mask",
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
         "vf_batch_last_error": (C.c_char_p, [P]),
         "vf_batch_cuda_stream": (P, [P]),
         "vf_batch_launches_per_frame": (I32, [P]),
+        "vf_batch_host_times": (None, [P, P]),
         "vf_batch_stream": (P, [P, I32]),
         "vf_batch_set_profiling": (I32, [P, I32]),
         "vf_batch_stage_count": (I32, []),

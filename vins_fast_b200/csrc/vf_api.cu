@@ -23,6 +23,7 @@
 // goes up and nothing but the <= max_cnt records comes down.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,8 +53,9 @@ struct vf_batch {
     int S = 0, device = 0;
     cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr;
     bool own_main = false, serialized = false;
+    double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
     cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr,
-                ev_sel = nullptr, ev_un = nullptr;
+                ev_sel = nullptr, ev_un = nullptr, ev_clear = nullptr;
     uint8_t* stage[2] = {nullptr, nullptr};   // unpadded upload targets (left, right): [S][H][stage_pitch]
     int stage_pitch = 0;
     DevBatch h;               // host copy of the device descriptor
@@ -215,6 +217,7 @@ void destroy_batch(vf_batch* b) {
     if (b->ev_img) cudaEventDestroy(b->ev_img);
     if (b->ev_sel) cudaEventDestroy(b->ev_sel);
     if (b->ev_un) cudaEventDestroy(b->ev_un);
+    if (b->ev_clear) cudaEventDestroy(b->ev_clear);
     for (int k = 0; k < 16; ++k) { if (b->st_beg[k]) cudaEventDestroy(b->st_beg[k]); if (b->st_end[k]) cudaEventDestroy(b->st_end[k]); }
     if (b->side_a && !b->serialized) cudaStreamDestroy(b->side_a);
     if (b->side_b && !b->serialized) cudaStreamDestroy(b->side_b);
@@ -242,20 +245,24 @@ vf_status reset_state(vf_batch* b) {
 vf_status issue_left_chain(vf_batch* b, int parity) {
     const DevBatch& h = b->h;
     int n = 0;
-    { StageTimer t(b, ST_CLEAR, b->main); launch_clear_frame(b->d, h, parity, b->main); ++n; }
+    // side A: clear the per-frame accumulators, then the corner response chain (reads the uploaded image only)
     VF_CUDA(b, cudaEventRecord(b->ev_fork, b->main));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_fork, 0));
+    { StageTimer t(b, ST_CLEAR, b->side_a); launch_clear_frame(b->d, h, parity, b->side_a); ++n; }
+    VF_CUDA(b, cudaEventRecord(b->ev_clear, b->side_a));
     { StageTimer t(b, ST_RESPONSE_NMS, b->side_a); launch_response_nms(b->d, h, parity, b->side_a); ++n; }
     { StageTimer t(b, ST_BUCKET_SCAN, b->side_a); launch_bucket_scan(b->d, h, parity, b->side_a); ++n; }
     { StageTimer t(b, ST_BUCKET_SCATTER, b->side_a); launch_bucket_scatter(b->d, h, parity, b->side_a); ++n; }
     VF_CUDA(b, cudaEventRecord(b->ev_resp, b->side_a));
+    // main: the pyramid of the new left image is the first thing the chain needs
     const PyrView& pv = h.left[parity];
     {
         StageTimer t(b, ST_PYR_LEFT, b->main);
         const Level0Src src = {b->stage[0], b->stage_pitch, (size_t)b->stage_pitch * h.H};
-        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT);
+        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT + 16 * parity);
     }
     { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, b->main); ++n; }
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_clear, 0));     // select_tracked writes this frame's counters
     { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); ++n; }
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_resp, 0));
     { StageTimer t(b, ST_MASK_AND_MAX, b->main); launch_mask_and_max(b->d, h, parity, b->main); ++n; }
@@ -289,7 +296,10 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     const int S = b->S, W = h.W, H = h.H, parity = (int)(b->frame & 1);
     if (!times) return fail(b, VF_ERR_INVALID_ARG, "times is null");
     // at most two frames in flight: the pinned staging of this parity was last used two frames ago
+    const auto t_wait0 = std::chrono::steady_clock::now();
     VF_CUDA(b, cudaEventSynchronize(b->ev_done[parity]));
+    const auto t_wait1 = std::chrono::steady_clock::now();
+    b->host_wait_us += std::chrono::duration<double, std::micro>(t_wait1 - t_wait0).count();
     if (stride0 < (size_t)W || stride1 < (size_t)W) return fail(b, VF_ERR_INVALID_ARG, "row stride is smaller than the image width");
     for (int s = 0; s < S; ++s) {
         const uint8_t* a = base0 ? base0 + (size_t)s * image_stride : (img0 ? img0[s] : nullptr);
@@ -324,7 +334,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     {
         StageTimer t(b, ST_PYR_RIGHT, b->side_b);
         const Level0Src src = {b->stage[1], b->stage_pitch, simg};
-        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_RIGHT);
+        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_RIGHT + 16 * parity);
     }
     VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
     // left chain
@@ -361,6 +371,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     b->launches = n_launch;
     b->last_parity = parity;
     b->frame++;
+    b->host_issue_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_wait1).count();
     return VF_OK;
 }
 
@@ -441,14 +452,23 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
 #define TRY(x) do { vf_status s__ = (x); if (s__ != VF_OK) return bail(s__); } while (0)
 #define TRYC(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { b->err = std::string(#x) + ": " + cudaGetErrorString(e__); return bail(VF_ERR_CUDA); } } while (0)
 
+    // the frame-to-frame chain (main) outranks the stereo pass (side C), which outranks the work that only has to be
+    // ready by the time the chain needs it (corner response on side A, right pyramid on side B)
+    int prio_lo = 0, prio_hi = 0;
+    TRYC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));     // numerically lower = higher priority
+    int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+    if (const char* e = getenv("VF_PRIO")) {   // measurement aid: 0 = one priority for all streams, 2 = stereo as high as main
+        if (atoi(e) == 0) { prio_hi = prio_lo; prio_mid = prio_lo; }
+        if (atoi(e) == 2) prio_mid = prio_hi;
+    }
     if (cfg->cuda_stream) { b->main = (cudaStream_t)cfg->cuda_stream; b->own_main = false; }
-    else { TRYC(cudaStreamCreateWithFlags(&b->main, cudaStreamNonBlocking)); b->own_main = true; }
+    else { TRYC(cudaStreamCreateWithPriority(&b->main, cudaStreamNonBlocking, prio_hi)); b->own_main = true; }
     if (getenv("VF_SERIALIZE")) {   // measurement aid: one stream, no overlap between the stages of a frame
         b->side_a = b->main; b->side_b = b->main; b->side_c = b->main; b->serialized = true;
     } else {
-        TRYC(cudaStreamCreateWithFlags(&b->side_a, cudaStreamNonBlocking));
-        TRYC(cudaStreamCreateWithFlags(&b->side_b, cudaStreamNonBlocking));
-        TRYC(cudaStreamCreateWithFlags(&b->side_c, cudaStreamNonBlocking));
+        TRYC(cudaStreamCreateWithPriority(&b->side_a, cudaStreamNonBlocking, prio_lo));
+        TRYC(cudaStreamCreateWithPriority(&b->side_b, cudaStreamNonBlocking, prio_lo));
+        TRYC(cudaStreamCreateWithPriority(&b->side_c, cudaStreamNonBlocking, prio_mid));
     }
     TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_resp, cudaEventDisableTiming));
@@ -456,6 +476,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRYC(cudaEventCreateWithFlags(&b->ev_img, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_un, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_clear, cudaEventDisableTiming));
     for (int p = 0; p < 2; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_done[p], cudaEventDisableTiming));
 
     DevBatch& h = b->h;
@@ -474,9 +495,9 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     b->stage_pitch = align_up(W, 16);
     for (int c = 0; c < 2; ++c) TRY(dalloc(b, &b->stage[c], (size_t)S * b->stage_pitch * H));
     if (getenv("VF_TRACE")) {   // measurement aid: per-kernel start / end stamps (read with vf_batch_trace_get)
-        TRY(dalloc(b, &h.trace, (size_t)64));
-        unsigned long long init[2 * TR_COUNT];
-        for (int k = 0; k < TR_COUNT; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+        TRY(dalloc(b, &h.trace, (size_t)128));
+        unsigned long long init[128];
+        for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
         TRYC(cudaMemcpy(h.trace, init, sizeof(init), cudaMemcpyHostToDevice));
     }
     h.stage_left = b->stage[0]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
@@ -505,6 +526,8 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRYC(cudaMallocHost(&b->pin_times, sizeof(double) * (size_t)S * 2));
     TRYC(select_tracked_prepare(cap));
     TRYC(lk_prepare());
+    TRYC(corners_prepare());
+    TRYC(pyramid_prepare());
     TRYC(cudaDeviceSynchronize());
     b->views.resize(S);
     for (int s = 0; s < S; ++s) { b->views[s].batch = b; b->views[s].stream_index = s; b->views[s].owns_batch = false; }
@@ -537,12 +560,12 @@ vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap) {
 // Measurement aid (VF_TRACE=1 in the environment at creation): copies the [TR_COUNT][2] start / end stamps (ns) of the kernels
 // launched since the last call and re-arms the buffer.  Returns the number of kernels, 0 when tracing is off.
 int32_t vf_batch_trace_get(vf_batch* b, unsigned long long* out, int32_t cap) {
-    if (!b || !b->h.trace || !out || cap < 64) return 0;
+    if (!b || !b->h.trace || !out || cap < 128) return 0;
     DeviceGuard g(b->device);
     if (sync_all(b) != cudaSuccess) return 0;
-    if (cudaMemcpy(out, b->h.trace, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-    unsigned long long init[2 * TR_COUNT];
-    for (int k = 0; k < TR_COUNT; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+    if (cudaMemcpy(out, b->h.trace, sizeof(unsigned long long) * 128, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    unsigned long long init[128];
+    for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
     cudaMemcpy(b->h.trace, init, sizeof(init), cudaMemcpyHostToDevice);
     return TR_COUNT;
 }
@@ -552,6 +575,8 @@ int32_t vf_batch_size(const vf_batch* b) { return b ? b->S : 0; }
 const char* vf_batch_last_error(const vf_batch* b) { return b ? b->err.c_str() : g_last_error.c_str(); }
 void* vf_batch_cuda_stream(const vf_batch* b) { return b ? (void*)b->main : nullptr; }
 int32_t vf_batch_launches_per_frame(const vf_batch* b) { return b ? b->launches : 0; }
+// Cumulative host microseconds spent inside the enqueue calls: [0] waiting for the frame two back, [1] issuing the frame.
+void vf_batch_host_times(const vf_batch* b, double* out2) { if (b && out2) { out2[0] = b->host_wait_us; out2[1] = b->host_issue_us; } }
 vf_tracker* vf_batch_stream(vf_batch* b, int32_t s) { return (b && s >= 0 && s < b->S) ? &b->views[s] : nullptr; }
 
 vf_status vf_batch_track(vf_batch* b, const double* times, const uint8_t* const* img0, size_t stride0,
@@ -826,6 +851,7 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(dp, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(dn, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
     VF_CUDA((vf_batch*)nullptr, lk_prepare());
+    VF_CUDA((vf_batch*)nullptr, pyramid_prepare());
     launch_lk_op(a.pv, c.pv, dp, dn, ds, di, n, max_level, use_initial_flow, 0);
     VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(next_pts, dn, sizeof(float2) * n, cudaMemcpyDeviceToHost));

@@ -12,6 +12,7 @@ constexpr int kMaxLevels = 8;        // pyramid levels 0..7 (BASELINE configs us
 constexpr int kWin = 21;             // LK window (reference: cv::Size(21,21), feature_tracker.cpp:42)
 constexpr int kWinPx = kWin * kWin;  // 441
 constexpr int kNumSms = 148;         // B200
+constexpr int kCarveout = 100;       // preferred shared-memory carveout (percent) requested by EVERY kernel of the library
 
 // One image pyramid resident in HBM.  Every level is stored with a REFLECT_101 border of kPyrPad pixels on all four
 // sides (what cv::buildOpticalFlowPyramid keeps around each level for the LK window, lkpyramid.cpp), so the LK kernels
@@ -80,7 +81,7 @@ enum Counter {
 };
 
 // Measurement aid: when a trace buffer is attached to the batch (vf_batch_set_trace), thread 0 of every CTA records the
-// kernel's first start and last end on the GPU's nanosecond timer: [id][0] = min start, [id][1] = max end.
+// kernel's first start and last end on the GPU's nanosecond timer: [id + 16 * parity][0] = min start, [..][1] = max end.
 enum TraceId { TR_CLEAR = 0, TR_PYR_LEFT, TR_PAD_LEFT, TR_LK_TEMPORAL, TR_SELECT, TR_RESPONSE, TR_SCAN, TR_SCATTER, TR_MASK,
                TR_GFTT, TR_PYR_RIGHT, TR_PAD_RIGHT, TR_LK_STEREO, TR_UNDISTORT_LEFT, TR_COUNT };
 #if defined(__CUDACC__)
@@ -92,9 +93,9 @@ struct TraceScope {
     }
     __device__ __forceinline__ ~TraceScope() { if (slot && threadIdx.x == 0) atomicMax(slot + 1, now()); }
 };
-// ad-hoc phase stamps inside a single-CTA kernel (slots 32..63 of the trace buffer)
+// ad-hoc phase stamps inside a single-CTA kernel (slots 96..127 of the trace buffer)
 __device__ __forceinline__ void trace_phase(unsigned long long* buf, int k) {
-    if (buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) buf[32 + k] = TraceScope::now();
+    if (buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) buf[96 + k] = TraceScope::now();
 }
 #endif
 

@@ -69,6 +69,8 @@ void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cu
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+cudaError_t corners_prepare();
+cudaError_t pyramid_prepare();
 cudaError_t lk_prepare();   // opt in to the LK kernels' dynamic shared memory (once per device, outside stream capture)
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream);

@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch*
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_LK_TEMPORAL);
+    TraceScope trace(b.trace, TR_LK_TEMPORAL + 16 * parity);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
 #ifdef VF_LK_TIMING
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_LK_STEREO);
+    TraceScope trace(b.trace, TR_LK_STEREO + 16 * parity);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
     const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
 __global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity) {
     extern __shared__ int prev_ids_sm[];   // [cap] ids_ of the previous frame
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_UNDISTORT_LEFT);
+    TraceScope trace(b.trace, TR_UNDISTORT_LEFT + 16 * parity);
     const int s = blockIdx.y, cap = b.cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
@@ -806,7 +806,14 @@ cudaError_t lk_prepare() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    e = cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    // same carveout as every other kernel of the library (see corners_prepare)
+    if ((e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(undistort_left_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(undistort_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout);
 }
 
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {

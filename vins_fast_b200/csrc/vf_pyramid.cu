@@ -264,4 +264,17 @@ void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cu
     scharr_s16x2_kernel<<<grid, block, 0, stream>>>(src, w, h, pitch, reinterpret_cast<short2*>(dst));
 }
 
+
+// Every kernel of the library asks for the same shared-memory carveout: kernels with different carveouts cannot be
+// co-resident on an SM (the split is reconfigured only when the SM drains), which serialises the streams of a frame.
+cudaError_t pyramid_prepare() {
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaFuncSetAttribute(pyr_fused_kernel<3, 8, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pyr_fused_kernel<2, 16, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pyr_fused_kernel<1, 32, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pad_levels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(scharr_s16x2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    return e;
+}
+
 }  // namespace vf

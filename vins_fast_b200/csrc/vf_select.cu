@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
     __shared__ int warp_cnt[ST_THREADS / 32];
     __shared__ int stack[3 * 40];
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_SELECT);
+    TraceScope trace(b.trace, TR_SELECT + 16 * parity);
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, cap = b.cap;
     const SelLayout L(cap);
     float2* pts = reinterpret_cast<float2*>(smem_raw + L.off_pts);
@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
 // outside any stream capture).
 cudaError_t select_tracked_prepare(int cap) {
     const size_t smem = select_tracked_smem_bytes(cap);
+    const cudaError_t e = cudaFuncSetAttribute(select_tracked_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout);
+    if (e != cudaSuccess) return e;
     if (smem <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(select_tracked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
