@@ -56,7 +56,7 @@ struct vf_batch {
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
     cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr,
                 ev_sel = nullptr, ev_un = nullptr, ev_clear = nullptr;
-    uint8_t* stage[2] = {nullptr, nullptr};   // unpadded upload targets (left, right): [S][H][stage_pitch]
+    uint8_t* stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // unpadded upload targets [camera][parity]: [S][H][stage_pitch]
     int stage_pitch = 0;
     DevBatch h;               // host copy of the device descriptor
     DevBatch* d = nullptr;    // device copy
@@ -258,7 +258,7 @@ vf_status issue_left_chain(vf_batch* b, int parity) {
     const PyrView& pv = h.left[parity];
     {
         StageTimer t(b, ST_PYR_LEFT, b->main);
-        const Level0Src src = {b->stage[0], b->stage_pitch, (size_t)b->stage_pitch * h.H};
+        const Level0Src src = {b->stage[0][parity], b->stage_pitch, (size_t)b->stage_pitch * h.H};
         n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT + 16 * parity);
     }
     { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, b->main); ++n; }
@@ -309,31 +309,34 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     }
     double* pt = b->pin_times + (size_t)parity * S;
     for (int s = 0; s < S; ++s) pt[s] = times[s];
-    VF_CUDA(b, cudaMemcpyAsync(h.times[parity], pt, sizeof(double) * S, cudaMemcpyHostToDevice, b->main));
     for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
+    // All uploads of the frame go through side B, in the order the frame needs them: times, left image, right image.
+    // The staging buffers are double-buffered by parity, so with asynchronous enqueues the upload of frame k+1 overlaps
+    // the chain of frame k; the main stream only waits for the left image.
+    VF_CUDA(b, cudaMemcpyAsync(h.times[parity], pt, sizeof(double) * S, cudaMemcpyHostToDevice, b->side_b));
     // the images go up as ONE linear copy each into unpadded staging buffers (a pitched 2-D copy of 480 short rows is
     // several times slower over PCIe); the pyramid launches read them there and move level 0 into its padded home
     const size_t SP = (size_t)b->stage_pitch, simg = SP * H;
     auto upload = [&](int cam, const uint8_t* const* imgs, const uint8_t* base, size_t stride, cudaStream_t st) -> cudaError_t {
         for (int s = 0; s < S; ++s) {
             const uint8_t* a = base ? base + (size_t)s * image_stride : imgs[s];
-            uint8_t* dst = b->stage[cam] + (size_t)s * simg;
+            uint8_t* dst = b->stage[cam][parity] + (size_t)s * simg;
             cudaError_t e = (stride == SP) ? cudaMemcpyAsync(dst, a, simg, kind, st)
                                            : cudaMemcpy2DAsync(dst, SP, a, stride, W, H, kind, st);
             if (e != cudaSuccess) return e;
         }
         return cudaSuccess;
     };
-    { StageTimer t(b, ST_H2D_LEFT, b->main); VF_CUDA(b, upload(0, img0, base0, stride0, b->main)); }
-    // right image + right pyramid on side B, overlapping the left chain; the right upload queues behind the left one so
-    // that the left image (which the frame's critical path waits for) has the link to itself
-    VF_CUDA(b, cudaEventRecord(b->ev_img, b->main));
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_img, 0));
+    { StageTimer t(b, ST_H2D_LEFT, b->side_b); VF_CUDA(b, upload(0, img0, base0, stride0, b->side_b)); }
+    VF_CUDA(b, cudaEventRecord(b->ev_img, b->side_b));
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
+    // right image + right pyramid, overlapping the left chain; the right upload queues behind the left one so that the
+    // left image (which the frame's critical path waits for) has the link to itself
     { StageTimer t(b, ST_H2D_RIGHT, b->side_b); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_b)); }
     int n_launch = 0;
     {
         StageTimer t(b, ST_PYR_RIGHT, b->side_b);
-        const Level0Src src = {b->stage[1], b->stage_pitch, simg};
+        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
         n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_RIGHT + 16 * parity);
     }
     VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
@@ -493,14 +496,15 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.left[p], W, H, h.n_levels, S));
     for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.right[p], W, H, h.n_levels, S));
     b->stage_pitch = align_up(W, 16);
-    for (int c = 0; c < 2; ++c) TRY(dalloc(b, &b->stage[c], (size_t)S * b->stage_pitch * H));
+    for (int c = 0; c < 2; ++c)
+        for (int p = 0; p < 2; ++p) TRY(dalloc(b, &b->stage[c][p], (size_t)S * b->stage_pitch * H));
     if (getenv("VF_TRACE")) {   // measurement aid: per-kernel start / end stamps (read with vf_batch_trace_get)
         TRY(dalloc(b, &h.trace, (size_t)128));
         unsigned long long init[128];
         for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
         TRYC(cudaMemcpy(h.trace, init, sizeof(init), cudaMemcpyHostToDevice));
     }
-    h.stage_left = b->stage[0]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
+    h.stage_left[0] = b->stage[0][0]; h.stage_left[1] = b->stage[0][1]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
     const size_t SC = (size_t)S * cap, SP = (size_t)S * W * H;
     for (int p = 0; p < 2; ++p) {
         TRY(dalloc(b, &h.kps[p], SC)); TRY(dalloc(b, &h.ids[p], SC)); TRY(dalloc(b, &h.cnt[p], SC));
@@ -867,7 +871,7 @@ vf_status vf_op_min_eigen(const uint8_t* img, int32_t w, int32_t h, int32_t devi
     if (st != VF_OK) return st;
     vf_batch* b = bh.b;
     DeviceGuard g(b->device);
-    VF_CUDA(b, cudaMemcpy2DAsync(b->stage[0], b->stage_pitch, img, w, w, h, cudaMemcpyHostToDevice, b->main));
+    VF_CUDA(b, cudaMemcpy2DAsync(b->stage[0][0], b->stage_pitch, img, w, w, h, cudaMemcpyHostToDevice, b->main));
     launch_clear_frame(b->d, b->h, 0, b->main);
     launch_response_nms(b->d, b->h, 0, b->main);
     VF_CUDA(b, cudaGetLastError());
@@ -886,7 +890,7 @@ vf_status vf_op_good_features(const uint8_t* img, int32_t w, int32_t h, int32_t 
     vf_batch* b = bh.b;
     DeviceGuard g(b->device);
     const size_t npx = (size_t)w * h;
-    VF_CUDA(b, cudaMemcpy2DAsync(b->stage[0], b->stage_pitch, img, w, w, h, cudaMemcpyHostToDevice, b->main));
+    VF_CUDA(b, cudaMemcpy2DAsync(b->stage[0][0], b->stage_pitch, img, w, w, h, cudaMemcpyHostToDevice, b->main));
     launch_clear_frame(b->d, b->h, 0, b->main);
     launch_response_nms(b->d, b->h, 0, b->main);
     launch_bucket_scan(b->d, b->h, 0, b->main);

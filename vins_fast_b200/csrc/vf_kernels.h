@@ -20,7 +20,7 @@ struct DevBatch {
     PyrView right[2];                // right pyramids, slot = frame parity (the stereo LK of frame k may still read its
                                      // pyramid while frame k+1 builds the next one)
     size_t lvl_stream_stride[kMaxLevels];   // bytes between consecutive streams of one level
-    const uint8_t* stage_left;       // [S][H][stage_pitch] the uploaded left image, unpadded (read by the corner response)
+    const uint8_t* stage_left[2];    // [parity][S][H][stage_pitch] the uploaded left image, unpadded (read by the corner response)
     int stage_pitch;
     size_t stage_stride;
 
