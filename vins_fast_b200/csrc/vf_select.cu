@@ -45,81 +45,114 @@ struct SelLayout {
 
 size_t select_tracked_smem_bytes(int cap) { return SelLayout(cap > 0 ? cap : 1).total + 64; }
 
-// std::__introsort_loop replayed by ONE WARP.  The control flow (explicit stack, depth limit, median-of-3, heap-sort
-// fallback) is the sequential algorithm of introsort_emul.h; only std::__unguarded_partition is evaluated in parallel:
+// std::__introsort_loop replayed exactly, one warp per range.  The control flow (depth limit, median-of-3, heap-sort
+// fallback, "recurse into [cut,last), continue with [first,cut)") is the sequential algorithm of introsort_emul.h; since
+// sub-ranges are disjoint, the order in which they are processed does not change the result, so every level of the
+// recursion tree is processed in parallel (one warp per pending range, ranges handed from level to level through a
+// shared-memory queue) and the chain is the tree depth (5 for 150 features) instead of the number of partitions (13).
+// std::__unguarded_partition itself is evaluated in parallel inside the warp:
 //   L = positions in (first, last) whose key does not precede the pivot's  (where the left scan stops),  ascending
 //   R = positions in (first, last) which the pivot does not precede        (where the right scan stops), descending
 //   the k-th swap of the sequential loop exchanges L[k] and R[k] for every k with L[k] < R[k]  (m of them), and the
 //   returned cut is min(L[m], R[m-1]).
-// (both scans only ever look at elements no swap has touched yet; tests/cpp/test_introsort.cpp checks this form
-//  against the real std::sort.)
-__device__ void warp_introsort_loop(SortItem* v, int n, int* stack, int* Lpos, int* Rpos) {
+// (both scans only ever look at elements no swap has touched yet; tests/cpp/test_introsort.cpp checks the sequential
+//  form against the real std::sort, the GPU tests check this form against both.)
+__device__ __forceinline__ int warp_partition_pivot(SortItem* v, int first, int last, int* Lpos, int* Rpos) {
     const int lane = threadIdx.x & 31;
     const unsigned int lt = (1u << lane) - 1u;
-    if (n <= 16) return;
-    int sp = 0;
-    if (lane == 0) { stack[0] = 0; stack[1] = n; stack[2] = 2 * floor_log2(n); }
-    sp = 3;
+    // std::__move_median_to_first(first, first+1, mid, last-1): every lane reads the three keys (broadcast loads,
+    // one round trip) and reaches the same verdict; lane 0 performs the swap
+    const int ia = first + 1, ib = first + (last - first) / 2, ic = last - 1;
+    const int ka = v[ia].key, kb = v[ib].key, kc = v[ic].key;
+    int im;
+    if (ka > kb) im = (kb > kc) ? ib : ((ka > kc) ? ic : ia);
+    else im = (ka > kc) ? ia : ((kb > kc) ? ic : ib);
+    const int pk = (im == ia) ? ka : (im == ib ? kb : kc);     // key of the pivot that ends up in v[first]
+    if (lane == 0) { const SortItem t = v[first]; v[first] = v[im]; v[im] = t; }
     __syncwarp();
-    while (sp > 0) {
-        int depth = stack[sp - 1], last = stack[sp - 2], first = stack[sp - 3];
-        sp -= 3;
-        __syncwarp();
-        while (last - first > 16) {
+    // both stopper lists from ONE pass over (first, last), 8 chunks of 32 keys in flight at a time; R is kept ascending
+    // in Rpos (the sequential right scan meets its stoppers in descending order: R[k] = Rpos[nR-1-k])
+    int nL = 0, nR = 0;
+    for (int base = first + 1; base < last; base += 256) {
+        int key[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int p = base + 32 * q + lane;
+            key[q] = p < last ? v[p].key : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int p = base + 32 * q + lane;
+            if (base + 32 * q < last) {                                   // uniform
+                const bool in = p < last;
+                const bool sl = in && !(key[q] > pk), sr = in && !(pk > key[q]);
+                const unsigned int bl = __ballot_sync(0xffffffffu, sl);
+                const unsigned int br = __ballot_sync(0xffffffffu, sr);
+                if (sl) Lpos[nL + __popc(bl & lt)] = p;
+                if (sr) Rpos[nR + __popc(br & lt)] = p;
+                nL += __popc(bl); nR += __popc(br);
+            }
+        }
+    }
+    __syncwarp();
+    const int K = min(nL, nR);
+    int m = 0;
+    for (int base = 0; base < K; base += 32) {
+        const int k = base + lane;
+        const bool ok = k < K && Lpos[k] < Rpos[nR - 1 - k];
+        const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+        if (bal == 0xffffffffu) { m += 32; continue; }
+        m += __ffs(~bal) - 1;
+        break;
+    }
+    for (int k = lane; k < m; k += 32) {
+        const int a = Lpos[k], c = Rpos[nR - 1 - k];
+        const SortItem t = v[a]; v[a] = v[c]; v[c] = t;
+    }
+    const int a_m = m < nL ? Lpos[m] : 0x7fffffff, b_prev = m > 0 ? Rpos[nR - m] : 0x7fffffff;
+    __syncwarp();
+    return min(a_m, b_prev);
+}
+
+constexpr int kSortQueue = 256;   // pending ranges of one level: at most cap / 17 (cap <= 4096)
+
+// All warps of the CTA.  queue: [2][kSortQueue] int4 (first, last, depth); qn: [2] counts; Lpos / Rpos: [cap] scratch
+// (a range only uses the slots of its own positions).
+__device__ void block_introsort_loop(SortItem* v, int n, int4* queue, int* qn, int* Lpos, int* Rpos) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        qn[0] = n > 16 ? 1 : 0; qn[1] = 0;
+        queue[0] = make_int4(0, n, 2 * floor_log2(n > 0 ? n : 1), 0);
+    }
+    __syncthreads();
+    int cur = 0;
+    while (qn[cur] > 0) {
+        const int cnt = qn[cur];
+        for (int i = wid; i < cnt; i += nw) {
+            const int4 r = queue[cur * kSortQueue + i];
+            const int first = r.x, last = r.y, depth = r.z;
             if (depth == 0) {
                 if (lane == 0) heap_sort_range(v + first, last - first);
-                __syncwarp();
-                break;
+            } else {
+                const int cut = warp_partition_pivot(v, first, last, Lpos + first, Rpos + first);
+                if (lane == 0) {
+                    if (last - cut > 16) queue[(cur ^ 1) * kSortQueue + atomicAdd(&qn[cur ^ 1], 1)] = make_int4(cut, last, depth - 1, 0);
+                    if (cut - first > 16) queue[(cur ^ 1) * kSortQueue + atomicAdd(&qn[cur ^ 1], 1)] = make_int4(first, cut, depth - 1, 0);
+                }
             }
-            --depth;
-            if (lane == 0) move_median_to_first(v, first, first + 1, first + (last - first) / 2, last - 1);
-            __syncwarp();
-            const int pk = v[first].key;
-            int nL = 0, nR = 0;
-            for (int base = first + 1; base < last; base += 32) {
-                const int p = base + lane;
-                const bool stop = p < last && !(v[p].key > pk);
-                const unsigned int bal = __ballot_sync(0xffffffffu, stop);
-                if (stop) Lpos[nL + __popc(bal & lt)] = p;
-                nL += __popc(bal);
-            }
-            for (int base = last - 1; base > first; base -= 32) {
-                const int p = base - lane;
-                const bool stop = p > first && !(pk > v[p].key);
-                const unsigned int bal = __ballot_sync(0xffffffffu, stop);
-                if (stop) Rpos[nR + __popc(bal & lt)] = p;
-                nR += __popc(bal);
-            }
-            __syncwarp();
-            const int K = min(nL, nR);
-            int m = 0;
-            for (int base = 0; base < K; base += 32) {
-                const int k = base + lane;
-                const bool ok = k < K && Lpos[k] < Rpos[k];
-                const unsigned int bal = __ballot_sync(0xffffffffu, ok);
-                if (bal == 0xffffffffu) { m += 32; continue; }
-                m += __ffs(~bal) - 1;
-                break;
-            }
-            for (int k = lane; k < m; k += 32) {
-                const int a = Lpos[k], c = Rpos[k];
-                const SortItem t = v[a]; v[a] = v[c]; v[c] = t;
-            }
-            const int a_m = m < nL ? Lpos[m] : 0x7fffffff, b_prev = m > 0 ? Rpos[m - 1] : 0x7fffffff;
-            const int cut = min(a_m, b_prev);
-            __syncwarp();
-            if (lane == 0) { stack[sp] = cut; stack[sp + 1] = last; stack[sp + 2] = depth; }
-            sp += 3;
-            last = cut;
         }
-        __syncwarp();
+        __syncthreads();
+        if (threadIdx.x == 0) qn[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
     }
 }
 
 __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBatch* __restrict__ bp, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[ST_THREADS / 32];
-    __shared__ int stack[3 * 40];
+    __shared__ int4 sort_queue[2 * kSortQueue];
+    __shared__ int sort_qn[2];
     const DevBatch& b = *bp;
     TraceScope trace(b.trace, TR_SELECT + 16 * parity);
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, cap = b.cap;
@@ -164,17 +197,24 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
 
     trace_phase(b.trace, 8);
     // ---- 2. libstdc++ std::sort order: introsort loop (sequential replay) + stable rank (parallel) ----
-    if (wid == 0) warp_introsort_loop(items, n_tr, stack, lists, lists + cap);
-    __syncthreads();
+    block_introsort_loop(items, n_tr, sort_queue, sort_qn, lists, lists + cap);
     trace_phase(b.trace, 9);
+    // stable rank by key (descending): r(j) = #{k : key_k > key_j} + #{k < j : key_k == key_j}; the keys go to a dense array
+    // first so that the n compares per thread run on vector loads with independent accumulators
+    int* dense = lists;                     // the partition's scratch is free again
+    for (int j = tid; j < ((n_tr + 3) & ~3); j += ST_THREADS) dense[j] = j < n_tr ? items[j].key : (int)0x80000000;
+    __syncthreads();
     for (int j = tid; j < n_tr; j += ST_THREADS) {
-        const int kj = items[j].key;
-        int r = 0;
-        for (int k = 0; k < n_tr; ++k) {
-            const int kk = items[k].key;
-            r += (kk > kj) || (kk == kj && k < j);
+        const int kj = dense[j];
+        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        for (int k = 0; k < n_tr; k += 4) {
+            const int4 q = *reinterpret_cast<const int4*>(dense + k);
+            r0 += (q.x > kj) || (q.x == kj && k + 0 < j);
+            r1 += (q.y > kj) || (q.y == kj && k + 1 < j);
+            r2 += (q.z > kj) || (q.z == kj && k + 2 < j);
+            r3 += (q.w > kj) || (q.w == kj && k + 3 < j);
         }
-        order[r] = items[j].payload;
+        order[(r0 + r1) + (r2 + r3)] = items[j].payload;
     }
     __syncthreads();
     for (int r = tid; r < n_tr; r += ST_THREADS) {
@@ -199,6 +239,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBat
         uint32_t bits = 0u;
         const int cx = (int)(short)(centre[r] & 0xffff), cy = centre[r] >> 16;
         const int kend = min(32, r - 32 * w);
+#pragma unroll 8
         for (int k = 0; k < kend; ++k) {
             const int c2 = centre[32 * w + k];
             const int dx = cx - (int)(short)(c2 & 0xffff), dy = cy - (c2 >> 16);
