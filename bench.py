@@ -333,6 +333,34 @@ def main():
         batch.set_profiling(False)
         stages_us = {k: v / max(n_prof, 1) * 1e3 for k, v in acc.items()}
 
+        # ---------------- kernel timeline of a synchronous frame on the GPU's own nanosecond timer ----------------
+        # (every kernel stamps its first start / last end when tracing is on: no event overhead, true launch gaps)
+        timeline = None
+        try:
+            os.environ["VF_TRACE"] = "1"
+            tb = vf.Batch(vf.make_config(W, H, MAX_CNT, MIN_DIST, FLOW_BACK, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__,
+                                         lk_max_level=LEVEL, device=local), 1)
+            del os.environ["VF_TRACE"]
+            tnames = ("clear_frame pyrdown_left pad_left lk_temporal select_tracked response_nms bucket_scan bucket_scatter "
+                      "mask_and_max gftt_select pyrdown_right pad_right lk_stereo undistort_left").split()
+            tbuf = (C.c_ulonglong * 128)()
+            tacc = []
+            for k in range(min(n_frames, Wm + 40)):
+                tb.track_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
+                vf.load().vf_batch_trace_get(tb._h, tbuf, 128)
+                if k >= Wm:
+                    a = np.array(list(tbuf), np.uint64)[:64].reshape(2, 16, 2)[k & 1, :14]
+                    tacc.append((a - a[:, 0].min()).astype(np.int64))
+            tm = np.mean(tacc, 0) / 1e3
+            timeline = {"kernels": {n: {"start_us": round(float(tm[i, 0]), 2), "end_us": round(float(tm[i, 1]), 2),
+                                        "us": round(float(tm[i, 1] - tm[i, 0]), 2)} for i, n in enumerate(tnames)},
+                        "frame_span_us": round(float(tm[:, 1].max()), 2),
+                        "note": "synchronous frames, mean of 40; t = 0 at the first kernel start; the uploads precede it"}
+            tb.close()
+        except Exception as e:  # tracing is a measurement aid; the bench line does not depend on it
+            os.environ.pop("VF_TRACE", None)
+            timeline = {"error": str(e)}
+
         # ---------------- extra: many independent streams on one GPU (BASELINE config 4 shape) ----------------
         multi = None
         if args.multi_streams > 0:
@@ -379,8 +407,10 @@ def main():
     npx = W * H
     alg_bytes = {
         "lk_stereo": lk_bytes, "lk_temporal": lk_bytes,
-        "pyrdown_left": npx * (1 + 0.25 + 0.0625) + npx * (0.25 + 0.0625 + 0.015625),   # separate level kernels: read l, write l+1
-        "pyrdown_right": npx * (1 + 0.25 + 0.0625) + npx * (0.25 + 0.0625 + 0.015625),
+        # fused pyramid (read level 0 once, write levels 1..3) + border kernel (read level 0 from staging, write the padded
+        # level 0 and the 28-pixel borders of levels 1..3)
+        "pyrdown_left": npx * 1 + npx * (0.25 + 0.0625 + 0.015625) + npx * 1 + (H + 56) * (W + 64) + 0.35 * npx,
+        "pyrdown_right": npx * 1 + npx * (0.25 + 0.0625 + 0.015625) + npx * 1 + (H + 56) * (W + 64) + 0.35 * npx,
         "response_nms": npx * 1 + npx * 4,                                            # read u8 image, write f32 response
         "mask_and_max": npx * 4 + npx * 1,                                            # read f32 response, write u8 mask
     }
@@ -411,7 +441,10 @@ def main():
                    "l2": f"inputs larger than L2: {D} distinct stereo frames = {D * frame_bytes / 2**20:.0f} MiB resident in HBM "
                          f"(L2 = 126 MiB), visited forward/backward so a frame is re-read only after all others; the tracker's "
                          f"own state (previous pyramid, 0.5 MB) is L2-resident by design",
-                   "cuda_graph": bool(cfg.use_cuda_graph)},
+                   "cuda_graph": bool(cfg.use_cuda_graph),
+                   "value_mode": "frames enqueued asynchronously (vf_batch_enqueue_device), records of every frame downloaded; the "
+                                 "stereo pass of frame k overlaps the temporal chain of frame k+1; K steps timed with CUDA events "
+                                 "on the stream the chain is launched on"},
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"], "rejected": bool(bad)},
         "e2e": {"value": e2e, "unit": "frames/s", "us_per_frame": ms_e2e / K * 1e3, "h2d_bytes_per_step": frame_bytes + 8,
@@ -421,7 +454,7 @@ def main():
                               "mode": "vf_batch_enqueue(k) + vf_batch_fetch_lagged(1): frame k-1 is collected while frame k runs; "
                                       "same H2D / D2H bytes per frame, host wall clock"}},
         "gpu_launches": launches, "launches_per_frame": batch.launches_per_frame,
-        "stages_us": stages_us, "roofline": roofline, "multi_stream": multi,
+        "stages_us": stages_us, "timeline": timeline, "roofline": roofline, "multi_stream": multi,
         "lk": {"iterations_per_frame": (iters_t + iters_s) / max(n_prof, 1),
                "exact_integer_path_fraction": fast_it / max(iters_t + iters_s, 1)},
     }

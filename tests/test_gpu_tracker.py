@@ -219,3 +219,12 @@ def test_pipelined_enqueue_fetch_lagged(lib, oracle, euroc_frames):
             assert_frames_equal(oracle.records_to_frame(batch.fetch(1)[0]), want[k - 1], f"lagged frame {k - 1}")
     assert_frames_equal(oracle.records_to_frame(batch.fetch(0)[0]), want[-1], "last frame")
     batch.close()
+
+
+def test_4k_2000_features_level5(lib, oracle):
+    """BASELINE config 5: 3840x2160 stereo, max_cnt 2000, maxLevel 5 (6 pyramid levels, 16-bit candidate buckets, the
+    conflict matrix of the min_dist keep in global memory)."""
+    from vins_fast_b200.synth import StereoSequence
+    seq = StereoSequence(3, 3840, 2160)
+    cam = pinhole_for(3840, 2160)
+    _run_pair(oracle, [seq.frame(k) for k in range(3)], 3840, 2160, 2000, 30, 1, cam, cam, level=5)

@@ -54,7 +54,7 @@ struct vf_batch {
     cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr;
     bool own_main = false, serialized = false;
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
-    cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[2] = {nullptr, nullptr}, ev_img = nullptr,
+    cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
                 ev_sel = nullptr, ev_un = nullptr, ev_clear = nullptr;
     uint8_t* stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // unpadded upload targets [camera][parity]: [S][H][stage_pitch]
     int stage_pitch = 0;
@@ -209,6 +209,7 @@ void destroy_batch(vf_batch* b) {
         if (b->pin_out[p]) cudaFreeHost(b->pin_out[p]);
         if (b->pin_counters[p]) cudaFreeHost(b->pin_counters[p]);
         if (b->ev_done[p]) cudaEventDestroy(b->ev_done[p]);
+        if (b->ev_done[p + 2]) cudaEventDestroy(b->ev_done[p + 2]);
     }
     if (b->pin_times) cudaFreeHost(b->pin_times);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
@@ -295,9 +296,12 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     const DevBatch& h = b->h;
     const int S = b->S, W = h.W, H = h.H, parity = (int)(b->frame & 1);
     if (!times) return fail(b, VF_ERR_INVALID_ARG, "times is null");
-    // at most two frames in flight: the pinned staging of this parity was last used two frames ago
+    // Buffers are double-buffered by parity: everything frame k overwrites was last used by frame k-2, whose completion
+    // (stereo pass + download) the GPU streams wait for below.  The host itself only throttles at four frames ahead, so
+    // that issuing frame k+1 never has to wait for the GPU to drain (the completion events form a ring of four).
+    const int slot = (int)(b->frame & 3);
     const auto t_wait0 = std::chrono::steady_clock::now();
-    VF_CUDA(b, cudaEventSynchronize(b->ev_done[parity]));
+    VF_CUDA(b, cudaEventSynchronize(b->ev_done[slot]));                      // frame k-4
     const auto t_wait1 = std::chrono::steady_clock::now();
     b->host_wait_us += std::chrono::duration<double, std::micro>(t_wait1 - t_wait0).count();
     if (stride0 < (size_t)W || stride1 < (size_t)W) return fail(b, VF_ERR_INVALID_ARG, "row stride is smaller than the image width");
@@ -307,7 +311,11 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         // the reference asserts both images are non-empty (stereo only): feature_tracker.cpp:30
         if (!a || !c) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
     }
-    double* pt = b->pin_times + (size_t)parity * S;
+    if (b->frame >= 2) {                                                     // frame k-2 (same parity) must be complete on the GPU
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 2) & 3], 0));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_done[(slot + 2) & 3], 0));
+    }
+    double* pt = b->pin_times + (size_t)slot * S;
     for (int s = 0; s < S; ++s) pt[s] = times[s];
     for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
     // All uploads of the frame go through side B, in the order the frame needs them: times, left image, right image.
@@ -370,7 +378,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaMemcpyAsync(b->pin_counters[parity], h.counters[parity], sizeof(int) * (size_t)S * C_COUNT,
                                    cudaMemcpyDeviceToHost, b->side_c));
     }
-    VF_CUDA(b, cudaEventRecord(b->ev_done[parity], b->side_c));
+    VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->side_c));
     b->launches = n_launch;
     b->last_parity = parity;
     b->frame++;
@@ -383,7 +391,7 @@ vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out, int lag = 0)
     if (b->last_parity < 0 || b->frame <= lag) return fail(b, VF_ERR_STATE, "that frame has not been enqueued");
     DeviceGuard g(b->device);
     const int p = b->last_parity ^ lag, S = b->S, cap = b->h.cap;
-    VF_CUDA(b, cudaEventSynchronize(b->ev_done[p]));
+    VF_CUDA(b, cudaEventSynchronize(b->ev_done[(int)((b->frame - 1 - lag) & 3)]));
     if (b->profiling) {
         VF_CUDA(b, cudaStreamSynchronize(b->side_a));
         VF_CUDA(b, cudaStreamSynchronize(b->side_b));
@@ -480,7 +488,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRYC(cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_un, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_clear, cudaEventDisableTiming));
-    for (int p = 0; p < 2; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_done[p], cudaEventDisableTiming));
+    for (int p = 0; p < 4; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_done[p], cudaEventDisableTiming));
 
     DevBatch& h = b->h;
     memset(&h, 0, sizeof(h));
@@ -527,7 +535,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
         TRYC(cudaMallocHost(&b->pin_out[p], sizeof(vf_feature) * SC));
         TRYC(cudaMallocHost(&b->pin_counters[p], sizeof(int) * (size_t)S * C_COUNT));
     }
-    TRYC(cudaMallocHost(&b->pin_times, sizeof(double) * (size_t)S * 2));
+    TRYC(cudaMallocHost(&b->pin_times, sizeof(double) * (size_t)S * 4));
     TRYC(select_tracked_prepare(cap));
     TRYC(lk_prepare());
     TRYC(corners_prepare());
