@@ -145,10 +145,10 @@ int32_t vf_batch_stage_count(void);
 const char* vf_batch_stage_name(int32_t i);
 vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap);
 /* Measurement aid (set VF_TRACE=1 in the environment before creating the batch): GPU-timer start / end stamps (ns) of every
- * kernel launched since the previous call, out[2*(k + 16*parity)] = first start, out[.. + 1] = last end of kernel k of
- * the frames of that parity (14 kernels, in the order clear, pyr_left, pad_left, lk_temporal, select_tracked, response,
+ * kernel launched since the previous call, out[2*(k + 16*(frame % 6))] = first start, out[.. + 1] = last end of kernel k
+ * of that frame (14 kernels, in the order clear, pyr_left, pad_left, lk_temporal, select_tracked, response,
  * bucket_scan, bucket_scatter, mask_and_max, gftt_select, pyr_right, pad_right, lk_stereo, undistort_left);
- * out[96..127] are ad-hoc phase stamps.  `cap` >= 128.
+ * out[224..255] are ad-hoc phase stamps.  `cap` >= 256.
  * Returns the kernel count, 0 when tracing is off. */
 int32_t vf_batch_trace_get(vf_batch* b, unsigned long long* out, int32_t cap);
 

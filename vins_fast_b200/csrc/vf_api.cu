@@ -51,11 +51,12 @@ struct vf_tracker {
 struct vf_batch {
     vf_config cfg;
     int S = 0, device = 0;
-    cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr;
+    cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr, side_d = nullptr;
     bool own_main = false, serialized = false;
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
     cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
-                ev_sel = nullptr, ev_un = nullptr, ev_clear = nullptr;
+                ev_sel = nullptr, ev_un = nullptr, ev_clear = nullptr, ev_pyrl = nullptr, ev_scat = nullptr,
+                ev_chain[2] = {nullptr, nullptr};
     uint8_t* stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // unpadded upload targets [camera][parity]: [S][H][stage_pitch]
     int stage_pitch = 0;
     DevBatch h;               // host copy of the device descriptor
@@ -66,7 +67,7 @@ struct vf_batch {
     double* pin_times = nullptr;
     long frame = 0;
     int last_parity = -1;
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per frame % 6 (parity x pyramid ring slot)
     int launches = 0, chain_launches = 0;
     std::string err;
     std::vector<vf_tracker> views;
@@ -193,7 +194,7 @@ CamParams to_cam(const vf_camera& c) {
 
 cudaError_t sync_all(vf_batch* b) {   // every stream a frame is spread over
     cudaError_t e = cudaSuccess;
-    for (cudaStream_t st : {b->main, b->side_a, b->side_b, b->side_c})
+    for (cudaStream_t st : {b->main, b->side_a, b->side_b, b->side_c, b->side_d})
         if (st) { const cudaError_t r = cudaStreamSynchronize(st); if (r != cudaSuccess) e = r; }
     return e;
 }
@@ -202,7 +203,7 @@ void destroy_batch(vf_batch* b) {
     if (!b) return;
     DeviceGuard g(b->device);
     sync_all(b);
-    for (int p = 0; p < 2; ++p) if (b->graph[p]) cudaGraphExecDestroy(b->graph[p]);
+    for (int p = 0; p < 6; ++p) if (b->graph[p]) cudaGraphExecDestroy(b->graph[p]);
     for (void* p : b->allocs) cudaFree(p);
     if (b->d) cudaFree(b->d);
     for (int p = 0; p < 2; ++p) {
@@ -219,10 +220,14 @@ void destroy_batch(vf_batch* b) {
     if (b->ev_sel) cudaEventDestroy(b->ev_sel);
     if (b->ev_un) cudaEventDestroy(b->ev_un);
     if (b->ev_clear) cudaEventDestroy(b->ev_clear);
+    if (b->ev_pyrl) cudaEventDestroy(b->ev_pyrl);
+    if (b->ev_scat) cudaEventDestroy(b->ev_scat);
+    for (int p = 0; p < 2; ++p) if (b->ev_chain[p]) cudaEventDestroy(b->ev_chain[p]);
     for (int k = 0; k < 16; ++k) { if (b->st_beg[k]) cudaEventDestroy(b->st_beg[k]); if (b->st_end[k]) cudaEventDestroy(b->st_end[k]); }
     if (b->side_a && !b->serialized) cudaStreamDestroy(b->side_a);
     if (b->side_b && !b->serialized) cudaStreamDestroy(b->side_b);
     if (b->side_c && !b->serialized) cudaStreamDestroy(b->side_c);
+    if (b->side_d && !b->serialized) cudaStreamDestroy(b->side_d);
     if (b->own_main && b->main) cudaStreamDestroy(b->main);
     delete b;
 }
@@ -243,8 +248,9 @@ vf_status reset_state(vf_batch* b) {
 }
 
 // The kernels of the left chain, issued on main/side_a (directly, or under stream capture).
-vf_status issue_left_chain(vf_batch* b, int parity) {
+vf_status issue_left_chain(vf_batch* b, int parity_, int cur, int prev, int phase) {
     const DevBatch& h = b->h;
+    const int parity = parity_ | (phase << 4);   // kernels take the frame parity in bit 0 and the trace slot above it
     int n = 0;
     // side A: clear the per-frame accumulators, then the corner response chain (reads the uploaded image only)
     VF_CUDA(b, cudaEventRecord(b->ev_fork, b->main));
@@ -252,37 +258,36 @@ vf_status issue_left_chain(vf_batch* b, int parity) {
     { StageTimer t(b, ST_CLEAR, b->side_a); launch_clear_frame(b->d, h, parity, b->side_a); ++n; }
     VF_CUDA(b, cudaEventRecord(b->ev_clear, b->side_a));
     { StageTimer t(b, ST_RESPONSE_NMS, b->side_a); launch_response_nms(b->d, h, parity, b->side_a); ++n; }
+    VF_CUDA(b, cudaEventRecord(b->ev_resp, b->side_a));          // the mask stage needs the response map and the candidate flags
     { StageTimer t(b, ST_BUCKET_SCAN, b->side_a); launch_bucket_scan(b->d, h, parity, b->side_a); ++n; }
     { StageTimer t(b, ST_BUCKET_SCATTER, b->side_a); launch_bucket_scatter(b->d, h, parity, b->side_a); ++n; }
-    VF_CUDA(b, cudaEventRecord(b->ev_resp, b->side_a));
-    // main: the pyramid of the new left image is the first thing the chain needs
-    const PyrView& pv = h.left[parity];
-    {
-        StageTimer t(b, ST_PYR_LEFT, b->main);
-        const Level0Src src = {b->stage[0][parity], b->stage_pitch, (size_t)b->stage_pitch * h.H};
-        n += launch_pyramid(pv, h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT + 16 * parity);
-    }
-    { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, b->main); ++n; }
+    VF_CUDA(b, cudaEventRecord(b->ev_scat, b->side_a));          // only the corner selection (bucket walk) needs the buckets
+    // main: the frame-to-frame chain proper (the pyramid of the new left image was built on side B, possibly while the
+    // previous frame was still on the chain)
+    { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); ++n; }
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_clear, 0));     // select_tracked writes this frame's counters
     { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); ++n; }
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_resp, 0));
     { StageTimer t(b, ST_MASK_AND_MAX, b->main); launch_mask_and_max(b->d, h, parity, b->main); ++n; }
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
     { StageTimer t(b, ST_GFTT_SELECT, b->main); launch_gftt_select(b->d, h, parity, b->main); ++n; }
     VF_CUDA(b, cudaGetLastError());
     b->chain_launches = n;
     return VF_OK;
 }
 
-vf_status build_graph(vf_batch* b, int parity) {
+vf_status build_graph(vf_batch* b, int phase) {   // phase = frame % 6
     cudaGraph_t graph = nullptr;
+    const int parity = phase & 1, cur = phase % 3, prev = (phase + 2) % 3;
     VF_CUDA(b, cudaStreamBeginCapture(b->main, cudaStreamCaptureModeThreadLocal));
-    vf_status st = issue_left_chain(b, parity);
+    vf_status st = issue_left_chain(b, parity, cur, prev, phase);
     cudaError_t e = cudaStreamEndCapture(b->main, &graph);
     if (st != VF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
     VF_CUDA(b, e);
-    e = cudaGraphInstantiate(&b->graph[parity], graph, 0);
+    e = cudaGraphInstantiate(&b->graph[phase], graph, 0);
     cudaGraphDestroy(graph);
     VF_CUDA(b, e);
+    VF_CUDA(b, cudaGraphUpload(b->graph[phase], b->main));   // keep the executable resident on the device: shorter launch latency
     return VF_OK;
 }
 
@@ -295,6 +300,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     if (!g.ok) return fail(b, VF_ERR_CUDA, "cudaSetDevice failed");
     const DevBatch& h = b->h;
     const int S = b->S, W = h.W, H = h.H, parity = (int)(b->frame & 1);
+    const int phase = (int)(b->frame % 6), cur = phase % 3, prev = (phase + 2) % 3;   // slots of the left pyramid ring
     if (!times) return fail(b, VF_ERR_INVALID_ARG, "times is null");
     // Buffers are double-buffered by parity: everything frame k overwrites was last used by frame k-2, whose completion
     // (stereo pass + download) the GPU streams wait for below.  The host itself only throttles at four frames ahead, so
@@ -311,9 +317,14 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         // the reference asserts both images are non-empty (stereo only): feature_tracker.cpp:30
         if (!a || !c) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
     }
-    if (b->frame >= 2) {                                                     // frame k-2 (same parity) must be complete on the GPU
+    if (b->frame >= 2) {
+        // frame k-2 (same parity) must be complete on the GPU before the chain and the right pyramid overwrite its buffers
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 2) & 3], 0));
-        VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_done[(slot + 2) & 3], 0));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_done[(slot + 2) & 3], 0));
+        // the left upload + pyramid only reuse what the CHAIN of frame k-2 read (staging image) and what the stereo pass of
+        // frame k-3 read (slot k % 3 of the pyramid ring): they may run while frame k-2's stereo pass is still going
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_chain[parity], 0));
+        if (b->frame >= 3) VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_done[(slot + 1) & 3], 0));
     }
     double* pt = b->pin_times + (size_t)slot * S;
     for (int s = 0; s < S; ++s) pt[s] = times[s];
@@ -337,26 +348,36 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     };
     { StageTimer t(b, ST_H2D_LEFT, b->side_b); VF_CUDA(b, upload(0, img0, base0, stride0, b->side_b)); }
     VF_CUDA(b, cudaEventRecord(b->ev_img, b->side_b));
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
-    // right image + right pyramid, overlapping the left chain; the right upload queues behind the left one so that the
-    // left image (which the frame's critical path waits for) has the link to itself
-    { StageTimer t(b, ST_H2D_RIGHT, b->side_b); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_b)); }
+    // left pyramid on side B right behind its upload: it does not depend on the previous frame, so with asynchronous
+    // enqueues it is built while the previous frame is still on the chain
     int n_launch = 0;
     {
-        StageTimer t(b, ST_PYR_RIGHT, b->side_b);
-        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
-        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_RIGHT + 16 * parity);
+        StageTimer t(b, ST_PYR_LEFT, b->side_b);
+        const Level0Src src = {b->stage[0][parity], b->stage_pitch, simg};
+        n_launch += launch_pyramid(h.left[cur], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_LEFT + 16 * phase);
     }
-    VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_b));
+    VF_CUDA(b, cudaEventRecord(b->ev_pyrl, b->side_b));
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));     // the corner response reads the staging image
+    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_pyrl, 0));
+    // right image + right pyramid on side D; the right upload queues behind the left one so that the left image (which
+    // the frame's critical path waits for) has the link to itself
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_img, 0));
+    { StageTimer t(b, ST_H2D_RIGHT, b->side_d); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_d)); }
+    {
+        StageTimer t(b, ST_PYR_RIGHT, b->side_d);
+        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
+        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_d, &src, h.trace, TR_PYR_RIGHT + 16 * phase);
+    }
+    VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
     // left chain
     if (b->cfg.use_cuda_graph && !b->profiling) {
-        if (!b->graph[parity]) {
-            vf_status st = build_graph(b, parity);
+        if (!b->graph[phase]) {
+            vf_status st = build_graph(b, phase);
             if (st != VF_OK) return st;
         }
-        VF_CUDA(b, cudaGraphLaunch(b->graph[parity], b->main));
+        VF_CUDA(b, cudaGraphLaunch(b->graph[phase], b->main));
     } else {
-        vf_status st = issue_left_chain(b, parity);
+        vf_status st = issue_left_chain(b, parity, cur, prev, phase);
         if (st != VF_OK) return st;
     }
     n_launch += b->chain_launches;
@@ -364,12 +385,13 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     // so it runs on its own stream: with asynchronous enqueues it overlaps the temporal chain of the next frame.
     // Beside it, the left camera's undistortion + velocity (needs current_kps_ / ids_ only).
     VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
+    VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_sel, 0));
-    { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_a); launch_undistort_left(b->d, h, parity, b->side_a); ++n_launch; }
+    { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_a); launch_undistort_left(b->d, h, parity | (phase << 4), b->side_a); ++n_launch; }
     VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_a));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
-    { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity, b->side_c); ++n_launch; }
+    { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, b->side_c); ++n_launch; }
     VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
     VF_CUDA(b, cudaGetLastError());
     {
@@ -393,8 +415,7 @@ vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out, int lag = 0)
     const int p = b->last_parity ^ lag, S = b->S, cap = b->h.cap;
     VF_CUDA(b, cudaEventSynchronize(b->ev_done[(int)((b->frame - 1 - lag) & 3)]));
     if (b->profiling) {
-        VF_CUDA(b, cudaStreamSynchronize(b->side_a));
-        VF_CUDA(b, cudaStreamSynchronize(b->side_b));
+        VF_CUDA(b, sync_all(b));
         for (int k = 0; k < ST_COUNT; ++k) {
             b->stage_ms[k] = 0.f;
             if (b->st_used[k]) cudaEventElapsedTime(&b->stage_ms[k], b->st_beg[k], b->st_end[k]);
@@ -475,10 +496,11 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     if (cfg->cuda_stream) { b->main = (cudaStream_t)cfg->cuda_stream; b->own_main = false; }
     else { TRYC(cudaStreamCreateWithPriority(&b->main, cudaStreamNonBlocking, prio_hi)); b->own_main = true; }
     if (getenv("VF_SERIALIZE")) {   // measurement aid: one stream, no overlap between the stages of a frame
-        b->side_a = b->main; b->side_b = b->main; b->side_c = b->main; b->serialized = true;
+        b->side_a = b->main; b->side_b = b->main; b->side_c = b->main; b->side_d = b->main; b->serialized = true;
     } else {
         TRYC(cudaStreamCreateWithPriority(&b->side_a, cudaStreamNonBlocking, prio_lo));
-        TRYC(cudaStreamCreateWithPriority(&b->side_b, cudaStreamNonBlocking, prio_lo));
+        TRYC(cudaStreamCreateWithPriority(&b->side_b, cudaStreamNonBlocking, prio_hi));    // left pyramid: the chain waits for it
+        TRYC(cudaStreamCreateWithPriority(&b->side_d, cudaStreamNonBlocking, prio_lo));
         TRYC(cudaStreamCreateWithPriority(&b->side_c, cudaStreamNonBlocking, prio_mid));
     }
     TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
@@ -488,6 +510,9 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRYC(cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_un, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_clear, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_pyrl, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_scat, cudaEventDisableTiming));
+    for (int p = 0; p < 2; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_chain[p], cudaEventDisableTiming));
     for (int p = 0; p < 4; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_done[p], cudaEventDisableTiming));
 
     DevBatch& h = b->h;
@@ -501,15 +526,15 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     h.cand_cap = 1;
     while (h.cand_cap < (size_t)W * H) h.cand_cap <<= 1;
     h.cam[0] = to_cam(cfg->cam[0]); h.cam[1] = to_cam(cfg->cam[1]);
-    for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.left[p], W, H, h.n_levels, S));
+    for (int p = 0; p < 3; ++p) TRY(alloc_pyramid(b, h.left[p], W, H, h.n_levels, S));
     for (int p = 0; p < 2; ++p) TRY(alloc_pyramid(b, h.right[p], W, H, h.n_levels, S));
     b->stage_pitch = align_up(W, 16);
     for (int c = 0; c < 2; ++c)
         for (int p = 0; p < 2; ++p) TRY(dalloc(b, &b->stage[c][p], (size_t)S * b->stage_pitch * H));
     if (getenv("VF_TRACE")) {   // measurement aid: per-kernel start / end stamps (read with vf_batch_trace_get)
-        TRY(dalloc(b, &h.trace, (size_t)128));
-        unsigned long long init[128];
-        for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+        TRY(dalloc(b, &h.trace, (size_t)256));
+        unsigned long long init[256];
+        for (int k = 0; k < 128; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
         TRYC(cudaMemcpy(h.trace, init, sizeof(init), cudaMemcpyHostToDevice));
     }
     h.stage_left[0] = b->stage[0][0]; h.stage_left[1] = b->stage[0][1]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
@@ -572,12 +597,12 @@ vf_status vf_batch_stage_times(vf_batch* b, float* ms_out, int32_t cap) {
 // Measurement aid (VF_TRACE=1 in the environment at creation): copies the [TR_COUNT][2] start / end stamps (ns) of the kernels
 // launched since the last call and re-arms the buffer.  Returns the number of kernels, 0 when tracing is off.
 int32_t vf_batch_trace_get(vf_batch* b, unsigned long long* out, int32_t cap) {
-    if (!b || !b->h.trace || !out || cap < 128) return 0;
+    if (!b || !b->h.trace || !out || cap < 256) return 0;
     DeviceGuard g(b->device);
     if (sync_all(b) != cudaSuccess) return 0;
-    if (cudaMemcpy(out, b->h.trace, sizeof(unsigned long long) * 128, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
-    unsigned long long init[128];
-    for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+    if (cudaMemcpy(out, b->h.trace, sizeof(unsigned long long) * 256, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    unsigned long long init[256];
+    for (int k = 0; k < 128; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
     cudaMemcpy(b->h.trace, init, sizeof(init), cudaMemcpyHostToDevice);
     return TR_COUNT;
 }
@@ -695,7 +720,7 @@ vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* b
     switch (what) {
         case VF_DBG_PYR_LEFT:
         case VF_DBG_PYR_RIGHT: {
-            const PyrView& pv = (what == VF_DBG_PYR_LEFT) ? h.left[p] : h.right[p];
+            const PyrView& pv = (what == VF_DBG_PYR_LEFT) ? h.left[(int)((b->frame - 1) % 3)] : h.right[p];
             if (arg < 0 || arg >= pv.n_levels) return fail(b, VF_ERR_INVALID_ARG, "pyramid level out of range");
             bytes = (size_t)pv.w[arg] * pv.h[arg];
             *size_out = bytes;

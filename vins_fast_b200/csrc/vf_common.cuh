@@ -81,7 +81,7 @@ enum Counter {
 };
 
 // Measurement aid: when a trace buffer is attached to the batch (vf_batch_set_trace), thread 0 of every CTA records the
-// kernel's first start and last end on the GPU's nanosecond timer: [id + 16 * parity][0] = min start, [..][1] = max end.
+// kernel's start (first CTA) and last end on the GPU's nanosecond timer (the latest launch that used the slot wins): [id + 16 * (frame % 6)][0] = min start, [..][1] = max end.
 enum TraceId { TR_CLEAR = 0, TR_PYR_LEFT, TR_PAD_LEFT, TR_LK_TEMPORAL, TR_SELECT, TR_RESPONSE, TR_SCAN, TR_SCATTER, TR_MASK,
                TR_GFTT, TR_PYR_RIGHT, TR_PAD_RIGHT, TR_LK_STEREO, TR_UNDISTORT_LEFT, TR_COUNT };
 #if defined(__CUDACC__)
@@ -89,13 +89,13 @@ struct TraceScope {
     unsigned long long* slot;
     __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
     __device__ __forceinline__ TraceScope(unsigned long long* buf, int id) : slot(buf ? buf + 2 * id : nullptr) {
-        if (slot && threadIdx.x == 0) atomicMin(slot, now());
+        if (slot && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *slot = now();   // first CTA
     }
     __device__ __forceinline__ ~TraceScope() { if (slot && threadIdx.x == 0) atomicMax(slot + 1, now()); }
 };
-// ad-hoc phase stamps inside a single-CTA kernel (slots 96..127 of the trace buffer)
+// ad-hoc phase stamps inside a single-CTA kernel (slots 224..255 of the trace buffer)
 __device__ __forceinline__ void trace_phase(unsigned long long* buf, int k) {
-    if (buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) buf[96 + k] = TraceScope::now();
+    if (buf && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) buf[224 + k] = TraceScope::now();
 }
 #endif
 

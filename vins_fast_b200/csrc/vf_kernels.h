@@ -16,7 +16,8 @@ struct DevBatch {
     double quality;
     CamParams cam[2];
 
-    PyrView left[2];                 // left pyramids, slot = frame parity (cur) / parity^1 (prev); stream 0 base
+    PyrView left[3];                 // left pyramids, ring of three: frame k builds slot k % 3 while frame k-1 may still track from
+                                     // slot (k-2) % 3 into slot (k-1) % 3; stream 0 base
     PyrView right[2];                // right pyramids, slot = frame parity (the stereo LK of frame k may still read its
                                      // pyramid while frame k+1 builds the next one)
     size_t lvl_stream_stride[kMaxLevels];   // bytes between consecutive streams of one level
@@ -66,8 +67,9 @@ int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaSt
 void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cudaStream_t stream);
 
 // ---- vf_lk.cu ----
-void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
-void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+// `cur` / `prev`: slots of the current and of the previous left pyramid in DevBatch::left
+void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream);
+void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, cudaStream_t stream);
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
 cudaError_t corners_prepare();
 cudaError_t pyramid_prepare();

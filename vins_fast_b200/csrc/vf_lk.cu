@@ -605,11 +605,12 @@ __device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // f
 extern __shared__ __align__(16) unsigned char lk_smem_raw[];
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
-__global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch* __restrict__ bp, int parity) {
+__global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch* __restrict__ bp, int parity_arg, int cur, int prev) {
+    const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_LK_TEMPORAL + 16 * parity);
+    TraceScope trace(b.trace, TR_LK_TEMPORAL + 16 * tphase);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
 #ifdef VF_LK_TIMING
@@ -617,11 +618,11 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch*
 #endif
     if (i >= n_prev) return;
     lk_smem_init(sm, stat, b.n_levels);
-    load_pyr(sm, 0, b.left[parity ^ 1], b.lvl_stream_stride, s);   // 0 = previous left
-    load_pyr(sm, 1, b.left[parity], b.lvl_stream_stride, s);       // 1 = current left
+    load_pyr(sm, 0, b.left[prev], b.lvl_stream_stride, s);   // 0 = previous left
+    load_pyr(sm, 1, b.left[cur], b.lvl_stream_stride, s);    // 1 = current left
     __syncthreads();
     const float2 p0 = b.kps[parity ^ 1][(size_t)s * cap + i];
-    const int L = min(b.lk_max_level, b.left[parity].n_levels - 1);
+    const int L = min(b.lk_max_level, b.left[cur].n_levels - 1);
 #ifdef VF_LK_TIMING_REPEAT
     {   // cold-vs-warm experiment: the same forward pass twice, the second one is accounted under phases 8..13
         lk_track_point(sm, 0, 1, p0, p0, false, L, stat);
@@ -671,11 +672,12 @@ __device__ __forceinline__ float2 velocity(float2 cur, float2 prev, double dt) {
 
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
 //      RemoveDistortion + ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
-__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* __restrict__ bp, int parity) {
+__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* __restrict__ bp, int parity_arg, int cur) {
+    const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_LK_STEREO + 16 * parity);
+    TraceScope trace(b.trace, TR_LK_STEREO + 16 * tphase);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
     const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
@@ -685,7 +687,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     if (i >= n) return;
     const size_t o = (size_t)s * cap + i;
     lk_smem_init(sm, stat, b.n_levels);
-    load_pyr(sm, 0, b.left[parity], b.lvl_stream_stride, s);   // 0 = current left
+    load_pyr(sm, 0, b.left[cur], b.lvl_stream_stride, s);   // 0 = current left
     load_pyr(sm, 1, b.right[parity], b.lvl_stream_stride, s);          // 1 = current right
     if (tid == 0) sm.found[1] = -1;
     __syncthreads();
@@ -736,10 +738,11 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
 
 // ---- left camera: RemoveDistortion + ComputeKpsVelocity (:103-104, :310-363) and the left half of the record.
 //      Depends on current_kps_ / ids_ only, so it runs beside the stereo LK on the side stream. ----
-__global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity) {
+__global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity_arg) {
+    const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     extern __shared__ int prev_ids_sm[];   // [cap] ids_ of the previous frame
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_UNDISTORT_LEFT + 16 * parity);
+    TraceScope trace(b.trace, TR_UNDISTORT_LEFT + 16 * tphase);
     const int s = blockIdx.y, cap = b.cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
@@ -816,13 +819,13 @@ cudaError_t lk_prepare() {
     return cudaFuncSetAttribute(undistort_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout);
 }
 
-void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
+void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity);
+    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity, cur, prev);
 }
-void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
+void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity);
+    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity, cur);
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
             *reinterpret_cast<const uint4*>(src + (size_t)(loy[0] + r) * a.spitch + ax0 + 16 * c);
     }
     __syncthreads();
+    if (blockIdx.z == 0 && a.trace_id == TR_PYR_LEFT) trace_phase(a.trace, 16);
 
     const uint8_t* in = buf0;
     int in_pitch = P0, in_ox = ax0;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
             }
         }
         in = out; in_pitch = PI; in_ox = lox[k + 1];
+        if (blockIdx.z == 0 && a.trace_id == TR_PYR_LEFT) trace_phase(a.trace, 17 + k);
         // the next transition overwrites tmp and the other ping-pong buffer only after every thread passed the barriers above
     }
 }
@@ -130,8 +132,8 @@ static void launch_pyr_fused(const PyrView& pv, const size_t* stride, int first,
     }
     const int tw = pv.w[first + count], th = pv.h[first + count];
     if (count == 3) {
-        dim3 grid((tw + 7) / 8, (th + 7) / 8, n_images);
-        pyr_fused_kernel<3, 8, 8><<<grid, 256, 0, stream>>>(a);
+        dim3 grid((tw + 7) / 8, (th + 3) / 4, n_images);
+        pyr_fused_kernel<3, 8, 4><<<grid, 256, 0, stream>>>(a);
     } else if (count == 2) {
         dim3 grid((tw + 15) / 16, (th + 7) / 8, n_images);
         pyr_fused_kernel<2, 16, 8><<<grid, 256, 0, stream>>>(a);
@@ -269,7 +271,7 @@ void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cu
 // co-resident on an SM (the split is reconfigured only when the SM drains), which serialises the streams of a frame.
 cudaError_t pyramid_prepare() {
     cudaError_t e = cudaSuccess;
-    if ((e = cudaFuncSetAttribute(pyr_fused_kernel<3, 8, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pyr_fused_kernel<3, 8, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(pyr_fused_kernel<2, 16, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(pyr_fused_kernel<1, 32, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(pad_levels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;

@@ -148,13 +148,14 @@ __device__ void block_introsort_loop(SortItem* v, int n, int4* queue, int* qn, i
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBatch* __restrict__ bp, int parity) {
+__global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBatch* __restrict__ bp, int parity_arg) {
+    const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[ST_THREADS / 32];
     __shared__ int4 sort_queue[2 * kSortQueue];
     __shared__ int sort_qn[2];
     const DevBatch& b = *bp;
-    TraceScope trace(b.trace, TR_SELECT + 16 * parity);
+    TraceScope trace(b.trace, TR_SELECT + 16 * tphase);
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, cap = b.cap;
     const SelLayout L(cap);
     float2* pts = reinterpret_cast<float2*>(smem_raw + L.off_pts);
