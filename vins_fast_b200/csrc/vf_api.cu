@@ -26,6 +26,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <initializer_list>
 #include <mutex>
@@ -62,9 +63,12 @@ struct vf_batch {
     DevBatch h;               // host copy of the device descriptor
     DevBatch* d = nullptr;    // device copy
     std::vector<void*> allocs;
-    vf_feature* pin_out[2] = {nullptr, nullptr};
-    int* pin_counters[2] = {nullptr, nullptr};
-    double* pin_times = nullptr;
+    vf_feature* pin_out[2] = {nullptr, nullptr};   // mapped pinned: records of the frames of each parity
+    int* pin_n[2] = {nullptr, nullptr};            // mapped pinned: [S] feature counts
+    int* dev_n[2] = {nullptr, nullptr};            // their device addresses
+    double* pin_dt = nullptr;                      // mapped pinned ring [4][S]: time since the previous frame
+    double* dev_dt = nullptr;
+    std::vector<double> prev_times;
     long frame = 0;
     int last_parity = -1;
     cudaGraphExec_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per frame % 6 (parity x pyramid ring slot)
@@ -208,11 +212,11 @@ void destroy_batch(vf_batch* b) {
     if (b->d) cudaFree(b->d);
     for (int p = 0; p < 2; ++p) {
         if (b->pin_out[p]) cudaFreeHost(b->pin_out[p]);
-        if (b->pin_counters[p]) cudaFreeHost(b->pin_counters[p]);
+        if (b->pin_n[p]) cudaFreeHost(b->pin_n[p]);
         if (b->ev_done[p]) cudaEventDestroy(b->ev_done[p]);
         if (b->ev_done[p + 2]) cudaEventDestroy(b->ev_done[p + 2]);
     }
-    if (b->pin_times) cudaFreeHost(b->pin_times);
+    if (b->pin_dt) cudaFreeHost(b->pin_dt);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_resp) cudaEventDestroy(b->ev_resp);
     if (b->ev_right) cudaEventDestroy(b->ev_right);
@@ -244,6 +248,7 @@ vf_status reset_state(vf_batch* b) {
     VF_CUDA(b, cudaStreamSynchronize(b->main));
     b->frame = 0;
     b->last_parity = -1;
+    std::fill(b->prev_times.begin(), b->prev_times.end(), 0.0);
     return VF_OK;
 }
 
@@ -326,13 +331,13 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_chain[parity], 0));
         if (b->frame >= 3) VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_done[(slot + 1) & 3], 0));
     }
-    double* pt = b->pin_times + (size_t)slot * S;
-    for (int s = 0; s < S; ++s) pt[s] = times[s];
+    double* pdt = b->pin_dt + (size_t)slot * S;                              // current_time_ - previous_time_ (feature_tracker.cpp:338)
+    for (int s = 0; s < S; ++s) { pdt[s] = times[s] - b->prev_times[s]; b->prev_times[s] = times[s]; }
+    const double* dev_dt = b->dev_dt + (size_t)slot * S;
     for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
     // All uploads of the frame go through side B, in the order the frame needs them: times, left image, right image.
     // The staging buffers are double-buffered by parity, so with asynchronous enqueues the upload of frame k+1 overlaps
     // the chain of frame k; the main stream only waits for the left image.
-    VF_CUDA(b, cudaMemcpyAsync(h.times[parity], pt, sizeof(double) * S, cudaMemcpyHostToDevice, b->side_b));
     // the images go up as ONE linear copy each into unpadded staging buffers (a pitched 2-D copy of 480 short rows is
     // several times slower over PCIe); the pyramid launches read them there and move level 0 into its padded home
     const size_t SP = (size_t)b->stage_pitch, simg = SP * H;
@@ -359,17 +364,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     VF_CUDA(b, cudaEventRecord(b->ev_pyrl, b->side_b));
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));     // the corner response reads the staging image
     VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_pyrl, 0));
-    // right image + right pyramid on side D; the right upload queues behind the left one so that the left image (which
-    // the frame's critical path waits for) has the link to itself
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_img, 0));
-    { StageTimer t(b, ST_H2D_RIGHT, b->side_d); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_d)); }
-    {
-        StageTimer t(b, ST_PYR_RIGHT, b->side_d);
-        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
-        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_d, &src, h.trace, TR_PYR_RIGHT + 16 * phase);
-    }
-    VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
-    // left chain
+    // left chain first (host order = how soon the work reaches the GPU: the chain is the critical path)
     if (b->cfg.use_cuda_graph && !b->profiling) {
         if (!b->graph[phase]) {
             vf_status st = build_graph(b, phase);
@@ -381,25 +376,30 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         if (st != VF_OK) return st;
     }
     n_launch += b->chain_launches;
+    // right image + right pyramid on side D; the right upload queues behind the left one so that the left image (which
+    // the frame's critical path waits for) has the link to itself
+    VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_img, 0));
+    { StageTimer t(b, ST_H2D_RIGHT, b->side_d); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_d)); }
+    {
+        StageTimer t(b, ST_PYR_RIGHT, b->side_d);
+        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
+        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_d, &src, h.trace, TR_PYR_RIGHT + 16 * phase);
+    }
+    VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
     // The stereo LK is not on the frame-to-frame dependency chain (frame k+1 only needs current_kps_ / ids_ of frame k),
     // so it runs on its own stream: with asynchronous enqueues it overlaps the temporal chain of the next frame.
     // Beside it, the left camera's undistortion + velocity (needs current_kps_ / ids_ only).
     VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
     VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_sel, 0));
-    { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_a); launch_undistort_left(b->d, h, parity | (phase << 4), b->side_a); ++n_launch; }
+    { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_a); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[parity], b->side_a); ++n_launch; }
     VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_a));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
     VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
-    { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, b->side_c); ++n_launch; }
+    { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); ++n_launch; }
     VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
     VF_CUDA(b, cudaGetLastError());
-    {
-        StageTimer t(b, ST_D2H, b->side_c);
-        VF_CUDA(b, cudaMemcpyAsync(b->pin_out[parity], h.out[parity], sizeof(vf_feature) * (size_t)S * h.cap, cudaMemcpyDeviceToHost, b->side_c));
-        VF_CUDA(b, cudaMemcpyAsync(b->pin_counters[parity], h.counters[parity], sizeof(int) * (size_t)S * C_COUNT,
-                                   cudaMemcpyDeviceToHost, b->side_c));
-    }
+    // no download commands: the records and the feature counts were written to mapped pinned host memory by the kernels
     VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->side_c));
     b->launches = n_launch;
     b->last_parity = parity;
@@ -422,7 +422,7 @@ vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out, int lag = 0)
         }
     }
     for (int s = 0; s < S; ++s) {
-        const int n = b->pin_counters[p][s * C_COUNT + C_N_TOTAL];
+        const int n = b->pin_n[p][s];
         if (n_out) n_out[s] = n;
         if (out) memcpy(out + (size_t)s * cap, b->pin_out[p] + (size_t)s * cap, sizeof(vf_feature) * (size_t)n);
     }
@@ -553,14 +553,22 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRY(dalloc(b, &h.hist, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start, (size_t)S * (h.n_buckets + 1)));
     TRY(dalloc(b, &h.bucket_fill, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz, (size_t)S * h.n_buckets));
     if (cap > 512) TRY(dalloc(b, &h.conflict, (size_t)S * cap * ((cap + 31) / 32)));
-    for (int p = 0; p < 2; ++p) TRY(dalloc(b, &h.out[p], SC));
+    // result records, feature counts and frame intervals live in mapped pinned host memory: the kernels write / read them
+    // in place, no copy commands at either end of a frame
+    for (int p = 0; p < 2; ++p) {
+        TRYC(cudaHostAlloc(&b->pin_out[p], sizeof(vf_feature) * SC, cudaHostAllocMapped));
+        memset(b->pin_out[p], 0, sizeof(vf_feature) * SC);
+        TRYC(cudaHostGetDevicePointer((void**)&h.out[p], b->pin_out[p], 0));
+        TRYC(cudaHostAlloc(&b->pin_n[p], sizeof(int) * (size_t)S, cudaHostAllocMapped));
+        memset(b->pin_n[p], 0, sizeof(int) * (size_t)S);
+        TRYC(cudaHostGetDevicePointer((void**)&b->dev_n[p], b->pin_n[p], 0));
+    }
+    TRYC(cudaHostAlloc(&b->pin_dt, sizeof(double) * (size_t)S * 4, cudaHostAllocMapped));
+    TRYC(cudaHostGetDevicePointer((void**)&b->dev_dt, b->pin_dt, 0));
+    b->prev_times.assign(S, 0.0);
     TRYC(cudaMalloc(&b->d, sizeof(DevBatch)));
     TRYC(cudaMemcpy(b->d, &h, sizeof(DevBatch), cudaMemcpyHostToDevice));
-    for (int p = 0; p < 2; ++p) {
-        TRYC(cudaMallocHost(&b->pin_out[p], sizeof(vf_feature) * SC));
-        TRYC(cudaMallocHost(&b->pin_counters[p], sizeof(int) * (size_t)S * C_COUNT));
-    }
-    TRYC(cudaMallocHost(&b->pin_times, sizeof(double) * (size_t)S * 4));
+
     TRYC(select_tracked_prepare(cap));
     TRYC(lk_prepare());
     TRYC(corners_prepare());

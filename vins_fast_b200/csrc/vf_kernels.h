@@ -32,7 +32,7 @@ struct DevBatch {
     float2* un_right[2];             // [parity][S][cap] right undistorted point where right_ok
     uint8_t* right_ok[2];            // [parity][S][cap] 1 = id has a right observation this frame
     int* counters[2];                // [parity][S][C_COUNT]
-    double* times[2];                // [parity][S]
+    double* times[2];                // (unused by the kernels: the frame interval reaches them through mapped host memory)
 
     // per-frame intermediates (kept for the debug getters)
     float2* fwd_pts; uint8_t* fwd_st; float2* rev_pts; uint8_t* rev_st; uint8_t* temporal_st;   // [S][cap]
@@ -54,7 +54,7 @@ struct DevBatch {
     int* bucket_nz;                  // [S][n_buckets] the non-empty d, ascending (counter C_N_NZ_BUCKETS)
     uint32_t* conflict;              // [S][cap][(cap+31)/32] min_dist conflict bit-matrix of select_tracked when cap > 512
 
-    vf_feature* out[2];              // [parity][S][cap] packed result records
+    vf_feature* out[2];              // [parity][S][cap] packed result records, in MAPPED PINNED HOST memory (zero-copy download)
     unsigned long long* trace;       // optional [TR_COUNT][2] kernel start / end stamps (measurement aid), else null
 };
 
@@ -69,8 +69,9 @@ void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cu
 // ---- vf_lk.cu ----
 // `cur` / `prev`: slots of the current and of the previous left pyramid in DevBatch::left
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream);
-void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, cudaStream_t stream);
-void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
+// dt_host: [S] time since the previous frame, n_host: [S] feature counts -- both in mapped pinned host memory
+void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream);
+void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, const double* dt_host, int* n_host, cudaStream_t stream);
 cudaError_t corners_prepare();
 cudaError_t pyramid_prepare();
 cudaError_t lk_prepare();   // opt in to the LK kernels' dynamic shared memory (once per device, outside stream capture)

@@ -31,8 +31,11 @@
 
 namespace vf {
 
-constexpr int kLkThreads = 256;
+constexpr int kLkThreads = 128;              // 4 warps: one per SM sub-partition; a second CTA (the other LK kernel of a
+                                             // pipelined frame pair) interleaves with it instead of queueing behind it
 constexpr int kLkWarps = kLkThreads / 32;
+constexpr int kLkItems = 256;                // work items of a pass are numbered 0..255; thread t owns items t, t + kLkThreads, ...
+constexpr int kIpt = kLkItems / kLkThreads;  // items per thread
 constexpr int kTileI = 24;                   // staged I tile (window + bilinear tap + Scharr ring)
 constexpr int kTileD = 22;                   // derivative tile (window + bilinear tap)
 constexpr int kJMargin = 5;                  // staged J tile = 22x22 taps + this margin on every side
@@ -181,9 +184,9 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
 
     // ================= prologue: everything that depends on the source point only, all levels at once =================
     __syncthreads();   // the previous pass may still be reading the shared buffers
-    if (tid >= 224 && tid < 236) (&sm.tot[0][0])[tid - 224] = 0;   // all three slots of the iteration totals start at zero
-    // ---- P1: one thread per tile row.  Threads 0..24*nlv-1: rows of the 24x24 tiles of I (level = tid / 24);
-    //      warp 6: rows of the top level's 32x32 tile of J (it only depends on the start point) ----
+    // ---- P1: one item per tile row.  Items 0..24*nlv-1: rows of the 24x24 tiles of I (level = item / 24); items 192..223:
+    //      rows of the top level's 32x32 tile of J (it only depends on the start point); items 224..235 clear the three
+    //      slots of the iteration totals ----
     int jx0, jy0, jbuf = 0;
     {
         const float scale = 1.f / (float)(1 << max_level);
@@ -192,38 +195,45 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         jx0 = clamp_tile_origin(__float2int_rd(__fsub_rn(__fmul_rn(sx, scale), half)) - kJMargin, LT.w);
         jy0 = clamp_tile_origin(__float2int_rd(__fsub_rn(__fmul_rn(sy, scale), half)) - kJMargin, LT.h);
     }
-    if (tid < kTileI * nlv) {
-        const int level = tid / kTileI, row = tid - level * kTileI;
-        const LevelRef LI = sm.pyr[ia][level];
-        const float scale = 1.f / (float)(1 << level);
-        const float ppx = __fsub_rn(__fmul_rn(prev_pt.x, scale), half), ppy = __fsub_rn(__fmul_rn(prev_pt.y, scale), half);
-        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
-        const int valid = !(ipx < -kWin || ipx >= LI.w || ipy < -kWin || ipy >= LI.h);
-        if (row == 0) {
-            LevelGeo& g = sm.lv[level].geo;
-            g.ipx = ipx; g.ipy = ipy; g.w = LI.w; g.h = LI.h; g.valid = valid;
-            bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), g.w00, g.w01, g.w10, g.w11);
-        }
-        if (valid) {
-            uint32_t v[kTileI / 4];
-            load_row_words<kTileI / 4>(LI, ipx - 1, ipy - 1 + row, v);
-            uint32_t* dst = reinterpret_cast<uint32_t*>(sm.lv[level].tileI + row * kTileI);
 #pragma unroll
-            for (int k = 0; k < kTileI / 4; ++k) dst[k] = v[k];
+    for (int q = 0; q < kIpt; ++q) {
+        const int it = tid + q * kLkThreads;
+        if (it < kTileI * nlv) {
+            const int level = it / kTileI, row = it - level * kTileI;
+            const LevelRef LI = sm.pyr[ia][level];
+            const float scale = 1.f / (float)(1 << level);
+            const float ppx = __fsub_rn(__fmul_rn(prev_pt.x, scale), half), ppy = __fsub_rn(__fmul_rn(prev_pt.y, scale), half);
+            const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+            const int valid = !(ipx < -kWin || ipx >= LI.w || ipy < -kWin || ipy >= LI.h);
+            if (row == 0) {
+                LevelGeo& g = sm.lv[level].geo;
+                g.ipx = ipx; g.ipy = ipy; g.w = LI.w; g.h = LI.h; g.valid = valid;
+                bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), g.w00, g.w01, g.w10, g.w11);
+            }
+            if (valid) {
+                uint32_t v[kTileI / 4];
+                load_row_words<kTileI / 4>(LI, ipx - 1, ipy - 1 + row, v);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(sm.lv[level].tileI + row * kTileI);
+#pragma unroll
+                for (int k = 0; k < kTileI / 4; ++k) dst[k] = v[k];
+            }
+        } else if (it >= 192 && it < 224) {
+            const int row = it - 192;
+            uint32_t v[kTileJ / 4];
+            load_row_words<kTileJ / 4>(sm.pyr[ja][max_level], jx0, jy0 + row, v);
+            uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[0] + row * kTileJ);
+            dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+        } else if (it >= 224 && it < 236) {
+            (&sm.tot[0][0])[it - 224] = 0;
         }
-    } else if (wid == 6) {
-        uint32_t v[kTileJ / 4];
-        load_row_words<kTileJ / 4>(sm.pyr[ja][max_level], jx0, jy0 + lane, v);
-        uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[0] + lane * kTileJ);
-        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
     LK_T(0);
     // ---- P2: Scharr (Ix,Iy) on the 22x22 tap positions of every level; zero outside the image.
-    //      A thread owns the same (at most two) tile positions on every level: the index arithmetic is level-invariant ----
+    //      A thread owns the same few tile positions on every level: the index arithmetic is level-invariant ----
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < (kTileD * kTileD + kLkThreads - 1) / kLkThreads; ++r) {
         const int e = tid + r * kLkThreads;
         if (e < kTileD * kTileD) {
             const int ty = e / kTileD, tx = e - ty * kTileD;
@@ -251,7 +261,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     //      in OpenCV's accumulation order: SIMD lane l = x & 3 sees columns l, 4+l, 8+l, 12+l of every row in turn
     //      (slot y*4 + x/4 of chain l), the scalar tail sees columns 16..20 of every row (slot y*5 + x-16 of chain 4) ----
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < (kWinPx + kLkThreads - 1) / kLkThreads; ++r) {
         const int e = tid + r * kLkThreads;
         if (e < kWinPx) {
             const int y = e / kWin, x = e - y * kWin;
@@ -313,20 +323,26 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     LK_T(3);
 
     // ================= level loop: J tile + iterations =================
-    // the two pixels this thread owns in every iteration: threads 0..167 take the 168 column pairs (c, c+4) of the two
-    // 8-wide SIMD groups of every row (pmaddwd pair sums), threads 192..244 take 53 pairs of consecutive tail pixels.
-    int e0 = -1, e1 = -1;
-    if (tid < 168) {
-        const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3;
-        e0 = y * kWin + 8 * g + c; e1 = e0 + 4;
-    } else if (tid >= 192 && tid < 192 + 53) {
-        const int t = 2 * (tid - 192);
-        e0 = (t / 5) * kWin + 16 + (t - (t / 5) * 5);
-        if (t + 1 < kTail) e1 = ((t + 1) / 5) * kWin + 16 + ((t + 1) - ((t + 1) / 5) * 5);
+    // Work items of an iteration: items 0..167 take the 168 column pairs (c, c+4) of the two 8-wide SIMD groups of every
+    // row (pmaddwd pair sums), items 192..244 take 53 pairs of consecutive tail pixels; a thread owns kIpt items.
+    int e0[kIpt], e1[kIpt], o0[kIpt], o1[kIpt];
+    bool is_pair[kIpt];
+#pragma unroll
+    for (int q = 0; q < kIpt; ++q) {
+        const int it = tid + q * kLkThreads;
+        e0[q] = -1; e1[q] = -1;
+        is_pair[q] = it < 168;
+        if (it < 168) {
+            const int y = it >> 3, g = (it >> 2) & 1, c = it & 3;
+            e0[q] = y * kWin + 8 * g + c; e1[q] = e0[q] + 4;
+        } else if (it >= 192 && it < 192 + 53) {
+            const int t = 2 * (it - 192);
+            e0[q] = (t / 5) * kWin + 16 + (t - (t / 5) * 5);
+            if (t + 1 < kTail) e1[q] = ((t + 1) / 5) * kWin + 16 + ((t + 1) - ((t + 1) / 5) * 5);
+        }
+        o0[q] = e0[q] < 0 ? 0 : (e0[q] / kWin) * kTileJ + (e0[q] - (e0[q] / kWin) * kWin);
+        o1[q] = e1[q] < 0 ? 0 : (e1[q] / kWin) * kTileJ + (e1[q] - (e1[q] / kWin) * kWin);
     }
-    const int o0 = e0 < 0 ? 0 : (e0 / kWin) * kTileJ + (e0 - (e0 / kWin) * kWin);
-    const int o1 = e1 < 0 ? 0 : (e1 / kWin) * kTileJ + (e1 - (e1 / kWin) * kWin);
-    const bool is_pair = tid < 168;
     bool tile_ready = true;      // the top level's J tile was staged by the prologue
     // shared-memory addresses of the three iteration-total slots, rotated every iteration (j, j+1, j+2)
     unsigned int slot_cur = (unsigned int)__cvta_generic_to_shared(sm.tot[0]);
@@ -354,15 +370,20 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         const float A11 = gA.x, A12 = gA.y, A22 = gA.z, D = gA.w;
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         // this thread's two source pixels stay in registers for the whole level
-        const int I0 = B.Iw[max(e0, 0)], I1 = B.Iw[max(e1, 0)];
-        const short2 g0 = e0 >= 0 ? B.dI[e0] : make_short2(0, 0), g1 = e1 >= 0 ? B.dI[e1] : make_short2(0, 0);
+        int I0[kIpt], I1[kIpt];
+        short2 g0[kIpt], g1[kIpt];
+#pragma unroll
+        for (int q = 0; q < kIpt; ++q) {
+            I0[q] = B.Iw[max(e0[q], 0)]; I1[q] = B.Iw[max(e1[q], 0)];
+            g0[q] = e0[q] >= 0 ? B.dI[e0[q]] : make_short2(0, 0); g1[q] = e1[q] >= 0 ? B.dI[e1[q]] : make_short2(0, 0);
+        }
         {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
             if (!tile_ready || inx < jx0 || iny < jy0 || inx + kTileD > jx0 + kTileJ || iny + kTileD > jy0 + kTileJ) {
                 // no usable prefetched tile: stage it now (one warp, one row per lane)
                 jx0 = clamp_tile_origin(inx - kJMargin, jcols); jy0 = clamp_tile_origin(iny - kJMargin, jrows);
                 jbuf ^= 1;
-                if (wid == 7) {
+                if (wid == kLkWarps - 1) {
                     uint32_t v[kTileJ / 4];
                     load_row_words<kTileJ / 4>(LJ, jx0, jy0 + lane, v);
                     uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
@@ -372,7 +393,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 __syncthreads();
             }
         }
-        // prefetch the next level's J tile around the current estimate: warp 7 issues the loads now and parks the
+        // prefetch the next level's J tile around the current estimate: the last warp issues the loads now and parks the
         // words in registers until the iterations of this level are done
         uint32_t pf[kTileJ / 4];
         int px0 = 0, py0 = 0;
@@ -380,7 +401,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             const LevelRef LN = sm.pyr[ja][level - 1];
             px0 = clamp_tile_origin(__float2int_rd(__fadd_rn(__fmul_rn(nx, 2.f), half)) - kJMargin, LN.w);   // 2*(nx + half) - half
             py0 = clamp_tile_origin(__float2int_rd(__fadd_rn(__fmul_rn(ny, 2.f), half)) - kJMargin, LN.h);
-            if (wid == 7) load_row_words<kTileJ / 4>(sm.pyr[ja][level - 1], px0, py0 + lane, pf);
+            if (wid == kLkWarps - 1) load_row_words<kTileJ / 4>(sm.pyr[ja][level - 1], px0, py0 + lane, pf);
         }
         LK_T(4);
         const uint8_t* tj = sm.tileJ[jbuf];
@@ -400,7 +421,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 // the window left the staged tile: re-centre it (uniform branch)
                 jx0 = inx - kJMargin; jy0 = iny - kJMargin;
                 __syncthreads();    // everybody is done with the current tile
-                if (wid == 6) {
+                if (wid == kLkWarps - 2) {
                     uint32_t v[kTileJ / 4];
                     load_row_words<kTileJ / 4>(LJ, jx0, jy0 + lane, v);
                     uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
@@ -415,17 +436,23 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             int w00, w01, w10, w11;
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             const uint8_t* jt = tj + (iny - jy0) * kTileJ + (inx - jx0);
-            const uint8_t* p0 = jt + o0;
-            const uint8_t* p1 = jt + o1;
-            const int d0 = VF_DESCALE(p0[0] * w00 + p0[1] * w01 + p0[kTileJ] * w10 + p0[kTileJ + 1] * w11, 9) - I0;
-            const int d1 = VF_DESCALE(p1[0] * w00 + p1[1] * w01 + p1[kTileJ] * w10 + p1[kTileJ + 1] * w11, 9) - I1;
-            // exact int32 products (idle threads own zero gradients); pair threads form OpenCV's pmaddwd pair sums,
-            // tail threads keep single terms
-            const int ex0 = d0 * g0.x, ey0 = d0 * g0.y, ex1 = d1 * g1.x, ey1 = d1 * g1.y;
-            const int tx = ex0 + ex1, ty = ey0 + ey1;
+            // exact int32 products (idle items own zero gradients); pair items form OpenCV's pmaddwd pair sums, tail items keep
+            // single terms.  tx / ty: what this thread adds to b; ab: its sum |term|, clamped so that the total over all
+            // contributing items stays below 2^32
+            int ex0[kIpt], ey0[kIpt], ex1[kIpt], ey1[kIpt];
+            int tx = 0, ty = 0, ab = 0;
+#pragma unroll
+            for (int q = 0; q < kIpt; ++q) {
+                const uint8_t* p0 = jt + o0[q];
+                const uint8_t* p1 = jt + o1[q];
+                const int d0 = VF_DESCALE(p0[0] * w00 + p0[1] * w01 + p0[kTileJ] * w10 + p0[kTileJ + 1] * w11, 9) - I0[q];
+                const int d1 = VF_DESCALE(p1[0] * w00 + p1[1] * w01 + p1[kTileJ] * w10 + p1[kTileJ + 1] * w11, 9) - I1[q];
+                ex0[q] = d0 * g0[q].x; ey0[q] = d0 * g0[q].y; ex1[q] = d1 * g1[q].x; ey1[q] = d1 * g1[q].y;
+                const int sx_ = ex0[q] + ex1[q], sy_ = ey0[q] + ey1[q];
+                tx += sx_; ty += sy_;
+                ab += min(is_pair[q] ? abs(sx_) + abs(sy_) : abs(ex0[q]) + abs(ey0[q]) + abs(ex1[q]) + abs(ey1[q]), kExact);
+            }
             LK_TF(6);
-            // sum |term| of this thread, clamped so that the total over the 221 contributing threads stays below 2^32
-            const int ab = min(is_pair ? abs(tx) + abs(ty) : abs(ex0) + abs(ey0) + abs(ex1) + abs(ey1), kExact);
 #if VF_LK_ABLATE == 1
             int bx = tx, by = ty, bz = ab & 0xffff, bw = 0;
 #elif VF_LK_ABLATE == 2
@@ -460,14 +487,18 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 ++fast;
             } else {
                 // spill the terms in OpenCV's accumulation order and run the 10 ordered float chains, one lane per chain
-                if (tid < 168) {
-                    const int y = tid >> 3, g = (tid >> 2) & 1, c = tid & 3, slot = y * 2 + g;
-                    sm.termsB[(2 * c + 0) * kChainA + slot] = (float)tx;      // v_cvt_f32 of the pmaddwd pair sum
-                    sm.termsB[(2 * c + 1) * kChainA + slot] = (float)ty;
-                } else if (tid >= 192 && tid < 192 + 53) {
-                    const int t = 2 * (tid - 192);
-                    sm.termsB[8 * kChainA + t] = (float)ex0; sm.termsB[9 * kChainA + t] = (float)ey0;
-                    if (t + 1 < kTail) { sm.termsB[8 * kChainA + t + 1] = (float)ex1; sm.termsB[9 * kChainA + t + 1] = (float)ey1; }
+#pragma unroll
+                for (int q = 0; q < kIpt; ++q) {
+                    const int it = tid + q * kLkThreads;
+                    if (it < 168) {
+                        const int y = it >> 3, g = (it >> 2) & 1, c = it & 3, slot = y * 2 + g;
+                        sm.termsB[(2 * c + 0) * kChainA + slot] = (float)(ex0[q] + ex1[q]);      // v_cvt_f32 of the pmaddwd pair sum
+                        sm.termsB[(2 * c + 1) * kChainA + slot] = (float)(ey0[q] + ey1[q]);
+                    } else if (it >= 192 && it < 192 + 53) {
+                        const int t = 2 * (it - 192);
+                        sm.termsB[8 * kChainA + t] = (float)ex0[q]; sm.termsB[9 * kChainA + t] = (float)ey0[q];
+                        if (t + 1 < kTail) { sm.termsB[8 * kChainA + t + 1] = (float)ex1[q]; sm.termsB[9 * kChainA + t + 1] = (float)ey1[q]; }
+                    }
                 }
                 __syncthreads();
                 if (wid == 0) {
@@ -528,7 +559,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         tile_ready = false;
         if (level > 0) {   // publish the prefetched tile of the next level
             jbuf ^= 1;
-            if (wid == 7) {
+            if (wid == kLkWarps - 1) {
                 uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
                 dst[0] = make_uint4(pf[0], pf[1], pf[2], pf[3]);
                 dst[1] = make_uint4(pf[4], pf[5], pf[6], pf[7]);
@@ -672,7 +703,7 @@ __device__ __forceinline__ float2 velocity(float2 cur, float2 prev, double dt) {
 
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
 //      RemoveDistortion + ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
-__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* __restrict__ bp, int parity_arg, int cur) {
+__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* __restrict__ bp, int parity_arg, int cur, const double* __restrict__ dt_host) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
@@ -715,13 +746,12 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
     }
     __syncthreads();
     if (tid == 0) {
-        const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
-        vf_feature* rec = &b.out[parity][o];
+        vf_feature* rec = &b.out[parity][o];     // mapped pinned host memory: the record goes straight to the caller's side
         rec->has_right = ok;
         float2 unr = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
         if (ok) {
             unr = undistort_point(b.cam[1], rp);
-            if (sm.found[1] >= 0) vr = velocity(unr, b.un_right[parity ^ 1][(size_t)s * cap + sm.found[1]], dt);
+            if (sm.found[1] >= 0) vr = velocity(unr, b.un_right[parity ^ 1][(size_t)s * cap + sm.found[1]], dt_host[s]);
         }
         rec->xr = unr.x; rec->yr = unr.y; rec->ur = ok ? rp.x : 0.f; rec->vr = ok ? rp.y : 0.f; rec->vxr = vr.x; rec->vyr = vr.y;
         b.un_right[parity][o] = unr;
@@ -738,7 +768,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
 
 // ---- left camera: RemoveDistortion + ComputeKpsVelocity (:103-104, :310-363) and the left half of the record.
 //      Depends on current_kps_ / ids_ only, so it runs beside the stereo LK on the side stream. ----
-__global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity_arg) {
+__global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity_arg, const double* __restrict__ dt_host, int* __restrict__ n_host) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     extern __shared__ int prev_ids_sm[];   // [cap] ids_ of the previous frame
     const DevBatch& b = *bp;
@@ -749,6 +779,7 @@ __global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __r
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
     const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
     for (int j = threadIdx.x; j < n_prev; j += blockDim.x) prev_ids_sm[j] = prev_ids[j];
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_host[s] = n;      // feature count of the frame, straight to pinned host memory
     __syncthreads();
     if (i >= n) return;
     const size_t o = (size_t)s * cap + i;
@@ -761,10 +792,7 @@ __global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __r
     if (b.cnt[parity][o] > 1)
         for (int j = 0; j < n_prev; ++j) found = prev_ids_sm[j] == id ? j : found;
     float2 v = make_float2(0.f, 0.f);
-    if (found >= 0) {
-        const double dt = b.times[parity][s] - b.times[parity ^ 1][s];
-        v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + found], dt);
-    }
+    if (found >= 0) v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + found], dt_host[s]);   // dt: zero-copy read of the host's value
     vf_feature* rec = &b.out[parity][o];
     rec->id = id; rec->track_cnt = b.cnt[parity][o];
     rec->x = un.x; rec->y = un.y; rec->u = p0.x; rec->v = p0.y; rec->vx = v.x; rec->vy = v.y;
@@ -823,13 +851,13 @@ void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, 
     dim3 grid(h.cap, h.n_streams);
     lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity, cur, prev);
 }
-void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, cudaStream_t stream) {
+void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity, cur);
+    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity, cur, dt_host);
 }
-void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
+void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, const double* dt_host, int* n_host, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);
-    undistort_left_kernel<<<grid, 128, sizeof(int) * (size_t)(h.cap > 0 ? h.cap : 1), stream>>>(d_batch, parity);
+    undistort_left_kernel<<<grid, 128, sizeof(int) * (size_t)(h.cap > 0 ? h.cap : 1), stream>>>(d_batch, parity, dt_host, n_host);
 }
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {
