@@ -74,8 +74,7 @@ struct LevelBlock {
 struct LkSmem {
     LevelRef pyr[2][kMaxLevels];
     alignas(16) uint8_t tileJ[2][kTileJ * kTileJ];
-    alignas(16) int tot[3][4];            // (sum tx, sum ty, sum |t|) of an iteration, accumulated with shared atomics;
-                                          // triple-buffered: slot j%3 is used by iteration j and re-zeroed during j+1
+    alignas(16) int4 part[2][kLkWarps];   // per-warp (sum tx, sum ty, sum |t|) of an iteration, double-buffered
     alignas(16) float termsB[10 * kChainA];   // terms of b in accumulation order (chain-major, zero padded), spilled
                                               // only when the global exactness bound fails
     alignas(16) float chainB[12];
@@ -185,8 +184,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     // ================= prologue: everything that depends on the source point only, all levels at once =================
     __syncthreads();   // the previous pass may still be reading the shared buffers
     // ---- P1: one item per tile row.  Items 0..24*nlv-1: rows of the 24x24 tiles of I (level = item / 24); items 192..223:
-    //      rows of the top level's 32x32 tile of J (it only depends on the start point); items 224..235 clear the three
-    //      slots of the iteration totals ----
+    //      rows of the top level's 32x32 tile of J (it only depends on the start point) ----
     int jx0, jy0, jbuf = 0;
     {
         const float scale = 1.f / (float)(1 << max_level);
@@ -224,8 +222,6 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[0] + row * kTileJ);
             dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
             dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
-        } else if (it >= 224 && it < 236) {
-            (&sm.tot[0][0])[it - 224] = 0;
         }
     }
     __syncthreads();
@@ -344,9 +340,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         o1[q] = e1[q] < 0 ? 0 : (e1[q] / kWin) * kTileJ + (e1[q] - (e1[q] / kWin) * kWin);
     }
     bool tile_ready = true;      // the top level's J tile was staged by the prologue
-    // shared-memory addresses of the three iteration-total slots, rotated every iteration (j, j+1, j+2)
-    unsigned int slot_cur = (unsigned int)__cvta_generic_to_shared(sm.tot[0]);
-    unsigned int slot_next = slot_cur + 16, slot_nn = slot_cur + 32;
+    int pbuf = 0;
 
 #pragma unroll 1
     for (int level = max_level; level >= 0; --level) {
@@ -453,32 +447,21 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 ab += min(is_pair[q] ? abs(sx_) + abs(sy_) : abs(ex0[q]) + abs(ey0[q]) + abs(ex1[q]) + abs(ey1[q]), kExact);
             }
             LK_TF(6);
-#if VF_LK_ABLATE == 1
-            int bx = tx, by = ty, bz = ab & 0xffff, bw = 0;
-#elif VF_LK_ABLATE == 2
-            const int sx = tx, sy = ty, sa = ab & 0xff;
-#else
             const int sx = __reduce_add_sync(0xffffffffu, tx);
             const int sy = __reduce_add_sync(0xffffffffu, ty);
             const int sa = __reduce_add_sync(0xffffffffu, ab);
-#endif
-#if VF_LK_ABLATE != 1
-            // lane 0 of every warp adds its three partial sums to the slot of this iteration (predicated, no branch)
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %0, 0;\n\t"
-                         "@p red.shared.add.s32 [%1], %2;\n\t@p red.shared.add.s32 [%1+4], %3;\n\t@p red.shared.add.s32 [%1+8], %4;\n\t}"
-                         :: "r"(lane), "r"(slot_cur), "r"(sx), "r"(sy), "r"(sa) : "memory");
+            // every warp publishes its three partial sums (double-buffered: the slot of iteration j is rewritten in j+2,
+            // after the barrier of j+1); one barrier; every thread folds the kLkWarps partials itself
+            if (lane == 0) sm.part[pbuf][wid] = make_int4(sx, sy, sa, 0);
             __syncthreads();
-#if VF_LK_ABLATE == 3
-            int bx = tx, by = ty, bz = ab & 0xffff, bw = 0;
-#else
-            int bx, by, bz, bw;
-            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(bx), "=r"(by), "=r"(bz), "=r"(bw) : "r"(slot_cur) : "memory");
-            asm volatile("st.shared.v4.s32 [%0], {%1, %1, %1, %1};" :: "r"(slot_nn), "r"(0) : "memory");   // slot of iteration j+2
-            { const unsigned int t3 = slot_cur; slot_cur = slot_next; slot_next = slot_nn; slot_nn = t3; }
-#endif
-#endif
+            int bx = 0, by = 0, bz = 0;
+#pragma unroll
+            for (int w = 0; w < kLkWarps; ++w) {
+                const int4 q4 = sm.part[pbuf][w];
+                bx += q4.x; by += q4.y; bz += q4.z;
+            }
+            pbuf ^= 1;
             const unsigned int bnd = (unsigned int)bz;
-            (void)bw;
             LK_TF(7);
             float ib1, ib2;
             if (bnd < (unsigned int)kExact) {
@@ -603,7 +586,6 @@ __device__ __forceinline__ void lk_smem_init(LkSmem& sm, int* counters2, int n_l
         sm.lv[level].termsA[(r / kPad) * kChainA + 84 + (r % kPad)] = 0.f;
     }
     for (int i = threadIdx.x; i < 10 * kChainA; i += kLkThreads) sm.termsB[i] = 0.f;
-    if (threadIdx.x < 12) (&sm.tot[0][0])[threadIdx.x] = 0;
     if (threadIdx.x == 0) { counters2[0] = 0; counters2[1] = 0; }
 #ifdef VF_LK_TIMING
     if (threadIdx.x < 16) { sm.tacc[threadIdx.x] = 0; sm.tcnt[threadIdx.x] = 0; }
