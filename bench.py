@@ -343,13 +343,13 @@ def main():
             del os.environ["VF_TRACE"]
             tnames = ("clear_frame pyrdown_left pad_left lk_temporal select_tracked response_nms bucket_scan bucket_scatter "
                       "mask_and_max gftt_select pyrdown_right pad_right lk_stereo undistort_left").split()
-            tbuf = (C.c_ulonglong * 128)()
+            tbuf = (C.c_ulonglong * 256)()
             tacc = []
             for k in range(min(n_frames, Wm + 40)):
                 tb.track_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
-                vf.load().vf_batch_trace_get(tb._h, tbuf, 128)
+                vf.load().vf_batch_trace_get(tb._h, tbuf, 256)
                 if k >= Wm:
-                    a = np.array(list(tbuf), np.uint64)[:64].reshape(2, 16, 2)[k & 1, :14]
+                    a = np.array(list(tbuf), np.uint64)[:192].reshape(6, 16, 2)[k % 6, :14]
                     tacc.append((a - a[:, 0].min()).astype(np.int64))
             tm = np.mean(tacc, 0) / 1e3
             timeline = {"kernels": {n: {"start_us": round(float(tm[i, 0]), 2), "end_us": round(float(tm[i, 1]), 2),
