@@ -1,0 +1,127 @@
+// estimator::FrontendPipeline -- the front-end half of the reference's Estimator, pipelined on the GPU.
+//
+// Mirrors Estimator::FrontendTracker and its hand-off to the back-end (vins/estimator/estimator.cpp:143-158):
+//     input_image_cnt_++;  frame_feature = feature_tracker_->TrackImage(t, img0, img1);
+//     if (input_image_cnt_ % 2 == 0) feature_buf_.push(make_pair(t, frame_feature));          // under feature_buf_mutex_
+// with the one difference the GPU makes worthwhile: Push(t, img0, img1) only ENQUEUES frame k (vf_batch_enqueue) and
+// collects frame k-1 (vf_batch_fetch_lagged), so the stereo pass and the result hand-over of a frame overlap the temporal
+// chain of the next one.  The back-end thread drains the queue with Pop() exactly like it drains feature_buf_
+// (estimator.cpp:179-200): it sees the same (t, featureFrame) pairs, one frame later.  Results are bit-identical to the
+// synchronous FeatureTracker::TrackImage.
+//
+// The images of a frame are referenced (cv::Mat shallow copies, like the reference's current_img_) until that frame has
+// been collected.
+#pragma once
+
+#include <mutex>
+#include <queue>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "feature_tracker.hpp"
+
+namespace estimator {
+
+class FrontendPipeline {
+public:
+    typedef FeatureTracker::FeatureFrame FeatureFrame;
+
+    /// every_nth: which results go to the back-end queue (the reference keeps every 2nd, estimator.cpp:153)
+    FrontendPipeline(int max_cnt, int min_dist, int flow_back, const vf_camera& left, const vf_camera& right, int every_nth = 2,
+                     int device = -1)
+        : every_nth_(every_nth < 1 ? 1 : every_nth) {
+        vf_config_default(&cfg_);
+        cfg_.max_cnt = max_cnt; cfg_.min_dist = min_dist; cfg_.flow_back = flow_back; cfg_.device = device;
+        cfg_.cam[0] = left; cfg_.cam[1] = right;
+    }
+    ~FrontendPipeline() { vf_batch_destroy(batch_); }
+    FrontendPipeline(const FrontendPipeline&) = delete;
+    FrontendPipeline& operator=(const FrontendPipeline&) = delete;
+
+    /// Estimator::FrontendTracker(t, img0, img1), asynchronous: starts frame k, hands frame k-1 to the queue
+    void Push(double t, const cv::Mat& img0, const cv::Mat& img1) {
+        if (img0.empty() || img1.empty()) VF_FATAL("FrontendPipeline::Push: !img0.empty() && !img1.empty()");
+        if (img0.type() != CV_8UC1 || img1.type() != CV_8UC1 || img0.rows != img1.rows || img0.cols != img1.cols)
+            VF_FATAL("FrontendPipeline::Push: both images must be CV_8UC1 of one size");
+        Ensure(img0.cols, img0.rows);
+        const int slot = (int)(input_image_cnt_ & 1);
+        held_[slot][0] = img0; held_[slot][1] = img1; times_[slot] = t;      // keep the pixels alive while the frame is in flight
+        const uint8_t* p0 = img0.data;
+        const uint8_t* p1 = img1.data;
+        if (vf_batch_enqueue(batch_, &t, &p0, img0.step, &p1, img1.step) != VF_OK)
+            VF_FATAL(std::string("vf_batch_enqueue: ") + vf_batch_last_error(batch_));
+        input_image_cnt_++;
+        if (input_image_cnt_ >= 2) Collect(1);
+    }
+
+    /// collects the frame that is still in flight (call when the image source has ended)
+    void Flush() {
+        if (input_image_cnt_ > collected_) Collect(0);
+    }
+
+    /// back-end side: feature_buf_.front() / pop() (estimator.cpp:179-200); false when the queue is empty
+    bool Pop(std::pair<double, FeatureFrame>& out) {
+        std::unique_lock<std::mutex> lck(feature_buf_mutex_);
+        if (feature_buf_.empty()) return false;
+        out = std::move(feature_buf_.front());
+        feature_buf_.pop();
+        return true;
+    }
+    size_t Pending() {
+        std::unique_lock<std::mutex> lck(feature_buf_mutex_);
+        return feature_buf_.size();
+    }
+    long FramesTracked() const { return collected_; }
+
+private:
+    void Ensure(int width, int height) {
+        if (batch_ && cfg_.width == width && cfg_.height == height) return;
+        vf_batch_destroy(batch_);
+        batch_ = nullptr;
+        cfg_.width = width; cfg_.height = height;
+        if (vf_batch_create(&cfg_, 1, &batch_) != VF_OK) VF_FATAL(std::string("vf_batch_create: ") + vf_last_global_error());
+        records_.resize((size_t)(cfg_.max_cnt > 0 ? cfg_.max_cnt : 1));
+        input_image_cnt_ = 0; collected_ = 0;
+    }
+    // featureFrame of the frame `lag` behind the last enqueued one (feature_tracker.cpp:173-213) -> queue
+    void Collect(int lag) {
+        int32_t n = 0;
+        if (vf_batch_fetch_lagged(batch_, lag, records_.data(), &n) != VF_OK)
+            VF_FATAL(std::string("vf_batch_fetch_lagged: ") + vf_batch_last_error(batch_));
+        const long index = input_image_cnt_ - 1 - lag;          // 0-based index of the collected frame
+        const int slot = (int)(index & 1);
+        collected_ = index + 1;
+        if (collected_ % every_nth_ == 0) {                       // input_image_cnt_ % 2 == 0 in the reference (1-based count)
+            FeatureFrame ff;
+            for (int i = 0; i < n; ++i) {
+                const vf_feature& r = records_[i];
+                Eigen::Matrix<double, 7, 1> v;
+                v << (double)r.x, (double)r.y, 1.0, (double)r.u, (double)r.v, (double)r.vx, (double)r.vy;
+                ff[r.id].emplace_back(0, v);
+            }
+            for (int i = 0; i < n; ++i) {
+                const vf_feature& r = records_[i];
+                if (!r.has_right) continue;
+                Eigen::Matrix<double, 7, 1> v;
+                v << (double)r.xr, (double)r.yr, 1.0, (double)r.ur, (double)r.vr, (double)r.vxr, (double)r.vyr;
+                ff[r.id].emplace_back(1, v);
+            }
+            std::unique_lock<std::mutex> lck(feature_buf_mutex_);
+            feature_buf_.push(std::make_pair(times_[slot], std::move(ff)));
+        }
+        held_[slot][0] = cv::Mat(); held_[slot][1] = cv::Mat();
+    }
+
+    vf_config cfg_;
+    vf_batch* batch_ = nullptr;
+    int every_nth_;
+    long input_image_cnt_ = 0, collected_ = 0;
+    std::vector<vf_feature> records_;
+    cv::Mat held_[2][2];
+    double times_[2] = {0, 0};
+    std::mutex feature_buf_mutex_;
+    std::queue<std::pair<double, FeatureFrame>> feature_buf_;
+};
+
+}  // namespace estimator

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "vins_fast_b200/feature_tracker.hpp"
+#include "vins_fast_b200/frontend_pipeline.hpp"
 
 #define CHECK(c) do { if (!(c)) { std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #c); return 1; } } while (0)
 
@@ -121,10 +122,62 @@ static int run_frames(int argc, char** argv) {
     return 0;
 }
 
+// Estimator::FrontendTracker + feature_buf_ (estimator.cpp:143-158) on the pipelined API: the queue must hold exactly what the
+// synchronous TrackImage returns for every 2nd frame, value for value.
+//   test_feature_tracker pipe <cam0.yaml> <cam1.yaml> <frames.bin> <W> <H> <n_frames>
+static int run_pipe(int argc, char** argv) {
+    CHECK(argc == 8);
+    const int W = std::atoi(argv[5]), H = std::atoi(argv[6]), n_frames = std::atoi(argv[7]);
+    vf_camera c0, c1;
+    CHECK(vf_camera_load_yaml(argv[2], &c0) == VF_OK && vf_camera_load_yaml(argv[3], &c1) == VF_OK);
+    estimator::FeatureTracker ft(150, 30, 1);
+    ft.SetCameras(c0, c1);
+    estimator::FrontendPipeline pipe(150, 30, 1, c0, c1);
+    std::FILE* in = std::fopen(argv[4], "rb");
+    CHECK(in);
+    std::vector<std::vector<unsigned char>> left(n_frames, std::vector<unsigned char>((size_t)W * H)), right = left;
+    std::vector<double> ts(n_frames);
+    std::vector<estimator::FeatureTracker::FeatureFrame> want;
+    for (int k = 0; k < n_frames; ++k) {
+        CHECK(std::fread(&ts[k], sizeof(double), 1, in) == 1);
+        CHECK(std::fread(left[k].data(), 1, left[k].size(), in) == left[k].size());
+        CHECK(std::fread(right[k].data(), 1, right[k].size(), in) == right[k].size());
+        cv::Mat img0(H, W, CV_8UC1, left[k].data()), img1(H, W, CV_8UC1, right[k].data());
+        want.push_back(ft.TrackImage(ts[k], img0, img1));
+    }
+    std::fclose(in);
+    for (int k = 0; k < n_frames; ++k) {
+        cv::Mat img0(H, W, CV_8UC1, left[k].data()), img1(H, W, CV_8UC1, right[k].data());
+        pipe.Push(ts[k], img0, img1);
+    }
+    pipe.Flush();
+    CHECK(pipe.FramesTracked() == n_frames);
+    CHECK((int)pipe.Pending() == n_frames / 2);
+    std::pair<double, estimator::FeatureTracker::FeatureFrame> item;
+    for (int k = 1; k < n_frames; k += 2) {                 // input_image_cnt_ % 2 == 0  <=>  0-based index odd
+        CHECK(pipe.Pop(item));
+        CHECK(item.first == ts[k]);
+        CHECK(item.second.size() == want[k].size());
+        auto a = item.second.begin();
+        auto b = want[k].begin();
+        for (; a != item.second.end(); ++a, ++b) {
+            CHECK(a->first == b->first && a->second.size() == b->second.size());
+            for (size_t o = 0; o < a->second.size(); ++o) {
+                CHECK(a->second[o].first == b->second[o].first);
+                for (int q = 0; q < 7; ++q) CHECK(a->second[o].second(q) == b->second[o].second(q));
+            }
+        }
+    }
+    CHECK(!pipe.Pop(item));
+    std::printf("pipe ok: %d frames, %d queued\n", n_frames, n_frames / 2);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     try {
         if (argc >= 5 && std::strcmp(argv[1], "host") == 0) return run_host(argv[2], argv[3], argv[4]);
         if (argc >= 2 && std::strcmp(argv[1], "run") == 0) return run_frames(argc, argv);
+        if (argc >= 2 && std::strcmp(argv[1], "pipe") == 0) return run_pipe(argc, argv);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
         return 2;

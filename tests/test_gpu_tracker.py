@@ -228,3 +228,21 @@ def test_4k_2000_features_level5(lib, oracle):
     seq = StereoSequence(3, 3840, 2160)
     cam = pinhole_for(3840, 2160)
     _run_pair(oracle, [seq.frame(k) for k in range(3)], 3840, 2160, 2000, 30, 1, cam, cam, level=5)
+
+
+def test_cpp_frontend_pipeline_feeds_feature_buf(lib, oracle, euroc_frames, tmp_path):
+    """estimator::FrontendPipeline (include/vins_fast_b200/frontend_pipeline.hpp): Estimator::FrontendTracker + feature_buf_
+    (estimator.cpp:143-158) on the pipelined API; the queued featureFrames equal the synchronous TrackImage results."""
+    import struct
+    import subprocess
+    from conftest import build_cpp_test, write_camera_yaml
+    exe = build_cpp_test("test_feature_tracker")
+    write_camera_yaml(tmp_path / "cam0_mei.yaml", EUROC_CAM0, 752, 480)
+    write_camera_yaml(tmp_path / "cam1_mei.yaml", EUROC_CAM1, 752, 480)
+    n = 9
+    with open(tmp_path / "frames.bin", "wb") as f:
+        for t, l, r in euroc_frames[:n]:
+            f.write(struct.pack("<d", t)); f.write(l.tobytes()); f.write(r.tobytes())
+    res = subprocess.run([exe, "pipe", str(tmp_path / "cam0_mei.yaml"), str(tmp_path / "cam1_mei.yaml"),
+                          str(tmp_path / "frames.bin"), "752", "480", str(n)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "pipe ok" in res.stdout, res.stdout + res.stderr
