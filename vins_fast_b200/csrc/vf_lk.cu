@@ -431,10 +431,10 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             const uint8_t* jt = tj + (iny - jy0) * kTileJ + (inx - jx0);
             // exact int32 products (idle items own zero gradients); pair items form OpenCV's pmaddwd pair sums, tail items keep
-            // single terms.  tx / ty: what this thread adds to b; ab: its sum |term|, clamped so that the total over all
-            // contributing items stays below 2^32
+            // single terms.  tx / ty: what this thread adds to b1 / b2; abx / aby: its sum |term| per
+            // component, clamped so that the totals over all contributing items stay below 2^32
             int ex0[kIpt], ey0[kIpt], ex1[kIpt], ey1[kIpt];
-            int tx = 0, ty = 0, ab = 0;
+            int tx = 0, ty = 0, abx = 0, aby = 0;
 #pragma unroll
             for (int q = 0; q < kIpt; ++q) {
                 const uint8_t* p0 = jt + o0[q];
@@ -444,24 +444,27 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 ex0[q] = d0 * g0[q].x; ey0[q] = d0 * g0[q].y; ex1[q] = d1 * g1[q].x; ey1[q] = d1 * g1[q].y;
                 const int sx_ = ex0[q] + ex1[q], sy_ = ey0[q] + ey1[q];
                 tx += sx_; ty += sy_;
-                ab += min(is_pair[q] ? abs(sx_) + abs(sy_) : abs(ex0[q]) + abs(ey0[q]) + abs(ex1[q]) + abs(ey1[q]), kExact);
+                abx += min(is_pair[q] ? abs(sx_) : abs(ex0[q]) + abs(ex1[q]), kExact);
+                aby += min(is_pair[q] ? abs(sy_) : abs(ey0[q]) + abs(ey1[q]), kExact);
             }
             LK_TF(6);
             const int sx = __reduce_add_sync(0xffffffffu, tx);
             const int sy = __reduce_add_sync(0xffffffffu, ty);
-            const int sa = __reduce_add_sync(0xffffffffu, ab);
+            const int sax = __reduce_add_sync(0xffffffffu, abx);
+            const int say = __reduce_add_sync(0xffffffffu, aby);
             // every warp publishes its three partial sums (double-buffered: the slot of iteration j is rewritten in j+2,
             // after the barrier of j+1); one barrier; every thread folds the kLkWarps partials itself
-            if (lane == 0) sm.part[pbuf][wid] = make_int4(sx, sy, sa, 0);
+            if (lane == 0) sm.part[pbuf][wid] = make_int4(sx, sy, sax, say);
             __syncthreads();
-            int bx = 0, by = 0, bz = 0;
+            int bx = 0, by = 0, bz = 0, bw = 0;
 #pragma unroll
             for (int w = 0; w < kLkWarps; ++w) {
                 const int4 q4 = sm.part[pbuf][w];
-                bx += q4.x; by += q4.y; bz += q4.z;
+                bx += q4.x; by += q4.y; bz += q4.z; bw += q4.w;
             }
             pbuf ^= 1;
-            const unsigned int bnd = (unsigned int)bz;
+            // b1 only adds x-terms, b2 only y-terms: each sum has its own exactness bound
+            const unsigned int bnd = max((unsigned int)bz, (unsigned int)bw);
             LK_TF(7);
             float ib1, ib2;
             if (bnd < (unsigned int)kExact) {
