@@ -75,6 +75,26 @@ public:
     }
     void SetCameras(const vf_camera& left, const vf_camera& right) { cameras_.clear(); cameras_.push_back(left); cameras_.push_back(right); Release(); }
 
+    /// featureFrame of one frame's records (feature_tracker.cpp:173-213): all left observations in ids_ order, then the
+    /// right ones, so every id holds [(0, left)] or [(0, left), (1, right)] -- what feature_manager.cpp:36-43 asserts
+    static FeatureFrame ToFeatureFrame(const vf_feature* records, int n) {
+        FeatureFrame feature_frame;
+        for (int i = 0; i < n; ++i) {                                        // :175-193
+            const vf_feature& r = records[i];
+            Eigen::Matrix<double, 7, 1> xyz_uv_velocity;
+            xyz_uv_velocity << (double)r.x, (double)r.y, 1.0, (double)r.u, (double)r.v, (double)r.vx, (double)r.vy;
+            feature_frame[r.id].emplace_back(0, xyz_uv_velocity);
+        }
+        for (int i = 0; i < n; ++i) {                                        // :195-213
+            const vf_feature& r = records[i];
+            if (!r.has_right) continue;
+            Eigen::Matrix<double, 7, 1> xyz_uv_velocity;
+            xyz_uv_velocity << (double)r.xr, (double)r.yr, 1.0, (double)r.ur, (double)r.vr, (double)r.vxr, (double)r.vyr;
+            feature_frame[r.id].emplace_back(1, xyz_uv_velocity);
+        }
+        return feature_frame;
+    }
+
     /// Main process image fun (feature_tracker.cpp:27-217)
     FeatureFrame TrackImage(double current_time, const cv::Mat& img0, const cv::Mat& img1 = cv::Mat()) {
         if (img0.empty() || img1.empty()) VF_FATAL("TrackImage: !img0.empty() && !img1.empty()");   // assert, :30
@@ -91,25 +111,16 @@ public:
         for (size_t i = 0; i < current_kps_.size(); ++i) previous_left_ids_kps_map_[ids_[i]] = current_kps_[i];   // :158-162 of the previous call
         ids_.clear(); track_count_.clear(); current_kps_.clear(); current_un_distortion_kps_.clear(); pts_velocity.clear();
         ids_right_.clear(); current_right_img_kps_.clear(); current_right_un_distortion_kps_.clear(); right_pts_velocity.clear();
-        FeatureFrame feature_frame;
-        for (int i = 0; i < n; ++i) {                                        // :175-193
+        for (int i = 0; i < n; ++i) {
             const vf_feature& r = records_[i];
             ids_.push_back(r.id); track_count_.push_back(r.track_cnt);
             current_kps_.emplace_back(r.u, r.v); current_un_distortion_kps_.emplace_back(r.x, r.y); pts_velocity.emplace_back(r.vx, r.vy);
-            Eigen::Matrix<double, 7, 1> xyz_uv_velocity;
-            xyz_uv_velocity << (double)r.x, (double)r.y, 1.0, (double)r.u, (double)r.v, (double)r.vx, (double)r.vy;
-            feature_frame[r.id].emplace_back(0, xyz_uv_velocity);
-        }
-        for (int i = 0; i < n; ++i) {                                        // :195-213
-            const vf_feature& r = records_[i];
             if (!r.has_right) continue;
             ids_right_.push_back(r.id);
             current_right_img_kps_.emplace_back(r.ur, r.vr); current_right_un_distortion_kps_.emplace_back(r.xr, r.yr);
             right_pts_velocity.emplace_back(r.vxr, r.vyr);
-            Eigen::Matrix<double, 7, 1> xyz_uv_velocity;
-            xyz_uv_velocity << (double)r.xr, (double)r.yr, 1.0, (double)r.ur, (double)r.vr, (double)r.vxr, (double)r.vyr;
-            feature_frame[r.id].emplace_back(1, xyz_uv_velocity);
         }
+        FeatureFrame feature_frame = ToFeatureFrame(records_.data(), n);
         previous_img_ = current_img_;
         current_img_ = img0;           // shallow, like the reference (:32); the device copy is what the next frame tracks from
         current_right_img_ = img1;

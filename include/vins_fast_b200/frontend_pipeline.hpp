@@ -93,20 +93,7 @@ private:
         const int slot = (int)(index & 1);
         collected_ = index + 1;
         if (collected_ % every_nth_ == 0) {                       // input_image_cnt_ % 2 == 0 in the reference (1-based count)
-            FeatureFrame ff;
-            for (int i = 0; i < n; ++i) {
-                const vf_feature& r = records_[i];
-                Eigen::Matrix<double, 7, 1> v;
-                v << (double)r.x, (double)r.y, 1.0, (double)r.u, (double)r.v, (double)r.vx, (double)r.vy;
-                ff[r.id].emplace_back(0, v);
-            }
-            for (int i = 0; i < n; ++i) {
-                const vf_feature& r = records_[i];
-                if (!r.has_right) continue;
-                Eigen::Matrix<double, 7, 1> v;
-                v << (double)r.xr, (double)r.yr, 1.0, (double)r.ur, (double)r.vr, (double)r.vxr, (double)r.vyr;
-                ff[r.id].emplace_back(1, v);
-            }
+            FeatureFrame ff = FeatureTracker::ToFeatureFrame(records_.data(), n);
             std::unique_lock<std::mutex> lck(feature_buf_mutex_);
             feature_buf_.push(std::make_pair(times_[slot], std::move(ff)));
         }

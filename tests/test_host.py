@@ -281,3 +281,54 @@ def test_cpp_header_compiles_against_the_reference_eigen(tmp_path):
     subprocess.check_call(["g++", "-std=c++14", "-w", "-I", os.path.join(ROOT, "include"), "-I", eigen, str(cpp), "-o", str(exe),
                            "-L", libdir, "-lvinsfast_b200", "-Wl,-rpath," + libdir])
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_feature_frames_feed_the_reference_consumer_types(tmp_path):
+    """featureFrames from the host layer's ToFeatureFrame go through the reference's unchanged
+    ObservedFrameFeature / IDWithObservedFeatures (compiled from the reference tree, this container only) with the calls
+    FeatureManager::AddFeatureAndCheckParallax makes (feature_manager.cpp:25-62); the bookkeeping it derives must match
+    what the golden sequence implies."""
+    ref = "/root/reference/vins"
+    if not os.path.isfile(os.path.join(ref, "estimator", "id_features.hpp")):
+        pytest.skip("reference tree not present")
+    from vins_fast_b200 import FEATURE_DTYPE
+    g = np.load(os.path.join(ROOT, "tests", "golden", "sequence_euroc_mei_cv2_4_13.npz"))
+    n_frames = len([k for k in g.keys() if k.endswith("_ids")])
+    seen, want = {}, []
+    with open(tmp_path / "records.bin", "wb") as f:
+        for k in range(n_frames):
+            ids = g[f"f{k}_ids"]
+            rec = np.zeros(len(ids), FEATURE_DTYPE)
+            rec["id"], rec["track_cnt"] = ids, g[f"f{k}_track_cnt"]
+            rec["u"], rec["v"] = g[f"f{k}_uv"].T
+            rec["x"], rec["y"] = g[f"f{k}_un"].T
+            rec["vx"], rec["vy"] = g[f"f{k}_vel"].T
+            pos = {int(i): j for j, i in enumerate(ids)}
+            rows = [pos[int(i)] for i in g[f"f{k}_ids_right"]]
+            rec["has_right"][rows] = 1
+            rec["ur"][rows], rec["vr"][rows] = g[f"f{k}_uv_right"].T
+            rec["xr"][rows], rec["yr"][rows] = g[f"f{k}_un_right"].T
+            rec["vxr"][rows], rec["vyr"][rows] = g[f"f{k}_vel_right"].T
+            f.write(np.int32(len(rec)).tobytes())
+            f.write(rec.tobytes())
+            last = sum(1 for i in ids if int(i) in seen)
+            for i in ids:
+                seen[int(i)] = seen.get(int(i), 0) + 1
+            long_ = sum(1 for i in ids if seen[int(i)] >= 4)
+            want.append((last, len(ids) - last, long_, len(rows)))
+    exe = tmp_path / "consumer"
+    subprocess.check_call(["g++", "-std=c++14", "-w", "-I", os.path.join(ROOT, "include"), "-I", ref,
+                           "-I", os.path.join(ref, "thirdparty", "eigen"),
+                           os.path.join(ROOT, "tests", "cpp", "test_consumer_types.cpp"), "-o", str(exe),
+                           "-L", os.path.join(ROOT, "vins_fast_b200"), "-lvinsfast_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "vins_fast_b200")])
+    out = subprocess.run([str(exe), str(tmp_path / "records.bin"), str(n_frames)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = [l.split() for l in out.stdout.strip().splitlines()]
+    assert len(lines) == n_frames
+    for k, l in enumerate(lines):
+        assert tuple(int(v) for v in l[:4]) == want[k], (k, l, want[k])
+        rec_sum = sum(float(np.float64(g[f"f{k}_{n}"]).sum()) for n in ("un", "uv", "vel"))
+        rec_sum += sum(float(np.float64(g[f"f{k}_{n}_right"][:, 0]).sum()) for n in ("un", "uv", "vel"))
+        assert abs(float(l[4]) - rec_sum) < 1e-6 * max(1.0, abs(rec_sum))
+    assert want[0][1] == len(g["f0_ids"]) and any(w[2] > 0 for w in want)      # all new on frame 0, long tracks later
