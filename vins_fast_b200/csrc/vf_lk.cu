@@ -621,11 +621,10 @@ __device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // f
 extern __shared__ __align__(16) unsigned char lk_smem_raw[];
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
-__global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const DevBatch* __restrict__ bp, int parity_arg, int cur, int prev) {
+__global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
-    const DevBatch& b = *bp;
     TraceScope trace(b.trace, TR_LK_TEMPORAL + 16 * tphase);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
@@ -688,11 +687,10 @@ __device__ __forceinline__ float2 velocity(float2 cur, float2 prev, double dt) {
 
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
 //      RemoveDistortion + ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
-__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* __restrict__ bp, int parity_arg, int cur, const double* __restrict__ dt_host) {
+__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
-    const DevBatch& b = *bp;
     TraceScope trace(b.trace, TR_LK_STEREO + 16 * tphase);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
     const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
@@ -753,10 +751,9 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const DevBatch* _
 
 // ---- left camera: RemoveDistortion + ComputeKpsVelocity (:103-104, :310-363) and the left half of the record.
 //      Depends on current_kps_ / ids_ only, so it runs beside the stereo LK on the side stream. ----
-__global__ void __launch_bounds__(128) undistort_left_kernel(const DevBatch* __restrict__ bp, int parity_arg, const double* __restrict__ dt_host, int* __restrict__ n_host) {
+__global__ void __launch_bounds__(128) undistort_left_kernel(const __grid_constant__ DevBatch b, int parity_arg, const double* __restrict__ dt_host, int* __restrict__ n_host) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     extern __shared__ int prev_ids_sm[];   // [cap] ids_ of the previous frame
-    const DevBatch& b = *bp;
     TraceScope trace(b.trace, TR_UNDISTORT_LEFT + 16 * tphase);
     const int s = blockIdx.y, cap = b.cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -834,15 +831,15 @@ cudaError_t lk_prepare() {
 
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity, cur, prev);
+    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(h, parity, cur, prev);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(d_batch, parity, cur, dt_host);
+    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(h, parity, cur, dt_host);
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, const double* dt_host, int* n_host, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);
-    undistort_left_kernel<<<grid, 128, sizeof(int) * (size_t)(h.cap > 0 ? h.cap : 1), stream>>>(d_batch, parity, dt_host, n_host);
+    undistort_left_kernel<<<grid, 128, sizeof(int) * (size_t)(h.cap > 0 ? h.cap : 1), stream>>>(h, parity, dt_host, n_host);
 }
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {

@@ -148,13 +148,12 @@ __device__ void block_introsort_loop(SortItem* v, int n, int4* queue, int* qn, i
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const DevBatch* __restrict__ bp, int parity_arg) {
+__global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid_constant__ DevBatch b, int parity_arg) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[ST_THREADS / 32];
     __shared__ int4 sort_queue[2 * kSortQueue];
     __shared__ int sort_qn[2];
-    const DevBatch& b = *bp;
     TraceScope trace(b.trace, TR_SELECT + 16 * tphase);
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, cap = b.cap;
     const SelLayout L(cap);
@@ -322,7 +321,7 @@ cudaError_t select_tracked_prepare(int cap) {
 }
 
 void launch_select_tracked(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
-    select_tracked_kernel<<<h.n_streams, ST_THREADS, select_tracked_smem_bytes(h.cap), stream>>>(d_batch, parity);
+    select_tracked_kernel<<<h.n_streams, ST_THREADS, select_tracked_smem_bytes(h.cap), stream>>>(h, parity);
 }
 
 }  // namespace vf
