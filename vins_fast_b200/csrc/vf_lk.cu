@@ -227,28 +227,43 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     __syncthreads();
     LK_T(0);
     // ---- P2: Scharr (Ix,Iy) on the 22x22 tap positions of every level; zero outside the image.
-    //      A thread owns the same few tile positions on every level: the index arithmetic is level-invariant ----
+    //      A thread owns the same few tile positions on every level (level-invariant index arithmetic); per level it
+    //      first issues the loads of all its positions, then computes, then stores -- the shared-memory stores would
+    //      otherwise fence the next position's loads behind them ----
+    {
+        constexpr int R2 = (kTileD * kTileD + kLkThreads - 1) / kLkThreads;
+        int toff[R2], txy[R2];
 #pragma unroll
-    for (int r = 0; r < (kTileD * kTileD + kLkThreads - 1) / kLkThreads; ++r) {
-        const int e = tid + r * kLkThreads;
-        if (e < kTileD * kTileD) {
+        for (int r = 0; r < R2; ++r) {
+            const int e = min(tid + r * kLkThreads, kTileD * kTileD - 1);
             const int ty = e / kTileD, tx = e - ty * kTileD;
-            const int toff = (ty + 1) * kTileI + (tx + 1);
+            toff[r] = (ty + 1) * kTileI + (tx + 1);
+            txy[r] = tx | (ty << 8);
+        }
 #pragma unroll 1
-            for (int level = 0; level < nlv; ++level) {
-                LevelBlock& B = sm.lv[level];
-                const int4 q = *reinterpret_cast<const int4*>(&B.geo.ipx);     // ipx, ipy, w, h
-                const int x = q.x + tx, y = q.y + ty;
-                const bool inside = (unsigned)x < (unsigned)q.z && (unsigned)y < (unsigned)q.w;
-                const uint8_t* p = B.tileI + toff;                             // always readable; stale for skipped levels
-                const int a00 = p[-kTileI - 1], a01 = p[-kTileI], a02 = p[-kTileI + 1];
-                const int a10 = p[-1], a12 = p[1];
-                const int a20 = p[kTileI - 1], a21 = p[kTileI], a22 = p[kTileI + 1];
-                const int t0m = (a00 + a20) * 3 + a10 * 10, t0p = (a02 + a22) * 3 + a12 * 10;
-                const int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
-                const int ix = inside ? t0p - t0m : 0, iy = inside ? (t1m + t1p) * 3 + t1c * 10 : 0;
-                B.dtile[e] = make_short2((short)ix, (short)iy);
+        for (int level = 0; level < nlv; ++level) {
+            LevelBlock& B = sm.lv[level];
+            const int4 q = *reinterpret_cast<const int4*>(&B.geo.ipx);     // ipx, ipy, w, h
+            int a[R2][8];
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                const uint8_t* p = B.tileI + toff[r];                      // always readable; stale for skipped levels
+                a[r][0] = p[-kTileI - 1]; a[r][1] = p[-kTileI]; a[r][2] = p[-kTileI + 1];
+                a[r][3] = p[-1]; a[r][4] = p[1];
+                a[r][5] = p[kTileI - 1]; a[r][6] = p[kTileI]; a[r][7] = p[kTileI + 1];
             }
+            short2 d[R2];
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                const int x = q.x + (txy[r] & 0xff), y = q.y + (txy[r] >> 8);
+                const bool inside = (unsigned)x < (unsigned)q.z && (unsigned)y < (unsigned)q.w;
+                const int t0m = (a[r][0] + a[r][5]) * 3 + a[r][3] * 10, t0p = (a[r][2] + a[r][7]) * 3 + a[r][4] * 10;
+                const int t1m = a[r][5] - a[r][0], t1c = a[r][6] - a[r][1], t1p = a[r][7] - a[r][2];
+                d[r] = make_short2((short)(inside ? t0p - t0m : 0), (short)(inside ? (t1m + t1p) * 3 + t1c * 10 : 0));
+            }
+#pragma unroll
+            for (int r = 0; r < R2; ++r)
+                if (tid + r * kLkThreads < kTileD * kTileD) B.dtile[tid + r * kLkThreads] = d[r];
         }
     }
     __syncthreads();
@@ -256,29 +271,43 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     // ---- P3: 21x21 bilinear patches (I in 2^5, derivatives in Scharr units) of every level + the terms of A, stored
     //      in OpenCV's accumulation order: SIMD lane l = x & 3 sees columns l, 4+l, 8+l, 12+l of every row in turn
     //      (slot y*4 + x/4 of chain l), the scalar tail sees columns 16..20 of every row (slot y*5 + x-16 of chain 4) ----
+    {
+        constexpr int R3 = (kWinPx + kLkThreads - 1) / kLkThreads;
+        int ioff[R3], doff[R3], aoff[R3];
 #pragma unroll
-    for (int r = 0; r < (kWinPx + kLkThreads - 1) / kLkThreads; ++r) {
-        const int e = tid + r * kLkThreads;
-        if (e < kWinPx) {
+        for (int r = 0; r < R3; ++r) {
+            const int e = min(tid + r * kLkThreads, kWinPx - 1);
             const int y = e / kWin, x = e - y * kWin;
-            const int ioff = (y + 1) * kTileI + (x + 1), doff = y * kTileD + x;
-            const int aoff = x < 16 ? (x & 3) * kChainA + y * 4 + (x >> 2) : 4 * kChainA + y * 5 + (x - 16);
+            ioff[r] = (y + 1) * kTileI + (x + 1); doff[r] = y * kTileD + x;
+            aoff[r] = x < 16 ? (x & 3) * kChainA + y * 4 + (x >> 2) : 4 * kChainA + y * 5 + (x - 16);
+        }
 #pragma unroll 1
-            for (int level = 0; level < nlv; ++level) {
-                LevelBlock& B = sm.lv[level];
-                const int4 w = *reinterpret_cast<const int4*>(&B.geo.w00);
-                const uint8_t* s = B.tileI + ioff;
-                const int ival = VF_DESCALE(s[0] * w.x + s[1] * w.y + s[kTileI] * w.z + s[kTileI + 1] * w.w, 9);
-                const short2* dt = B.dtile + doff;
-                const short2 d00 = dt[0], d01 = dt[1], d10 = dt[kTileD], d11 = dt[kTileD + 1];
-                const int ixval = VF_DESCALE(d00.x * w.x + d01.x * w.y + d10.x * w.z + d11.x * w.w, 14);
-                const int iyval = VF_DESCALE(d00.y * w.x + d01.y * w.y + d10.y * w.z + d11.y * w.w, 14);
-                B.Iw[e] = (short)ival;
-                B.dI[e] = make_short2((short)ixval, (short)iyval);
-                float* ta = B.termsA + aoff;                       // |ixval|, |iyval| <= 4080: products < 2^24, exact in float
-                ta[0] = (float)(ixval * ixval);
-                ta[5 * kChainA] = (float)(ixval * iyval);
-                ta[10 * kChainA] = (float)(iyval * iyval);
+        for (int level = 0; level < nlv; ++level) {
+            LevelBlock& B = sm.lv[level];
+            const int4 w = *reinterpret_cast<const int4*>(&B.geo.w00);
+            int sv[R3][4];
+            short2 dv[R3][4];
+#pragma unroll
+            for (int r = 0; r < R3; ++r) {                                 // loads of all positions first (see P2)
+                const uint8_t* s = B.tileI + ioff[r];
+                sv[r][0] = s[0]; sv[r][1] = s[1]; sv[r][2] = s[kTileI]; sv[r][3] = s[kTileI + 1];
+                const short2* dt = B.dtile + doff[r];
+                dv[r][0] = dt[0]; dv[r][1] = dt[1]; dv[r][2] = dt[kTileD]; dv[r][3] = dt[kTileD + 1];
+            }
+#pragma unroll
+            for (int r = 0; r < R3; ++r) {
+                const int e = tid + r * kLkThreads;
+                const int ival = VF_DESCALE(sv[r][0] * w.x + sv[r][1] * w.y + sv[r][2] * w.z + sv[r][3] * w.w, 9);
+                const int ixval = VF_DESCALE(dv[r][0].x * w.x + dv[r][1].x * w.y + dv[r][2].x * w.z + dv[r][3].x * w.w, 14);
+                const int iyval = VF_DESCALE(dv[r][0].y * w.x + dv[r][1].y * w.y + dv[r][2].y * w.z + dv[r][3].y * w.w, 14);
+                if (e < kWinPx) {
+                    B.Iw[e] = (short)ival;
+                    B.dI[e] = make_short2((short)ixval, (short)iyval);
+                    float* ta = B.termsA + aoff[r];                    // |ixval|, |iyval| <= 4080: products < 2^24, exact in float
+                    ta[0] = (float)(ixval * ixval);
+                    ta[5 * kChainA] = (float)(ixval * iyval);
+                    ta[10 * kChainA] = (float)(iyval * iyval);
+                }
             }
         }
     }
