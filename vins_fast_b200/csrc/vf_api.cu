@@ -52,11 +52,11 @@ struct vf_tracker {
 struct vf_batch {
     vf_config cfg;
     int S = 0, device = 0;
-    cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr, side_d = nullptr;
+    cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr, side_d = nullptr, side_e = nullptr;
     bool own_main = false, serialized = false;
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
-    cudaEvent_t ev_fork = nullptr, ev_resp = nullptr, ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
-                ev_sel = nullptr, ev_un = nullptr, ev_clear = nullptr, ev_pyrl = nullptr, ev_scat = nullptr,
+    cudaEvent_t ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
+                ev_sel = nullptr, ev_un = nullptr, ev_pyrl = nullptr, ev_scat = nullptr,
                 ev_chain[2] = {nullptr, nullptr};
     uint8_t* stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // unpadded upload targets [camera][parity]: [S][H][stage_pitch]
     int stage_pitch = 0;
@@ -66,13 +66,14 @@ struct vf_batch {
     vf_feature* pin_out[2] = {nullptr, nullptr};   // mapped pinned: records of the frames of each parity
     int* pin_n[2] = {nullptr, nullptr};            // mapped pinned: [S] feature counts
     int* dev_n[2] = {nullptr, nullptr};            // their device addresses
-    double* pin_dt = nullptr;                      // mapped pinned ring [4][S]: time since the previous frame
+    double* pin_dt = nullptr;                      // mapped pinned ring [6][S] (slot = frame % 6): time since the previous frame
     double* dev_dt = nullptr;
     std::vector<double> prev_times;
     long frame = 0;
     int last_parity = -1;
-    cudaGraphExec_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per frame % 6 (parity x pyramid ring slot)
-    int launches = 0, chain_launches = 0;
+    cudaGraphExec_t graph[4][6] = {};
+    int pyr_launches = 1;   // one per frame % 6 (parity x pyramid ring slot)
+    int launches = 0;
     std::string err;
     std::vector<vf_tracker> views;
     size_t bytes_allocated = 0;
@@ -198,7 +199,7 @@ CamParams to_cam(const vf_camera& c) {
 
 cudaError_t sync_all(vf_batch* b) {   // every stream a frame is spread over
     cudaError_t e = cudaSuccess;
-    for (cudaStream_t st : {b->main, b->side_a, b->side_b, b->side_c, b->side_d})
+    for (cudaStream_t st : {b->main, b->side_a, b->side_b, b->side_c, b->side_d, b->side_e})
         if (st) { const cudaError_t r = cudaStreamSynchronize(st); if (r != cudaSuccess) e = r; }
     return e;
 }
@@ -207,7 +208,7 @@ void destroy_batch(vf_batch* b) {
     if (!b) return;
     DeviceGuard g(b->device);
     sync_all(b);
-    for (int p = 0; p < 6; ++p) if (b->graph[p]) cudaGraphExecDestroy(b->graph[p]);
+    for (int w = 0; w < 4; ++w) for (int p = 0; p < 6; ++p) if (b->graph[w][p]) cudaGraphExecDestroy(b->graph[w][p]);
     for (void* p : b->allocs) cudaFree(p);
     if (b->d) cudaFree(b->d);
     for (int p = 0; p < 2; ++p) {
@@ -217,13 +218,10 @@ void destroy_batch(vf_batch* b) {
         if (b->ev_done[p + 2]) cudaEventDestroy(b->ev_done[p + 2]);
     }
     if (b->pin_dt) cudaFreeHost(b->pin_dt);
-    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
-    if (b->ev_resp) cudaEventDestroy(b->ev_resp);
     if (b->ev_right) cudaEventDestroy(b->ev_right);
     if (b->ev_img) cudaEventDestroy(b->ev_img);
     if (b->ev_sel) cudaEventDestroy(b->ev_sel);
     if (b->ev_un) cudaEventDestroy(b->ev_un);
-    if (b->ev_clear) cudaEventDestroy(b->ev_clear);
     if (b->ev_pyrl) cudaEventDestroy(b->ev_pyrl);
     if (b->ev_scat) cudaEventDestroy(b->ev_scat);
     for (int p = 0; p < 2; ++p) if (b->ev_chain[p]) cudaEventDestroy(b->ev_chain[p]);
@@ -232,6 +230,7 @@ void destroy_batch(vf_batch* b) {
     if (b->side_b && !b->serialized) cudaStreamDestroy(b->side_b);
     if (b->side_c && !b->serialized) cudaStreamDestroy(b->side_c);
     if (b->side_d && !b->serialized) cudaStreamDestroy(b->side_d);
+    if (b->side_e && !b->serialized) cudaStreamDestroy(b->side_e);
     if (b->own_main && b->main) cudaStreamDestroy(b->main);
     delete b;
 }
@@ -252,47 +251,64 @@ vf_status reset_state(vf_batch* b) {
     return VF_OK;
 }
 
-// The kernels of the left chain, issued on main/side_a (directly, or under stream capture).
-vf_status issue_left_chain(vf_batch* b, int parity_, int cur, int prev, int phase) {
+// The kernel sequences of a frame.  Each can be issued directly or captured into a graph (one executable per frame % 6:
+// parity, slots of the left pyramid ring, the frame-interval slot and the trace slot are baked into the launches).
+//   SEQ_CORNER     side A: per-frame accumulators, response + local maxima, candidate buckets.  Reads the uploaded image
+//                  only and writes parity-buffered outputs, so it may run ahead of the frame's chain.
+//   SEQ_CHAIN      main: the frame-to-frame chain proper, four kernels in a row with no join in between -- every
+//                  cross-stream input (left pyramid, corner stage) is waited for once, ahead of the first kernel.
+//   SEQ_HEAD_SYNC  main, synchronous frames: left pyramid + temporal LK back to back (behind the left upload).
+//   SEQ_REST_SYNC  main, synchronous frames: what follows the temporal LK, with the stereo pass appended and the left
+//                  undistortion on a branch beside it.
+enum { SEQ_CORNER = 0, SEQ_CHAIN = 1, SEQ_REST_SYNC = 2, SEQ_HEAD_SYNC = 3, SEQ_COUNT = 4 };
+
+vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev, int phase) {
     const DevBatch& h = b->h;
     const int parity = parity_ | (phase << 4);   // kernels take the frame parity in bit 0 and the trace slot above it
-    int n = 0;
-    // side A: clear the per-frame accumulators, then the corner response chain (reads the uploaded image only)
-    VF_CUDA(b, cudaEventRecord(b->ev_fork, b->main));
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_fork, 0));
-    { StageTimer t(b, ST_CLEAR, b->side_a); launch_clear_frame(b->d, h, parity, b->side_a); ++n; }
-    VF_CUDA(b, cudaEventRecord(b->ev_clear, b->side_a));
-    { StageTimer t(b, ST_RESPONSE_NMS, b->side_a); launch_response_nms(b->d, h, parity, b->side_a); ++n; }
-    VF_CUDA(b, cudaEventRecord(b->ev_resp, b->side_a));          // the mask stage needs the response map and the candidate flags
-    { StageTimer t(b, ST_BUCKET_SCAN, b->side_a); launch_bucket_scan(b->d, h, parity, b->side_a); ++n; }
-    { StageTimer t(b, ST_BUCKET_SCATTER, b->side_a); launch_bucket_scatter(b->d, h, parity, b->side_a); ++n; }
-    VF_CUDA(b, cudaEventRecord(b->ev_scat, b->side_a));          // only the corner selection (bucket walk) needs the buckets
-    // main: the frame-to-frame chain proper (the pyramid of the new left image was built on side B, possibly while the
-    // previous frame was still on the chain)
-    { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); ++n; }
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_clear, 0));     // select_tracked writes this frame's counters
-    { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); ++n; }
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_resp, 0));
-    { StageTimer t(b, ST_MASK_AND_MAX, b->main); launch_mask_and_max(b->d, h, parity, b->main); ++n; }
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
-    { StageTimer t(b, ST_GFTT_SELECT, b->main); launch_gftt_select(b->d, h, parity, b->main); ++n; }
+    const double* dev_dt = b->dev_dt + (size_t)phase * b->S;
+    if (which == SEQ_HEAD_SYNC) {
+        {
+            StageTimer t(b, ST_PYR_LEFT, b->main);
+            const Level0Src src = {b->stage[0][parity_], b->stage_pitch, (size_t)b->stage_pitch * h.H};
+            b->pyr_launches = launch_pyramid(h.left[cur], h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT + 16 * phase);
+        }
+        { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); }
+    } else if (which == SEQ_CORNER) {
+        { StageTimer t(b, ST_CLEAR, b->side_a); launch_clear_frame(b->d, h, parity, b->side_a); }
+        { StageTimer t(b, ST_RESPONSE_NMS, b->side_a); launch_response_nms(b->d, h, parity, b->side_a); }
+        { StageTimer t(b, ST_BUCKET_SCAN, b->side_a); launch_bucket_scan(b->d, h, parity, b->side_a); }
+        { StageTimer t(b, ST_BUCKET_SCATTER, b->side_a); launch_bucket_scatter(b->d, h, parity, b->side_a); }
+    } else {
+        if (which == SEQ_CHAIN) { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); }
+        { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); }
+        { StageTimer t(b, ST_MASK_AND_MAX, b->main); launch_mask_and_max(b->d, h, parity, b->main); }
+        { StageTimer t(b, ST_GFTT_SELECT, b->main); launch_gftt_select(b->d, h, parity, b->main); }
+        if (which == SEQ_REST_SYNC) {
+            VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
+            VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
+            { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity, dev_dt, b->dev_n[parity_], b->side_e); }
+            VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
+            { StageTimer t(b, ST_LK_STEREO, b->main); launch_lk_stereo(b->d, h, parity, cur, dev_dt, b->main); }
+            VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_un, 0));
+        }
+    }
     VF_CUDA(b, cudaGetLastError());
-    b->chain_launches = n;
     return VF_OK;
 }
 
-vf_status build_graph(vf_batch* b, int phase) {   // phase = frame % 6
+vf_status build_graph(vf_batch* b, int phase, int which) {
     cudaGraph_t graph = nullptr;
     const int parity = phase & 1, cur = phase % 3, prev = (phase + 2) % 3;
-    VF_CUDA(b, cudaStreamBeginCapture(b->main, cudaStreamCaptureModeThreadLocal));
-    vf_status st = issue_left_chain(b, parity, cur, prev, phase);
-    cudaError_t e = cudaStreamEndCapture(b->main, &graph);
+    cudaStream_t st_cap = which == SEQ_CORNER ? b->side_a : b->main;
+    VF_CUDA(b, cudaStreamBeginCapture(st_cap, cudaStreamCaptureModeThreadLocal));
+    vf_status st = issue_sequence(b, which, parity, cur, prev, phase);
+    cudaError_t e = cudaStreamEndCapture(st_cap, &graph);
     if (st != VF_OK) { if (graph) cudaGraphDestroy(graph); return st; }
     VF_CUDA(b, e);
-    e = cudaGraphInstantiate(&b->graph[phase], graph, 0);
+    e = cudaGraphInstantiate(&b->graph[which][phase], graph, 0);
     cudaGraphDestroy(graph);
     VF_CUDA(b, e);
-    VF_CUDA(b, cudaGraphUpload(b->graph[phase], b->main));   // keep the executable resident on the device: shorter launch latency
+    VF_CUDA(b, cudaGraphUpload(b->graph[which][phase], st_cap));   // keep the executable resident on the device: shorter launch latency
     return VF_OK;
 }
 
@@ -300,7 +316,7 @@ vf_status build_graph(vf_batch* b, int phase) {   // phase = frame % 6
 // when `contiguous`, else at imgs[c][s].
 vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* img0, const uint8_t* const* img1,
                         const uint8_t* base0, const uint8_t* base1, size_t image_stride, size_t stride0, size_t stride1,
-                        cudaMemcpyKind kind) {
+                        cudaMemcpyKind kind, bool overlap) {
     DeviceGuard g(b->device);
     if (!g.ok) return fail(b, VF_ERR_CUDA, "cudaSetDevice failed");
     const DevBatch& h = b->h;
@@ -331,9 +347,9 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_chain[parity], 0));
         if (b->frame >= 3) VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_done[(slot + 1) & 3], 0));
     }
-    double* pdt = b->pin_dt + (size_t)slot * S;                              // current_time_ - previous_time_ (feature_tracker.cpp:338)
+    double* pdt = b->pin_dt + (size_t)phase * S;                              // current_time_ - previous_time_ (feature_tracker.cpp:338)
     for (int s = 0; s < S; ++s) { pdt[s] = times[s] - b->prev_times[s]; b->prev_times[s] = times[s]; }
-    const double* dev_dt = b->dev_dt + (size_t)slot * S;
+    const double* dev_dt = b->dev_dt + (size_t)phase * S;
     for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
     // All uploads of the frame go through side B, in the order the frame needs them: times, left image, right image.
     // The staging buffers are double-buffered by parity, so with asynchronous enqueues the upload of frame k+1 overlaps
@@ -353,54 +369,95 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     };
     { StageTimer t(b, ST_H2D_LEFT, b->side_b); VF_CUDA(b, upload(0, img0, base0, stride0, b->side_b)); }
     VF_CUDA(b, cudaEventRecord(b->ev_img, b->side_b));
-    // left pyramid on side B right behind its upload: it does not depend on the previous frame, so with asynchronous
-    // enqueues it is built while the previous frame is still on the chain
+    // right image on side D; its upload queues behind the left one so that the left image (which the frame's critical path
+    // waits for) has the link to itself.  A synchronous frame issues it now (the stereo pass is part of its chain); an
+    // overlapped one issues it after the chain -- host order is how soon the chain reaches the GPU.
+    auto issue_right = [&]() -> vf_status {
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_img, 0));
+        { StageTimer t(b, ST_H2D_RIGHT, b->side_d); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_d)); }
+        return VF_OK;
+    };
+    auto issue_right_pyramid = [&](int& n) -> vf_status {
+        StageTimer t(b, ST_PYR_RIGHT, b->side_d);
+        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
+        n += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_d, &src, h.trace, TR_PYR_RIGHT + 16 * phase);
+        VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
+        return VF_OK;
+    };
+    if (!overlap) { vf_status st = issue_right(); if (st != VF_OK) return st; }
+    // left pyramid: an overlapped frame builds it on side B right behind its upload (it does not depend on the previous
+    // frame, so it is built while that one is still on the chain); a synchronous frame builds it on main, back to back with
+    // the temporal LK
     int n_launch = 0;
-    {
+    if (overlap) {
         StageTimer t(b, ST_PYR_LEFT, b->side_b);
         const Level0Src src = {b->stage[0][parity], b->stage_pitch, simg};
         n_launch += launch_pyramid(h.left[cur], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_LEFT + 16 * phase);
+        VF_CUDA(b, cudaEventRecord(b->ev_pyrl, b->side_b));
     }
-    VF_CUDA(b, cudaEventRecord(b->ev_pyrl, b->side_b));
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));     // the corner response reads the staging image
-    VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_pyrl, 0));
-    // left chain first (host order = how soon the work reaches the GPU: the chain is the critical path)
-    if (b->cfg.use_cuda_graph && !b->profiling) {
-        if (!b->graph[phase]) {
-            vf_status st = build_graph(b, phase);
-            if (st != VF_OK) return st;
+    const bool use_graph = b->cfg.use_cuda_graph && !b->profiling;
+    auto run = [&](int which, cudaStream_t st) -> vf_status {   // one of the captured kernel sequences, as a graph or directly
+        if (use_graph) {
+            if (!b->graph[which][phase]) {
+                vf_status r = build_graph(b, phase, which);
+                if (r != VF_OK) return r;
+            }
+            VF_CUDA(b, cudaGraphLaunch(b->graph[which][phase], st));
+            return VF_OK;
         }
-        VF_CUDA(b, cudaGraphLaunch(b->graph[phase], b->main));
-    } else {
-        vf_status st = issue_left_chain(b, parity, cur, prev, phase);
+        return issue_sequence(b, which, parity, cur, prev, phase);
+    };
+    // corner stage on side A right behind the left upload (the staging image is all it reads)
+    auto issue_corner = [&]() -> vf_status {
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_img, 0));
+        vf_status st = run(SEQ_CORNER, b->side_a);
         if (st != VF_OK) return st;
+        VF_CUDA(b, cudaEventRecord(b->ev_scat, b->side_a));
+        return VF_OK;
+    };
+    if (overlap) {
+        { vf_status st = issue_corner(); if (st != VF_OK) return st; }
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_pyrl, 0));
+        // Asynchronous enqueue: the corner stage ran while the previous frame was on the chain, so the chain joins it up
+        // front (for free) and is four kernels in a row; the stereo pass gets its own stream and overlaps the next chain.
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
+        { vf_status st = run(SEQ_CHAIN, b->main); if (st != VF_OK) return st; }
+        VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
+        VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
+        { vf_status st = issue_right(); if (st != VF_OK) return st; }
+        { vf_status st = issue_right_pyramid(n_launch); if (st != VF_OK) return st; }
+        // left camera's undistortion + velocity beside the stereo pass (needs current_kps_ / ids_ only)
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
+        { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[parity], b->side_e); }
+        VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
+        { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); }
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
+        VF_CUDA(b, cudaGetLastError());
+        VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->side_c));
+    } else {
+        // Synchronous frame: nothing to overlap with, so the temporal LK starts as soon as the left pyramid stands (the
+        // corner stage runs beside it and is joined before select_tracked) and the stereo pass follows the corner
+        // selection inside the same graph, the left undistortion on a branch beside it.
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
+        { vf_status st = run(SEQ_HEAD_SYNC, b->main); if (st != VF_OK) return st; }
+        n_launch += b->pyr_launches;
+        { vf_status st = issue_corner(); if (st != VF_OK) return st; }
+        { vf_status st = issue_right_pyramid(n_launch); if (st != VF_OK) return st; }
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
+        // the stereo pass / left undistortion read what the previous frame's wrote (velocity): if that frame was an
+        // overlapped one they ran on other streams
+        if (b->frame >= 1) VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 3) & 3], 0));
+        { vf_status st = run(SEQ_REST_SYNC, b->main); if (st != VF_OK) return st; }
+        VF_CUDA(b, cudaGetLastError());
+        VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
+        VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
+        VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->main));
     }
-    n_launch += b->chain_launches;
-    // right image + right pyramid on side D; the right upload queues behind the left one so that the left image (which
-    // the frame's critical path waits for) has the link to itself
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_img, 0));
-    { StageTimer t(b, ST_H2D_RIGHT, b->side_d); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_d)); }
-    {
-        StageTimer t(b, ST_PYR_RIGHT, b->side_d);
-        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
-        n_launch += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_d, &src, h.trace, TR_PYR_RIGHT + 16 * phase);
-    }
-    VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
-    // The stereo LK is not on the frame-to-frame dependency chain (frame k+1 only needs current_kps_ / ids_ of frame k),
-    // so it runs on its own stream: with asynchronous enqueues it overlaps the temporal chain of the next frame.
-    // Beside it, the left camera's undistortion + velocity (needs current_kps_ / ids_ only).
-    VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
-    VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_sel, 0));
-    { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_a); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[parity], b->side_a); ++n_launch; }
-    VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_a));
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
-    { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); ++n_launch; }
-    VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
-    VF_CUDA(b, cudaGetLastError());
+    n_launch += 4 /* corner stage */ + 4 /* chain */ + 2 /* stereo, left undistortion */;
     // no download commands: the records and the feature counts were written to mapped pinned host memory by the kernels
-    VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->side_c));
     b->launches = n_launch;
     b->last_parity = parity;
     b->frame++;
@@ -496,20 +553,18 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     if (cfg->cuda_stream) { b->main = (cudaStream_t)cfg->cuda_stream; b->own_main = false; }
     else { TRYC(cudaStreamCreateWithPriority(&b->main, cudaStreamNonBlocking, prio_hi)); b->own_main = true; }
     if (getenv("VF_SERIALIZE")) {   // measurement aid: one stream, no overlap between the stages of a frame
-        b->side_a = b->main; b->side_b = b->main; b->side_c = b->main; b->side_d = b->main; b->serialized = true;
+        b->side_a = b->main; b->side_b = b->main; b->side_c = b->main; b->side_d = b->main; b->side_e = b->main; b->serialized = true;
     } else {
         TRYC(cudaStreamCreateWithPriority(&b->side_a, cudaStreamNonBlocking, prio_lo));
         TRYC(cudaStreamCreateWithPriority(&b->side_b, cudaStreamNonBlocking, prio_hi));    // left pyramid: the chain waits for it
         TRYC(cudaStreamCreateWithPriority(&b->side_d, cudaStreamNonBlocking, prio_lo));
+        TRYC(cudaStreamCreateWithPriority(&b->side_e, cudaStreamNonBlocking, prio_lo));
         TRYC(cudaStreamCreateWithPriority(&b->side_c, cudaStreamNonBlocking, prio_mid));
     }
-    TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
-    TRYC(cudaEventCreateWithFlags(&b->ev_resp, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_right, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_img, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_un, cudaEventDisableTiming));
-    TRYC(cudaEventCreateWithFlags(&b->ev_clear, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_pyrl, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_scat, cudaEventDisableTiming));
     for (int p = 0; p < 2; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_chain[p], cudaEventDisableTiming));
@@ -547,11 +602,15 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRY(dalloc(b, &h.fwd_pts, SC)); TRY(dalloc(b, &h.fwd_st, SC)); TRY(dalloc(b, &h.rev_pts, SC)); TRY(dalloc(b, &h.rev_st, SC));
     TRY(dalloc(b, &h.temporal_st, SC)); TRY(dalloc(b, &h.lr_pts, SC)); TRY(dalloc(b, &h.lr_st, SC)); TRY(dalloc(b, &h.rl_pts, SC));
     TRY(dalloc(b, &h.rl_st, SC)); TRY(dalloc(b, &h.sort_perm, SC)); TRY(dalloc(b, &h.lk_iters, SC)); TRY(dalloc(b, &h.lk_iters_stereo, SC));
-    TRY(dalloc(b, &h.eig, SP)); TRY(dalloc(b, &h.mask, SP)); TRY(dalloc(b, &h.lmflag, SP));
+    TRY(dalloc(b, &h.mask, SP));
     TRY(dalloc(b, &h.surv, (size_t)S * h.cand_cap));
-    TRY(dalloc(b, &h.cand, (size_t)S * h.cand_cap)); TRY(dalloc(b, &h.cand_sorted, (size_t)S * h.cand_cap));
-    TRY(dalloc(b, &h.hist, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start, (size_t)S * (h.n_buckets + 1)));
-    TRY(dalloc(b, &h.bucket_fill, (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz, (size_t)S * h.n_buckets));
+    for (int p = 0; p < 2; ++p) {   // corner stage, double-buffered: frame k+1's response runs while frame k is on the chain
+        TRY(dalloc(b, &h.eig[p], SP)); TRY(dalloc(b, &h.lmflag[p], SP));
+        TRY(dalloc(b, &h.cand[p], (size_t)S * h.cand_cap)); TRY(dalloc(b, &h.cand_sorted[p], (size_t)S * h.cand_cap));
+        TRY(dalloc(b, &h.hist[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start[p], (size_t)S * (h.n_buckets + 1)));
+        TRY(dalloc(b, &h.bucket_fill[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz[p], (size_t)S * h.n_buckets));
+        TRY(dalloc(b, &h.ccnt[p], (size_t)S * C_COUNT));
+    }
     if (cap > 512) TRY(dalloc(b, &h.conflict, (size_t)S * cap * ((cap + 31) / 32)));
     // result records, feature counts and frame intervals live in mapped pinned host memory: the kernels write / read them
     // in place, no copy commands at either end of a frame
@@ -563,7 +622,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
         memset(b->pin_n[p], 0, sizeof(int) * (size_t)S);
         TRYC(cudaHostGetDevicePointer((void**)&b->dev_n[p], b->pin_n[p], 0));
     }
-    TRYC(cudaHostAlloc(&b->pin_dt, sizeof(double) * (size_t)S * 4, cudaHostAllocMapped));
+    TRYC(cudaHostAlloc(&b->pin_dt, sizeof(double) * (size_t)S * 6, cudaHostAllocMapped));
     TRYC(cudaHostGetDevicePointer((void**)&b->dev_dt, b->pin_dt, 0));
     b->prev_times.assign(S, 0.0);
     TRYC(cudaMalloc(&b->d, sizeof(DevBatch)));
@@ -628,19 +687,24 @@ vf_status vf_batch_track(vf_batch* b, const double* times, const uint8_t* const*
                          const uint8_t* const* img1, size_t stride1, vf_feature* out, int32_t* n_out) {
     if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
     if (!img0 || !img1) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
-    vf_status st = enqueue_frame(b, times, img0, img1, nullptr, nullptr, 0, stride0, stride1, cudaMemcpyHostToDevice);
+    vf_status st = enqueue_frame(b, times, img0, img1, nullptr, nullptr, 0, stride0, stride1, cudaMemcpyHostToDevice, false);
     if (st != VF_OK) return st;
     return fetch_frame(b, out, n_out);
 }
 
-vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
-                                  size_t row_stride, size_t image_stride_bytes) {
+static vf_status enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
+                                size_t row_stride, size_t image_stride_bytes, bool overlap) {
     if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
     if (!d_img0 || !d_img1) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
     if (b->S > 1 && image_stride_bytes < row_stride * (size_t)b->h.H)
         return fail(b, VF_ERR_INVALID_ARG, "image_stride_bytes is smaller than one image");
     return enqueue_frame(b, times, nullptr, nullptr, d_img0, d_img1, image_stride_bytes, row_stride, row_stride,
-                         cudaMemcpyDeviceToDevice);
+                         cudaMemcpyDeviceToDevice, overlap);
+}
+
+vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
+                                  size_t row_stride, size_t image_stride_bytes) {
+    return enqueue_device(b, times, d_img0, d_img1, row_stride, image_stride_bytes, true);
 }
 
 vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out) {
@@ -657,12 +721,12 @@ vf_status vf_batch_enqueue(vf_batch* b, const double* times, const uint8_t* cons
                            const uint8_t* const* img1, size_t stride1) {
     if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
     if (!img0 || !img1) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
-    return enqueue_frame(b, times, img0, img1, nullptr, nullptr, 0, stride0, stride1, cudaMemcpyHostToDevice);
+    return enqueue_frame(b, times, img0, img1, nullptr, nullptr, 0, stride0, stride1, cudaMemcpyHostToDevice, true);
 }
 
 vf_status vf_batch_track_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
                                 size_t row_stride, size_t image_stride_bytes, vf_feature* out, int32_t* n_out) {
-    vf_status st = vf_batch_enqueue_device(b, times, d_img0, d_img1, row_stride, image_stride_bytes);
+    vf_status st = enqueue_device(b, times, d_img0, d_img1, row_stride, image_stride_bytes, false);
     if (st != VF_OK) return st;
     return fetch_frame(b, out, n_out);
 }
@@ -722,6 +786,7 @@ vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* b
     const int s = t->stream_index, p = b->last_parity, cap = h.cap;
     int cnt_now[C_COUNT];
     VF_CUDA(b, cudaMemcpy(cnt_now, h.counters[p] + s * C_COUNT, sizeof(cnt_now), cudaMemcpyDeviceToHost));
+    VF_CUDA(b, cudaMemcpy(&cnt_now[C_N_LOCALMAX], h.ccnt[p] + s * C_COUNT + C_N_LOCALMAX, sizeof(int), cudaMemcpyDeviceToHost));
     const size_t so = (size_t)s * cap;
     const void* src = nullptr;
     size_t bytes = 0;
@@ -737,7 +802,7 @@ vf_status vf_tracker_debug_get(vf_tracker* t, int32_t what, int32_t arg, void* b
                                     pv.h[arg], cudaMemcpyDeviceToHost));
             return VF_OK;
         }
-        case VF_DBG_EIG: src = h.eig + (size_t)s * h.W * h.H; bytes = sizeof(float) * (size_t)h.W * h.H; break;
+        case VF_DBG_EIG: src = h.eig[p] + (size_t)s * h.W * h.H; bytes = sizeof(float) * (size_t)h.W * h.H; break;
         case VF_DBG_MASK: src = h.mask + (size_t)s * h.W * h.H; bytes = (size_t)h.W * h.H; break;
         case VF_DBG_FWD_PTS: src = h.fwd_pts + so; bytes = sizeof(float2) * (size_t)cnt_now[C_N_PREV]; break;
         case VF_DBG_FWD_STATUS: src = h.fwd_st + so; bytes = (size_t)cnt_now[C_N_PREV]; break;
@@ -916,7 +981,7 @@ vf_status vf_op_min_eigen(const uint8_t* img, int32_t w, int32_t h, int32_t devi
     launch_clear_frame(b->d, b->h, 0, b->main);
     launch_response_nms(b->d, b->h, 0, b->main);
     VF_CUDA(b, cudaGetLastError());
-    VF_CUDA(b, cudaMemcpyAsync(out, b->h.eig, sizeof(float) * (size_t)w * h, cudaMemcpyDeviceToHost, b->main));
+    VF_CUDA(b, cudaMemcpyAsync(out, b->h.eig[0], sizeof(float) * (size_t)w * h, cudaMemcpyDeviceToHost, b->main));
     VF_CUDA(b, cudaStreamSynchronize(b->main));
     return VF_OK;
 }
@@ -938,6 +1003,7 @@ vf_status vf_op_good_features(const uint8_t* img, int32_t w, int32_t h, int32_t 
     launch_bucket_scatter(b->d, b->h, 0, b->main);
     if (mask) VF_CUDA(b, cudaMemcpyAsync(b->h.mask, mask, npx, cudaMemcpyHostToDevice, b->main));
     else VF_CUDA(b, cudaMemsetAsync(b->h.mask, 255, npx, b->main));
+    VF_CUDA(b, cudaMemsetAsync(b->h.counters[0], 0, sizeof(int) * C_COUNT, b->main));   // what select_tracked does in a frame
     launch_masked_max_from_mask(b->d, b->h, 0, b->main);
     launch_gftt_select(b->d, b->h, 0, b->main);   // C_N_KEPT == 0 -> tops up to max_corners
     VF_CUDA(b, cudaGetLastError());

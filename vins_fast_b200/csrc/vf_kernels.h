@@ -41,17 +41,20 @@ struct DevBatch {
     int* lk_iters;                   // [S][cap] inner LK iterations of the temporal passes (indexed like previous_kps_)
     int* lk_iters_stereo;            // [S][cap] inner LK iterations of the stereo passes (indexed like current_kps_)
 
-    float* eig;                      // [S][H][W] cornerMinEigenVal of the current left image
-    uint8_t* mask;                   // [S][H][W] SetFeatureExtractorMask
-    uint8_t* lmflag;                 // [S][H][W] 1 = 3x3 local maximum of the response (candidate of goodFeaturesToTrack)
-    unsigned long long* surv;        // [S][cand_cap] candidates outside the mask (unordered), written by mask_and_max
-    unsigned long long* cand;        // [S][cand_cap] local maxima, key = float_key(eig) << 32 | raster index (unordered);
+    // Corner stage (clear -> response -> scan -> scatter): depends on the uploaded image only, so it is double-buffered by
+    // frame parity and runs AHEAD of the frame's chain, while the previous frame is still on it.
+    float* eig[2];                   // [parity][S][H][W] cornerMinEigenVal of the current left image
+    uint8_t* lmflag[2];              // [parity][S][H][W] 1 = 3x3 local maximum of the response (candidate of goodFeaturesToTrack)
+    unsigned long long* cand[2];     // [parity][S][cand_cap] local maxima, key = float_key(eig) << 32 | raster index (unordered);
                                      //               reused as sort scratch by gftt_select once scattered
-    unsigned long long* cand_sorted; // [S][cand_cap] same keys grouped by bucket, strongest bucket first
-    unsigned int* hist;              // [S][n_buckets]
-    unsigned int* bucket_start;      // [S][n_buckets + 1] start of bucket d in cand_sorted, d = n_buckets-1-bucket (descending)
-    unsigned int* bucket_fill;       // [S][n_buckets] scatter cursors (indexed by d)
-    int* bucket_nz;                  // [S][n_buckets] the non-empty d, ascending (counter C_N_NZ_BUCKETS)
+    unsigned long long* cand_sorted[2]; // [parity][S][cand_cap] same keys grouped by bucket, strongest bucket first
+    unsigned int* hist[2];           // [parity][S][n_buckets]
+    unsigned int* bucket_start[2];   // [parity][S][n_buckets + 1] start of bucket d in cand_sorted, d = n_buckets-1-bucket (descending)
+    unsigned int* bucket_fill[2];    // [parity][S][n_buckets] scatter cursors (indexed by d)
+    int* bucket_nz[2];               // [parity][S][n_buckets] the non-empty d, ascending (counter C_N_NZ_BUCKETS)
+    int* ccnt[2];                    // [parity][S][C_COUNT] the corner stage's own counters (C_N_LOCALMAX, C_N_NZ_BUCKETS)
+    uint8_t* mask;                   // [S][H][W] SetFeatureExtractorMask
+    unsigned long long* surv;        // [S][cand_cap] candidates outside the mask (unordered), written by mask_and_max
     uint32_t* conflict;              // [S][cap][(cap+31)/32] min_dist conflict bit-matrix of select_tracked when cap > 512
 
     vf_feature* out[2];              // [parity][S][cap] packed result records, in MAPPED PINNED HOST memory (zero-copy download)

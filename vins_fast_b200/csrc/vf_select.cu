@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
     const int words = L.words;
     int* counters = b.counters[parity] + s * C_COUNT;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
+    if (tid < C_COUNT) counters[tid] = 0;   // first kernel of the frame that touches them: the atomics of the later stages start from 0
     const size_t so = (size_t)s * cap;
 
     // ---- 1. ReduceVector by the temporal status (order preserving) and ++track_count ----
