@@ -66,7 +66,7 @@ struct vf_batch {
     vf_feature* pin_out[2] = {nullptr, nullptr};   // mapped pinned: records of the frames of each parity
     int* pin_n[2] = {nullptr, nullptr};            // mapped pinned: [S] feature counts
     int* dev_n[2] = {nullptr, nullptr};            // their device addresses
-    double* pin_dt = nullptr;                      // mapped pinned ring [6][S] (slot = frame % 6): time since the previous frame
+    double* pin_dt = nullptr;                      // pinned ring [6][S] (slot = frame % 6): time since the previous frame; dev_dt = its device copy
     double* dev_dt = nullptr;
     std::vector<double> prev_times;
     long frame = 0;
@@ -374,6 +374,8 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     // overlapped one issues it after the chain -- host order is how soon the chain reaches the GPU.
     auto issue_right = [&]() -> vf_status {
         VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_img, 0));
+        // frame interval(s) -> device, ahead of the right image (both consumers wait for the right pyramid's event)
+        VF_CUDA(b, cudaMemcpyAsync(b->dev_dt + (size_t)phase * S, pdt, sizeof(double) * (size_t)S, cudaMemcpyHostToDevice, b->side_d));
         { StageTimer t(b, ST_H2D_RIGHT, b->side_d); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_d)); }
         return VF_OK;
     };
@@ -428,11 +430,13 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         { vf_status st = issue_right_pyramid(n_launch); if (st != VF_OK) return st; }
         // left camera's undistortion + velocity beside the stereo pass (needs current_kps_ / ids_ only)
         VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
-        { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[parity], b->side_e); }
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_right, 0));   // the frame interval travels with the right image
+        static const int xp = getenv("VF_XP") ? atoi(getenv("VF_XP")) : 0;
+        if (!(xp & 1)) { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[parity], b->side_e); }
         VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
-        { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); }
+        if (!(xp & 2)) { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); }
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
         VF_CUDA(b, cudaGetLastError());
         VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->side_c));
@@ -623,7 +627,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
         TRYC(cudaHostGetDevicePointer((void**)&b->dev_n[p], b->pin_n[p], 0));
     }
     TRYC(cudaHostAlloc(&b->pin_dt, sizeof(double) * (size_t)S * 6, cudaHostAllocMapped));
-    TRYC(cudaHostGetDevicePointer((void**)&b->dev_dt, b->pin_dt, 0));
+    TRY(dalloc(b, &b->dev_dt, (size_t)S * 6));   // device copy: a read of host memory at the end of every LK CTA costs a PCIe round trip
     b->prev_times.assign(S, 0.0);
     TRYC(cudaMalloc(&b->d, sizeof(DevBatch)));
     TRYC(cudaMemcpy(b->d, &h, sizeof(DevBatch), cudaMemcpyHostToDevice));
