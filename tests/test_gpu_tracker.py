@@ -221,6 +221,39 @@ def test_pipelined_enqueue_fetch_lagged(lib, oracle, euroc_frames):
     batch.close()
 
 
+def test_mixed_synchronous_and_overlapped_frames(lib, oracle, euroc_frames):
+    """The synchronous call and the overlapped enqueue use different stream plans for the same kernels; a sequence may
+    switch between them at any frame and must still reproduce the oracle frame after frame (also without CUDA graphs)."""
+    import vins_fast_b200 as v
+    frames = euroc_frames[:14]
+    plan = "ssooosoosssoos"          # s = vf_batch_track, o = vf_batch_enqueue (+ lagged fetch)
+    for use_graph in (1, 0):
+        cfg = v.make_config(752, 480, 150, 30, 1, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__)
+        cfg.use_cuda_graph = use_graph
+        batch = v.Batch(cfg, 1)
+        ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
+        want, keep, pending = [], [], None
+        for k, (t, l, r) in enumerate(frames):
+            want.append(ref.track_image(t, l, r))
+            pl, pr = (C.c_void_p * 1)(l.ctypes.data), (C.c_void_p * 1)(r.ctypes.data)
+            keep.append((pl, pr))
+            if plan[k] == "s":
+                batch.track_ptrs(t, pl, 752, pr, 752)
+                rec = batch._results()[0]
+                if pending is not None:      # the overlapped frame before this one is still readable afterwards (lag 1)
+                    assert_frames_equal(oracle.records_to_frame(batch.fetch(1)[0]), want[pending], f"graph {use_graph} lagged {pending}")
+                    pending = None
+                assert_frames_equal(oracle.records_to_frame(rec), want[k], f"graph {use_graph} sync frame {k}")
+            else:
+                batch.enqueue_ptrs(t, pl, 752, pr, 752)
+                if pending is not None:
+                    assert_frames_equal(oracle.records_to_frame(batch.fetch(1)[0]), want[pending], f"graph {use_graph} lagged {pending}")
+                pending = k
+        if pending is not None:
+            assert_frames_equal(oracle.records_to_frame(batch.fetch(0)[0]), want[pending], f"graph {use_graph} last")
+        batch.close()
+
+
 def test_4k_2000_features_level5(lib, oracle):
     """BASELINE config 5: 3840x2160 stereo, max_cnt 2000, maxLevel 5 (6 pyramid levels, 16-bit candidate buckets, the
     conflict matrix of the min_dist keep in global memory)."""

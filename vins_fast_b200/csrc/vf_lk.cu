@@ -657,6 +657,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_co
     TraceScope trace(b.trace, TR_LK_TEMPORAL + 16 * tphase);
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
+    const float2 p0 = b.kps[parity ^ 1][(size_t)s * cap + i];   // i < cap: always readable; in flight beside the count
 #ifdef VF_LK_TIMING
     const unsigned long long cta_t0 = vf_globaltimer();
 #endif
@@ -665,7 +666,6 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_co
     load_pyr(sm, 0, b.left[prev], b.lvl_stream_stride, s);   // 0 = previous left
     load_pyr(sm, 1, b.left[cur], b.lvl_stream_stride, s);    // 1 = current left
     __syncthreads();
-    const float2 p0 = b.kps[parity ^ 1][(size_t)s * cap + i];
     const int L = min(b.lk_max_level, b.left[cur].n_levels - 1);
 #ifdef VF_LK_TIMING_REPEAT
     {   // cold-vs-warm experiment: the same forward pass twice, the second one is accounted under phases 8..13
@@ -724,24 +724,29 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_cons
     const int s = blockIdx.y, i = blockIdx.x, cap = b.cap, tid = threadIdx.x;
     const int* cnt_prev = b.counters[parity ^ 1] + s * C_COUNT;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
+    // everything the CTA needs from HBM goes out in one batch, beside the count (i < cap: always readable)
+    const size_t o = (size_t)s * cap + i;
+    const float2 p0 = b.kps[parity][o];
+    const int id = b.ids[parity][o];
+    const int n_prev = cnt_prev[C_N_TOTAL];
 #ifdef VF_LK_TIMING
     const unsigned long long cta_t0 = vf_globaltimer();
 #endif
     if (i >= n) return;
-    const size_t o = (size_t)s * cap + i;
     lk_smem_init(sm, stat, b.n_levels);
     load_pyr(sm, 0, b.left[cur], b.lvl_stream_stride, s);   // 0 = current left
     load_pyr(sm, 1, b.right[parity], b.lvl_stream_stride, s);          // 1 = current right
     if (tid == 0) sm.found[1] = -1;
     __syncthreads();
-    const float2 p0 = b.kps[parity][o];
-    const int id = b.ids[parity][o];
     // id lookup in the previous frame's right map (previous_right_un_distortion_ids_kps_map_); independent of the LK
     {
-        const int n_prev = cnt_prev[C_N_TOTAL];
         const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
-        for (int j = tid; j < n_prev; j += kLkThreads)
-            if (prev_ids[j] == id && b.right_ok[parity ^ 1][(size_t)s * cap + j]) sm.found[1] = j;
+        const uint8_t* prev_ok = b.right_ok[parity ^ 1] + (size_t)s * cap;
+        for (int j = tid; j < n_prev; j += kLkThreads) {
+            const int pid = prev_ids[j];
+            const int pok = prev_ok[j];
+            if (pid == id && pok) sm.found[1] = j;
+        }
     }
     const int L = min(b.lk_max_level, b.right[parity].n_levels - 1);
     const LkResult f = lk_track_point(sm, 0, 1, p0, p0, false, L, stat);
