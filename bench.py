@@ -299,21 +299,26 @@ def main():
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
         assert int(out_n[0]) == n_last, "device-resident and host paths disagree on the feature count"
 
-        # ---------------- e2e, pipelined: enqueue frame k from pinned host images, collect frame k-1 meanwhile ----------------
-        batch.reset()
-        for k in range(Wm):
-            batch.enqueue_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
-            if k >= 1:
-                batch.fetch_counts_lagged(1)
-        barrier()
-        t_wall = time.perf_counter()
-        for k in range(Wm, Wm + K):
-            batch.enqueue_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
-            out_n = batch.fetch_counts_lagged(1)          # every frame's records reach the host inside the timed region
-        out_n = batch.fetch_counts_lagged(0)
-        torch.cuda.synchronize()
-        ms_e2e_pipe = max_over_ranks((time.perf_counter() - t_wall) * 1e3)
-        assert int(out_n[0]) == n_last, "pipelined and synchronous host paths disagree on the feature count"
+        # ---------------- e2e, pipelined: enqueue frame k from pinned host images, collect frame k-lag meanwhile ----------------
+        def run_pipelined(lag):
+            batch.reset()
+            for k in range(Wm):
+                batch.enqueue_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
+                if k >= lag:
+                    batch.fetch_counts_lagged(lag)
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(Wm, Wm + K):
+                batch.enqueue_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
+                batch.fetch_counts_lagged(lag)            # every frame's records reach the host inside the timed region
+            for back in range(lag - 1, -1, -1):
+                n = batch.fetch_counts_lagged(back)
+            torch.cuda.synchronize()
+            ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            assert int(n[0]) == n_last, "pipelined and synchronous host paths disagree on the feature count"
+            return ms
+        ms_e2e_pipe = run_pipelined(1)
+        ms_e2e_pipe2 = run_pipelined(2)
 
         # ---------------- per-kernel times (CUDA events on the launching streams) ----------------
         batch.reset()
@@ -452,7 +457,9 @@ def main():
                 "mode": "host-synchronous vf_batch_track per frame (what the reference's TrackImage does)",
                 "pipelined": {"value": world * K / (ms_e2e_pipe * 1e-3), "unit": "frames/s", "us_per_frame": ms_e2e_pipe / K * 1e3,
                               "mode": "vf_batch_enqueue(k) + vf_batch_fetch_lagged(1): frame k-1 is collected while frame k runs; "
-                                      "same H2D / D2H bytes per frame, host wall clock"}},
+                                      "same H2D / D2H bytes per frame, host wall clock"},
+                "pipelined_lag2": {"value": world * K / (ms_e2e_pipe2 * 1e-3), "unit": "frames/s", "us_per_frame": ms_e2e_pipe2 / K * 1e3,
+                                   "mode": "same with vf_batch_fetch_lagged(2): the host never waits for a running frame"}},
         "gpu_launches": launches, "launches_per_frame": batch.launches_per_frame,
         "stages_us": stages_us, "timeline": timeline, "roofline": roofline, "multi_stream": multi,
         "lk": {"iterations_per_frame": (iters_t + iters_s) / max(n_prof, 1),

@@ -125,10 +125,13 @@ vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_
                                   size_t row_stride, size_t image_stride_bytes);
 vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out);
 /* Pipelined front-end (Estimator::FrontendTracker pushes results into feature_buf_ and the back-end consumes them later,
- * estimator.cpp:143-158): vf_batch_enqueue starts frame k from HOST images and returns at once (at most two frames are
- * in flight; the call blocks until frame k-2 has finished); vf_batch_fetch_lagged(b, 1, ...) then returns frame k-1 while
- * frame k runs -- its stereo pass and download overlap the temporal chain of frame k+1.  lag 0 = vf_batch_fetch.
- * The host images of a frame must stay valid until that frame has been fetched (or a later frame has). */
+ * estimator.cpp:143-158): vf_batch_enqueue starts frame k from HOST images and returns at once (the host runs at most
+ * four frames ahead of the GPU); vf_batch_fetch_lagged(b, lag, ...) then returns frame k-lag, lag = 0 (= vf_batch_fetch),
+ * 1 or 2.  With lag 1 the stereo pass and hand-over of frame k-1 overlap the temporal chain of frame k; with lag 2 the
+ * host never waits for a running frame, so the upload and pyramid of frame k+1 are ready when the chain of frame k ends
+ * (highest throughput, one more frame of latency).  Results are bit-identical to the synchronous call.  The records of a
+ * frame stay readable until three more frames have been enqueued.  The host images of a frame must stay valid until that
+ * frame has been fetched (or a later frame has). */
 vf_status vf_batch_enqueue(vf_batch* b, const double* times, const uint8_t* const* img0, size_t stride0,
                            const uint8_t* const* img1, size_t stride1);
 vf_status vf_batch_fetch_lagged(vf_batch* b, int32_t lag, vf_feature* out, int32_t* n_out);

@@ -4,10 +4,11 @@
 //     input_image_cnt_++;  frame_feature = feature_tracker_->TrackImage(t, img0, img1);
 //     if (input_image_cnt_ % 2 == 0) feature_buf_.push(make_pair(t, frame_feature));          // under feature_buf_mutex_
 // with the one difference the GPU makes worthwhile: Push(t, img0, img1) only ENQUEUES frame k (vf_batch_enqueue) and
-// collects frame k-1 (vf_batch_fetch_lagged), so the stereo pass and the result hand-over of a frame overlap the temporal
-// chain of the next one.  The back-end thread drains the queue with Pop() exactly like it drains feature_buf_
-// (estimator.cpp:179-200): it sees the same (t, featureFrame) pairs, one frame later.  Results are bit-identical to the
-// synchronous FeatureTracker::TrackImage.
+// collects frame k-depth (vf_batch_fetch_lagged), so the stereo pass and the result hand-over of a frame overlap the
+// temporal chain of the next one.  The back-end thread drains the queue with Pop() exactly like it drains feature_buf_
+// (estimator.cpp:179-200): it sees the same (t, featureFrame) pairs, `depth` frames later (1 by default; 2 keeps the GPU
+// busy back to back, for replaying recorded sequences).  Results are bit-identical to the synchronous
+// FeatureTracker::TrackImage.
 //
 // The images of a frame are referenced (cv::Mat shallow copies, like the reference's current_img_) until that frame has
 // been collected.
@@ -29,8 +30,8 @@ public:
 
     /// every_nth: which results go to the back-end queue (the reference keeps every 2nd, estimator.cpp:153)
     FrontendPipeline(int max_cnt, int min_dist, int flow_back, const vf_camera& left, const vf_camera& right, int every_nth = 2,
-                     int device = -1)
-        : every_nth_(every_nth < 1 ? 1 : every_nth) {
+                     int device = -1, int depth = 1)
+        : every_nth_(every_nth < 1 ? 1 : every_nth), depth_(depth < 1 ? 1 : (depth > 2 ? 2 : depth)) {
         vf_config_default(&cfg_);
         cfg_.max_cnt = max_cnt; cfg_.min_dist = min_dist; cfg_.flow_back = flow_back; cfg_.device = device;
         cfg_.cam[0] = left; cfg_.cam[1] = right;
@@ -45,19 +46,19 @@ public:
         if (img0.type() != CV_8UC1 || img1.type() != CV_8UC1 || img0.rows != img1.rows || img0.cols != img1.cols)
             VF_FATAL("FrontendPipeline::Push: both images must be CV_8UC1 of one size");
         Ensure(img0.cols, img0.rows);
-        const int slot = (int)(input_image_cnt_ & 1);
+        const int slot = (int)(input_image_cnt_ % 3);
         held_[slot][0] = img0; held_[slot][1] = img1; times_[slot] = t;      // keep the pixels alive while the frame is in flight
         const uint8_t* p0 = img0.data;
         const uint8_t* p1 = img1.data;
         if (vf_batch_enqueue(batch_, &t, &p0, img0.step, &p1, img1.step) != VF_OK)
             VF_FATAL(std::string("vf_batch_enqueue: ") + vf_batch_last_error(batch_));
         input_image_cnt_++;
-        if (input_image_cnt_ >= 2) Collect(1);
+        if (input_image_cnt_ > depth_) Collect(depth_);
     }
 
-    /// collects the frame that is still in flight (call when the image source has ended)
+    /// collects the frames that are still in flight (call when the image source has ended)
     void Flush() {
-        if (input_image_cnt_ > collected_) Collect(0);
+        while (input_image_cnt_ > collected_) Collect((int)(input_image_cnt_ - collected_ - 1));
     }
 
     /// back-end side: feature_buf_.front() / pop() (estimator.cpp:179-200); false when the queue is empty
@@ -90,7 +91,7 @@ private:
         if (vf_batch_fetch_lagged(batch_, lag, records_.data(), &n) != VF_OK)
             VF_FATAL(std::string("vf_batch_fetch_lagged: ") + vf_batch_last_error(batch_));
         const long index = input_image_cnt_ - 1 - lag;          // 0-based index of the collected frame
-        const int slot = (int)(index & 1);
+        const int slot = (int)(index % 3);
         collected_ = index + 1;
         if (collected_ % every_nth_ == 0) {                       // input_image_cnt_ % 2 == 0 in the reference (1-based count)
             FeatureFrame ff = FeatureTracker::ToFeatureFrame(records_.data(), n);
@@ -102,11 +103,11 @@ private:
 
     vf_config cfg_;
     vf_batch* batch_ = nullptr;
-    int every_nth_;
+    int every_nth_, depth_;
     long input_image_cnt_ = 0, collected_ = 0;
     std::vector<vf_feature> records_;
-    cv::Mat held_[2][2];
-    double times_[2] = {0, 0};
+    cv::Mat held_[3][2];
+    double times_[3] = {0, 0, 0};
     std::mutex feature_buf_mutex_;
     std::queue<std::pair<double, FeatureFrame>> feature_buf_;
 };

@@ -124,15 +124,16 @@ static int run_frames(int argc, char** argv) {
 
 // Estimator::FrontendTracker + feature_buf_ (estimator.cpp:143-158) on the pipelined API: the queue must hold exactly what the
 // synchronous TrackImage returns for every 2nd frame, value for value.
-//   test_feature_tracker pipe <cam0.yaml> <cam1.yaml> <frames.bin> <W> <H> <n_frames>
+//   test_feature_tracker pipe <cam0.yaml> <cam1.yaml> <frames.bin> <W> <H> <n_frames> [depth]
 static int run_pipe(int argc, char** argv) {
-    CHECK(argc == 8);
+    CHECK(argc == 8 || argc == 9);
     const int W = std::atoi(argv[5]), H = std::atoi(argv[6]), n_frames = std::atoi(argv[7]);
     vf_camera c0, c1;
     CHECK(vf_camera_load_yaml(argv[2], &c0) == VF_OK && vf_camera_load_yaml(argv[3], &c1) == VF_OK);
     estimator::FeatureTracker ft(150, 30, 1);
     ft.SetCameras(c0, c1);
-    estimator::FrontendPipeline pipe(150, 30, 1, c0, c1);
+    const int depth = argc > 8 ? std::atoi(argv[8]) : 1;
+    estimator::FrontendPipeline pipe(150, 30, 1, c0, c1, 2, -1, depth);
     std::FILE* in = std::fopen(argv[4], "rb");
     CHECK(in);
     std::vector<std::vector<unsigned char>> left(n_frames, std::vector<unsigned char>((size_t)W * H)), right = left;

@@ -218,6 +218,16 @@ def test_pipelined_enqueue_fetch_lagged(lib, oracle, euroc_frames):
         if k >= 1:
             assert_frames_equal(oracle.records_to_frame(batch.fetch(1)[0]), want[k - 1], f"lagged frame {k - 1}")
     assert_frames_equal(oracle.records_to_frame(batch.fetch(0)[0]), want[-1], "last frame")
+    # lag 2: two frames stay in flight behind the one being collected
+    batch.reset()
+    with pytest.raises(v.VfError):
+        batch.fetch(3)
+    for k, (t, l, r) in enumerate(frames):
+        batch.enqueue_ptrs(t, *keep[k][:1], 752, *keep[k][1:], 752)
+        if k >= 2:
+            assert_frames_equal(oracle.records_to_frame(batch.fetch(2)[0]), want[k - 2], f"lag-2 frame {k - 2}")
+    assert_frames_equal(oracle.records_to_frame(batch.fetch(1)[0]), want[-2], "lag-2 run, frame before last")
+    assert_frames_equal(oracle.records_to_frame(batch.fetch(0)[0]), want[-1], "lag-2 run, last frame")
     batch.close()
 
 
@@ -276,6 +286,7 @@ def test_cpp_frontend_pipeline_feeds_feature_buf(lib, oracle, euroc_frames, tmp_
     with open(tmp_path / "frames.bin", "wb") as f:
         for t, l, r in euroc_frames[:n]:
             f.write(struct.pack("<d", t)); f.write(l.tobytes()); f.write(r.tobytes())
-    res = subprocess.run([exe, "pipe", str(tmp_path / "cam0_mei.yaml"), str(tmp_path / "cam1_mei.yaml"),
-                          str(tmp_path / "frames.bin"), "752", "480", str(n)], capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0 and "pipe ok" in res.stdout, res.stdout + res.stderr
+    for depth in ("1", "2"):     # frames collected one / two behind the newest
+        res = subprocess.run([exe, "pipe", str(tmp_path / "cam0_mei.yaml"), str(tmp_path / "cam1_mei.yaml"),
+                              str(tmp_path / "frames.bin"), "752", "480", str(n), depth], capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0 and "pipe ok" in res.stdout, res.stdout + res.stderr

@@ -63,9 +63,9 @@ struct vf_batch {
     DevBatch h;               // host copy of the device descriptor
     DevBatch* d = nullptr;    // device copy
     std::vector<void*> allocs;
-    vf_feature* pin_out[2] = {nullptr, nullptr};   // mapped pinned: records of the frames of each parity
-    int* pin_n[2] = {nullptr, nullptr};            // mapped pinned: [S] feature counts
-    int* dev_n[2] = {nullptr, nullptr};            // their device addresses
+    vf_feature* pin_out[3] = {nullptr, nullptr, nullptr};   // mapped pinned: records, ring of three (slot = frame % 3)
+    int* pin_n[3] = {nullptr, nullptr, nullptr};            // mapped pinned: [S] feature counts, same ring
+    int* dev_n[3] = {nullptr, nullptr, nullptr};            // their device addresses
     double* pin_dt = nullptr;                      // pinned ring [6][S] (slot = frame % 6): time since the previous frame; dev_dt = its device copy
     double* dev_dt = nullptr;
     std::vector<double> prev_times;
@@ -211,12 +211,11 @@ void destroy_batch(vf_batch* b) {
     for (int w = 0; w < 4; ++w) for (int p = 0; p < 6; ++p) if (b->graph[w][p]) cudaGraphExecDestroy(b->graph[w][p]);
     for (void* p : b->allocs) cudaFree(p);
     if (b->d) cudaFree(b->d);
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < 3; ++p) {
         if (b->pin_out[p]) cudaFreeHost(b->pin_out[p]);
         if (b->pin_n[p]) cudaFreeHost(b->pin_n[p]);
-        if (b->ev_done[p]) cudaEventDestroy(b->ev_done[p]);
-        if (b->ev_done[p + 2]) cudaEventDestroy(b->ev_done[p + 2]);
     }
+    for (int p = 0; p < 4; ++p) if (b->ev_done[p]) cudaEventDestroy(b->ev_done[p]);
     if (b->pin_dt) cudaFreeHost(b->pin_dt);
     if (b->ev_right) cudaEventDestroy(b->ev_right);
     if (b->ev_img) cudaEventDestroy(b->ev_img);
@@ -286,7 +285,7 @@ vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev,
         if (which == SEQ_REST_SYNC) {
             VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
             VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
-            { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity, dev_dt, b->dev_n[parity_], b->side_e); }
+            { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity, dev_dt, b->dev_n[phase % 3], b->side_e); }
             VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
             { StageTimer t(b, ST_LK_STEREO, b->main); launch_lk_stereo(b->d, h, parity, cur, dev_dt, b->main); }
             VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_un, 0));
@@ -432,7 +431,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_right, 0));   // the frame interval travels with the right image
         static const int xp = getenv("VF_XP") ? atoi(getenv("VF_XP")) : 0;
-        if (!(xp & 1)) { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[parity], b->side_e); }
+        if (!(xp & 1)) { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[phase % 3], b->side_e); }
         VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
@@ -470,10 +469,10 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
 }
 
 vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out, int lag = 0) {
-    if (lag < 0 || lag > 1) return fail(b, VF_ERR_INVALID_ARG, "lag must be 0 (last enqueued frame) or 1 (the one before)");
+    if (lag < 0 || lag > 2) return fail(b, VF_ERR_INVALID_ARG, "lag must be 0 (last enqueued frame), 1 or 2 (the ones before)");
     if (b->last_parity < 0 || b->frame <= lag) return fail(b, VF_ERR_STATE, "that frame has not been enqueued");
     DeviceGuard g(b->device);
-    const int p = b->last_parity ^ lag, S = b->S, cap = b->h.cap;
+    const int p = (int)((b->frame - 1 - lag) % 3), S = b->S, cap = b->h.cap;   // the records live in a ring of three frames
     VF_CUDA(b, cudaEventSynchronize(b->ev_done[(int)((b->frame - 1 - lag) & 3)]));
     if (b->profiling) {
         VF_CUDA(b, sync_all(b));
@@ -618,7 +617,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     if (cap > 512) TRY(dalloc(b, &h.conflict, (size_t)S * cap * ((cap + 31) / 32)));
     // result records, feature counts and frame intervals live in mapped pinned host memory: the kernels write / read them
     // in place, no copy commands at either end of a frame
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < 3; ++p) {
         TRYC(cudaHostAlloc(&b->pin_out[p], sizeof(vf_feature) * SC, cudaHostAllocMapped));
         memset(b->pin_out[p], 0, sizeof(vf_feature) * SC);
         TRYC(cudaHostGetDevicePointer((void**)&h.out[p], b->pin_out[p], 0));

@@ -57,7 +57,8 @@ struct DevBatch {
     unsigned long long* surv;        // [S][cand_cap] candidates outside the mask (unordered), written by mask_and_max
     uint32_t* conflict;              // [S][cap][(cap+31)/32] min_dist conflict bit-matrix of select_tracked when cap > 512
 
-    vf_feature* out[2];              // [parity][S][cap] packed result records, in MAPPED PINNED HOST memory (zero-copy download)
+    vf_feature* out[3];              // [frame % 3][S][cap] packed result records, in MAPPED PINNED HOST memory (zero-copy download);
+                                     // a ring of three so that the host may collect frame k-2 while k-1 and k are in flight
     unsigned long long* trace;       // optional [TR_COUNT][2] kernel start / end stamps (measurement aid), else null
 };
 

@@ -763,7 +763,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_cons
     }
     __syncthreads();
     if (tid == 0) {
-        vf_feature* rec = &b.out[parity][o];     // mapped pinned host memory: the record goes straight to the caller's side
+        vf_feature* rec = &b.out[tphase % 3][o];     // mapped pinned host memory (ring of three frames): the record goes straight to the caller's side
         rec->has_right = ok;
         float2 unr = make_float2(0.f, 0.f), vr = make_float2(0.f, 0.f);
         if (ok) {
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(128) undistort_left_kernel(const __grid_consta
         for (int j = 0; j < n_prev; ++j) found = prev_ids_sm[j] == id ? j : found;
     float2 v = make_float2(0.f, 0.f);
     if (found >= 0) v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + found], dt_host[s]);   // dt: zero-copy read of the host's value
-    vf_feature* rec = &b.out[parity][o];
+    vf_feature* rec = &b.out[tphase % 3][o];
     rec->id = id; rec->track_cnt = b.cnt[parity][o];
     rec->x = un.x; rec->y = un.y; rec->u = p0.x; rec->v = p0.y; rec->vx = v.x; rec->vy = v.y;
     b.un_left[parity][o] = un;

@@ -224,7 +224,7 @@ class Batch:
               self.last_error)
 
     def fetch(self, lag: int = 0):
-        """Results of the last enqueued frame (lag 0) or of the one before it (lag 1, while the last one still runs)."""
+        """Results of the last enqueued frame (lag 0) or of the ones before it (lag 1 or 2, while the later ones still run)."""
         check(self._lib.vf_batch_fetch_lagged(self._h, lag, self._out.ctypes.data, self._n.ctypes.data), self.last_error)
         return self._results()
 
