@@ -70,6 +70,7 @@ struct vf_batch {
     double* dev_dt = nullptr;
     std::vector<double> prev_times;
     long frame = 0;
+    long known_done = -1;                          // newest frame index a fetch has seen complete (frames complete in order)
     int last_parity = -1;
     cudaGraphExec_t graph[4][6] = {};
     int pyr_launches = 1;   // one per frame % 6 (parity x pyramid ring slot)
@@ -245,6 +246,7 @@ vf_status reset_state(vf_batch* b) {
     }
     VF_CUDA(b, cudaStreamSynchronize(b->main));
     b->frame = 0;
+    b->known_done = -1;
     b->last_parity = -1;
     std::fill(b->prev_times.begin(), b->prev_times.end(), 0.0);
     return VF_OK;
@@ -327,7 +329,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     // that issuing frame k+1 never has to wait for the GPU to drain (the completion events form a ring of four).
     const int slot = (int)(b->frame & 3);
     const auto t_wait0 = std::chrono::steady_clock::now();
-    VF_CUDA(b, cudaEventSynchronize(b->ev_done[slot]));                      // frame k-4
+    if (b->frame - 4 > b->known_done) VF_CUDA(b, cudaEventSynchronize(b->ev_done[slot]));   // frame k-4 (frames complete in order)
     const auto t_wait1 = std::chrono::steady_clock::now();
     b->host_wait_us += std::chrono::duration<double, std::micro>(t_wait1 - t_wait0).count();
     if (stride0 < (size_t)W || stride1 < (size_t)W) return fail(b, VF_ERR_INVALID_ARG, "row stride is smaller than the image width");
@@ -430,12 +432,11 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         // left camera's undistortion + velocity beside the stereo pass (needs current_kps_ / ids_ only)
         VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_right, 0));   // the frame interval travels with the right image
-        static const int xp = getenv("VF_XP") ? atoi(getenv("VF_XP")) : 0;
-        if (!(xp & 1)) { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[phase % 3], b->side_e); }
+        { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[phase % 3], b->side_e); }
         VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
-        if (!(xp & 2)) { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); }
+        { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); }
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
         VF_CUDA(b, cudaGetLastError());
         VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->side_c));
@@ -474,6 +475,7 @@ vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out, int lag = 0)
     DeviceGuard g(b->device);
     const int p = (int)((b->frame - 1 - lag) % 3), S = b->S, cap = b->h.cap;   // the records live in a ring of three frames
     VF_CUDA(b, cudaEventSynchronize(b->ev_done[(int)((b->frame - 1 - lag) & 3)]));
+    if (b->frame - 1 - lag > b->known_done) b->known_done = b->frame - 1 - lag;
     if (b->profiling) {
         VF_CUDA(b, sync_all(b));
         for (int k = 0; k < ST_COUNT; ++k) {
