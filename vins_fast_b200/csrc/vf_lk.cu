@@ -137,6 +137,16 @@ __device__ __forceinline__ void load_row_words(const LevelRef& L, int x0, int y,
 #pragma unroll
     for (int k = 0; k < NW; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], 8 * m);
 }
+// The same fetch in two halves for a prefetch: issue_row_words only issues the loads (the raw words stay in flight while
+// the caller does other work -- realigning them at once would stall the warp on the memory round trip), align_row_word
+// realigns one word when the data is finally consumed.  Reads one word more than load_row_words (inside the border).
+template <int NW>
+__device__ __forceinline__ void issue_row_words(const LevelRef& L, int x0, int y, uint32_t (&raw)[NW + 1]) {
+    const uint8_t* row = L.p + (ptrdiff_t)y * L.pitch;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row + (x0 - (x0 & 3)));
+#pragma unroll
+    for (int k = 0; k <= NW; ++k) raw[k] = __ldg(wp + k);
+}
 
 // Origin of a speculative (prefetched) J tile, clamped so that the 32x32 tile stays inside the filled border.
 __device__ __forceinline__ int clamp_tile_origin(int o, int n) { return min(max(o, -(kPyrPadFill - 2)), n + kPyrPadFill - 2 - kTileJ); }
@@ -418,13 +428,13 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         }
         // prefetch the next level's J tile around the current estimate: the last warp issues the loads now and parks the
         // words in registers until the iterations of this level are done
-        uint32_t pf[kTileJ / 4];
+        uint32_t pf[kTileJ / 4 + 1];
         int px0 = 0, py0 = 0;
         if (level > 0) {
             const LevelRef LN = sm.pyr[ja][level - 1];
             px0 = clamp_tile_origin(__float2int_rd(__fadd_rn(__fmul_rn(nx, 2.f), half)) - kJMargin, LN.w);   // 2*(nx + half) - half
             py0 = clamp_tile_origin(__float2int_rd(__fadd_rn(__fmul_rn(ny, 2.f), half)) - kJMargin, LN.h);
-            if (wid == kLkWarps - 1) load_row_words<kTileJ / 4>(sm.pyr[ja][level - 1], px0, py0 + lane, pf);
+            if (wid == kLkWarps - 1) issue_row_words<kTileJ / 4>(sm.pyr[ja][level - 1], px0, py0 + lane, pf);
         }
         LK_T(4);
         const uint8_t* tj = sm.tileJ[jbuf];
@@ -575,9 +585,13 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         if (level > 0) {   // publish the prefetched tile of the next level
             jbuf ^= 1;
             if (wid == kLkWarps - 1) {
+                const int sh = 8 * (px0 & 3);
+                uint32_t v[kTileJ / 4];
+#pragma unroll
+                for (int k = 0; k < kTileJ / 4; ++k) v[k] = __funnelshift_r(pf[k], pf[k + 1], sh);
                 uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
-                dst[0] = make_uint4(pf[0], pf[1], pf[2], pf[3]);
-                dst[1] = make_uint4(pf[4], pf[5], pf[6], pf[7]);
+                dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
             }
             jx0 = px0; jy0 = py0;
             tile_ready = true;
