@@ -113,6 +113,9 @@ __device__ __forceinline__ unsigned int vf_smid() { unsigned int r; asm volatile
 #define LK_TF(k) do { } while (0)
 #endif
 
+// 1.f / (1 << level), exactly (OpenCV: (float)(1. / (1 << level))), without an IEEE division on the level chain
+__device__ __forceinline__ float pow2_neg(int level) { return __int_as_float((127 - level) << 23); }
+
 __device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
     const float one_a = __fsub_rn(1.f, a), one_b = __fsub_rn(1.f, b);
     w00 = __float2int_rn(__fmul_rn(__fmul_rn(one_a, one_b), 16384.f));
@@ -197,7 +200,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     //      rows of the top level's 32x32 tile of J (it only depends on the start point) ----
     int jx0, jy0, jbuf = 0;
     {
-        const float scale = 1.f / (float)(1 << max_level);
+        const float scale = pow2_neg(max_level);
         const float sx = use_init ? init_pt.x : prev_pt.x, sy = use_init ? init_pt.y : prev_pt.y;
         const LevelRef LT = sm.pyr[ja][max_level];
         jx0 = clamp_tile_origin(__float2int_rd(__fsub_rn(__fmul_rn(sx, scale), half)) - kJMargin, LT.w);
@@ -209,7 +212,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         if (it < kTileI * nlv) {
             const int level = it / kTileI, row = it - level * kTileI;
             const LevelRef LI = sm.pyr[ia][level];
-            const float scale = 1.f / (float)(1 << level);
+            const float scale = pow2_neg(level);
             const float ppx = __fsub_rn(__fmul_rn(prev_pt.x, scale), half), ppy = __fsub_rn(__fmul_rn(prev_pt.y, scale), half);
             const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
             const int valid = !(ipx < -kWin || ipx >= LI.w || ipy < -kWin || ipy >= LI.h);
@@ -386,7 +389,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
         const LevelRef LJ = sm.pyr[ja][level];
         const LevelBlock& B = sm.lv[level];
         const int jcols = LJ.w, jrows = LJ.h;
-        const float scale = 1.f / (float)(1 << level);
+        const float scale = pow2_neg(level);
         float nx, ny;
         if (level == max_level) {
             if (use_init) { nx = __fmul_rn(outx, scale); ny = __fmul_rn(outy, scale); }
@@ -410,6 +413,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             I0[q] = B.Iw[max(e0[q], 0)]; I1[q] = B.Iw[max(e1[q], 0)];
             g0[q] = e0[q] >= 0 ? B.dI[e0[q]] : make_short2(0, 0); g1[q] = e1[q] >= 0 ? B.dI[e1[q]] : make_short2(0, 0);
         }
+        LK_T(11);
         {
             const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
             if (!tile_ready || inx < jx0 || iny < jy0 || inx + kTileD > jx0 + kTileJ || iny + kTileD > jy0 + kTileJ) {
@@ -597,6 +601,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             tile_ready = true;
             __syncthreads();
         }
+        LK_T(10);
         if (status && level == 0) {   // the caller passes an err vector: final window test (lkpyramid.cpp)
             const int ix = __float2int_rd(__fsub_rn(outx, half)), iy = __float2int_rd(__fsub_rn(outy, half));
             if (ix < -kWin || ix >= jcols || iy < -kWin || iy >= jrows) status = 0;
