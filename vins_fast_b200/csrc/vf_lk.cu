@@ -602,6 +602,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             __syncthreads();
         }
         LK_T(10);
+        LK_T(10);
         if (status && level == 0) {   // the caller passes an err vector: final window test (lkpyramid.cpp)
             const int ix = __float2int_rd(__fsub_rn(outx, half)), iy = __float2int_rd(__fsub_rn(outy, half));
             if (ix < -kWin || ix >= jcols || iy < -kWin || iy >= jrows) status = 0;
