@@ -52,6 +52,9 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+SAMPLE_S = float(os.environ.get("VF_BENCH_SAMPLE_MS", "2")) * 1e-3   # NVML polling period of the clock sampler
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING a timed region: NVML polled every ~2 ms from a thread (the regions are
     tens of milliseconds long, too short for `nvidia-smi -lms`); falls back to nvidia-smi when NVML is unavailable."""
@@ -75,7 +78,7 @@ class ClockSampler:
             for k, bit in names.items():
                 if r & bit:
                     self.reasons.add(k)
-            time.sleep(0.002)
+            time.sleep(SAMPLE_S)
 
     def _smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -272,11 +275,14 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
+            h0 = batch.host_times_us()
             e0.record(stream)
             n_last = int(run_device(Wm, K)[0])
             e1.record(stream)
+            h1 = batch.host_times_us()
             barrier()
         ms_value = max_over_ranks(e0.elapsed_time(e1))
+        host_issue_us = max_over_ranks((h1[1] - h0[1]) / K)      # host time spent issuing one frame (slowest rank)
         launches = batch.launches_per_frame * K
 
         # ---------------- e2e: pinned host images in, records out, host-synchronous per frame ----------------
@@ -460,7 +466,7 @@ def main():
                                       "same H2D / D2H bytes per frame, host wall clock"},
                 "pipelined_lag2": {"value": world * K / (ms_e2e_pipe2 * 1e-3), "unit": "frames/s", "us_per_frame": ms_e2e_pipe2 / K * 1e3,
                                    "mode": "same with vf_batch_fetch_lagged(2): the host never waits for a running frame"}},
-        "gpu_launches": launches, "launches_per_frame": batch.launches_per_frame,
+        "gpu_launches": launches, "launches_per_frame": batch.launches_per_frame, "host_issue_us_per_frame": host_issue_us,
         "stages_us": stages_us, "timeline": timeline, "roofline": roofline, "multi_stream": multi,
         "lk": {"iterations_per_frame": (iters_t + iters_s) / max(n_prof, 1),
                "exact_integer_path_fraction": fast_it / max(iters_t + iters_s, 1)},

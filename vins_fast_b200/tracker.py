@@ -252,6 +252,12 @@ class Batch:
     def cuda_stream(self) -> int:
         return int(self._lib.vf_batch_cuda_stream(self._h) or 0)
 
+    def host_times_us(self):
+        """Cumulative host microseconds inside the enqueue calls: (waiting for frame k-4, issuing the frames)."""
+        t = (C.c_double * 2)()
+        self._lib.vf_batch_host_times(self._h, t)
+        return float(t[0]), float(t[1])
+
     @property
     def launches_per_frame(self) -> int:
         return int(self._lib.vf_batch_launches_per_frame(self._h))
