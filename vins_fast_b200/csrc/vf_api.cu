@@ -55,7 +55,7 @@ struct vf_batch {
     cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr, side_d = nullptr, side_e = nullptr;
     bool own_main = false, serialized = false;
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
-    cudaEvent_t ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
+    cudaEvent_t ev_fork = nullptr, ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
                 ev_sel = nullptr, ev_un = nullptr, ev_pyrl = nullptr, ev_scat = nullptr,
                 ev_chain[2] = {nullptr, nullptr};
     uint8_t* stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // unpadded upload targets [camera][parity]: [S][H][stage_pitch]
@@ -72,7 +72,7 @@ struct vf_batch {
     long frame = 0;
     long known_done = -1;                          // newest frame index a fetch has seen complete (frames complete in order)
     int last_parity = -1;
-    cudaGraphExec_t graph[4][6] = {};
+    cudaGraphExec_t graph[7][6] = {};
     int pyr_launches = 1;   // one per frame % 6 (parity x pyramid ring slot)
     int launches = 0;
     std::string err;
@@ -209,7 +209,7 @@ void destroy_batch(vf_batch* b) {
     if (!b) return;
     DeviceGuard g(b->device);
     sync_all(b);
-    for (int w = 0; w < 4; ++w) for (int p = 0; p < 6; ++p) if (b->graph[w][p]) cudaGraphExecDestroy(b->graph[w][p]);
+    for (int w = 0; w < 7; ++w) for (int p = 0; p < 6; ++p) if (b->graph[w][p]) cudaGraphExecDestroy(b->graph[w][p]);
     for (void* p : b->allocs) cudaFree(p);
     if (b->d) cudaFree(b->d);
     for (int p = 0; p < 3; ++p) {
@@ -219,6 +219,7 @@ void destroy_batch(vf_batch* b) {
     for (int p = 0; p < 4; ++p) if (b->ev_done[p]) cudaEventDestroy(b->ev_done[p]);
     if (b->pin_dt) cudaFreeHost(b->pin_dt);
     if (b->ev_right) cudaEventDestroy(b->ev_right);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_img) cudaEventDestroy(b->ev_img);
     if (b->ev_sel) cudaEventDestroy(b->ev_sel);
     if (b->ev_un) cudaEventDestroy(b->ev_un);
@@ -261,7 +262,11 @@ vf_status reset_state(vf_batch* b) {
 //   SEQ_HEAD_SYNC  main, synchronous frames: left pyramid + temporal LK back to back (behind the left upload).
 //   SEQ_REST_SYNC  main, synchronous frames: what follows the temporal LK, with the stereo pass appended and the left
 //                  undistortion on a branch beside it.
-enum { SEQ_CORNER = 0, SEQ_CHAIN = 1, SEQ_REST_SYNC = 2, SEQ_HEAD_SYNC = 3, SEQ_COUNT = 4 };
+//   SEQ_PYR_LEFT / SEQ_PYR_RIGHT   side B / side D: pyramid + borders of one image (overlapped frames; right: both plans).
+//   SEQ_TAIL       side C, overlapped frames: stereo pass with the left undistortion on a branch (side E) beside it.
+// (A plain launch of one of these kernels costs the host 4-4.5 us -- the batch descriptor travels by value -- a graph
+//  launch 3.5 us whatever it holds.)
+enum { SEQ_CORNER = 0, SEQ_CHAIN = 1, SEQ_REST_SYNC = 2, SEQ_HEAD_SYNC = 3, SEQ_PYR_LEFT = 4, SEQ_PYR_RIGHT = 5, SEQ_TAIL = 6, SEQ_COUNT = 7 };
 
 vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev, int phase) {
     const DevBatch& h = b->h;
@@ -274,6 +279,20 @@ vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev,
             b->pyr_launches = launch_pyramid(h.left[cur], h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT + 16 * phase);
         }
         { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); }
+    } else if (which == SEQ_PYR_LEFT || which == SEQ_PYR_RIGHT) {
+        const int cam = which == SEQ_PYR_RIGHT;
+        cudaStream_t st = cam ? b->side_d : b->side_b;
+        StageTimer t(b, cam ? ST_PYR_RIGHT : ST_PYR_LEFT, st);
+        const Level0Src src = {b->stage[cam][parity_], b->stage_pitch, (size_t)b->stage_pitch * h.H};
+        b->pyr_launches = launch_pyramid(cam ? h.right[parity_] : h.left[cur], h.lvl_stream_stride, b->S, st, &src, h.trace,
+                                         (cam ? TR_PYR_RIGHT : TR_PYR_LEFT) + 16 * phase);
+    } else if (which == SEQ_TAIL) {
+        VF_CUDA(b, cudaEventRecord(b->ev_fork, b->side_c));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_fork, 0));
+        { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity, dev_dt, b->dev_n[phase % 3], b->side_e); }
+        VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
+        { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity, cur, dev_dt, b->side_c); }
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
     } else if (which == SEQ_CORNER) {
         { StageTimer t(b, ST_CLEAR, b->side_a); launch_clear_frame(b->d, h, parity, b->side_a); }
         { StageTimer t(b, ST_RESPONSE_NMS, b->side_a); launch_response_nms(b->d, h, parity, b->side_a); }
@@ -300,7 +319,8 @@ vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev,
 vf_status build_graph(vf_batch* b, int phase, int which) {
     cudaGraph_t graph = nullptr;
     const int parity = phase & 1, cur = phase % 3, prev = (phase + 2) % 3;
-    cudaStream_t st_cap = which == SEQ_CORNER ? b->side_a : b->main;
+    cudaStream_t st_cap = which == SEQ_CORNER ? b->side_a : which == SEQ_PYR_LEFT ? b->side_b : which == SEQ_PYR_RIGHT ? b->side_d
+                          : which == SEQ_TAIL ? b->side_c : b->main;
     VF_CUDA(b, cudaStreamBeginCapture(st_cap, cudaStreamCaptureModeThreadLocal));
     vf_status st = issue_sequence(b, which, parity, cur, prev, phase);
     cudaError_t e = cudaStreamEndCapture(st_cap, &graph);
@@ -380,24 +400,6 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         { StageTimer t(b, ST_H2D_RIGHT, b->side_d); VF_CUDA(b, upload(1, img1, base1, stride1, b->side_d)); }
         return VF_OK;
     };
-    auto issue_right_pyramid = [&](int& n) -> vf_status {
-        StageTimer t(b, ST_PYR_RIGHT, b->side_d);
-        const Level0Src src = {b->stage[1][parity], b->stage_pitch, simg};
-        n += launch_pyramid(h.right[parity], h.lvl_stream_stride, S, b->side_d, &src, h.trace, TR_PYR_RIGHT + 16 * phase);
-        VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
-        return VF_OK;
-    };
-    if (!overlap) { vf_status st = issue_right(); if (st != VF_OK) return st; }
-    // left pyramid: an overlapped frame builds it on side B right behind its upload (it does not depend on the previous
-    // frame, so it is built while that one is still on the chain); a synchronous frame builds it on main, back to back with
-    // the temporal LK
-    int n_launch = 0;
-    if (overlap) {
-        StageTimer t(b, ST_PYR_LEFT, b->side_b);
-        const Level0Src src = {b->stage[0][parity], b->stage_pitch, simg};
-        n_launch += launch_pyramid(h.left[cur], h.lvl_stream_stride, S, b->side_b, &src, h.trace, TR_PYR_LEFT + 16 * phase);
-        VF_CUDA(b, cudaEventRecord(b->ev_pyrl, b->side_b));
-    }
     const bool use_graph = b->cfg.use_cuda_graph && !b->profiling;
     auto run = [&](int which, cudaStream_t st) -> vf_status {   // one of the captured kernel sequences, as a graph or directly
         if (use_graph) {
@@ -410,6 +412,21 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         }
         return issue_sequence(b, which, parity, cur, prev, phase);
     };
+    auto issue_right_pyramid = [&]() -> vf_status {
+        vf_status st = run(SEQ_PYR_RIGHT, b->side_d);
+        if (st != VF_OK) return st;
+        VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
+        return VF_OK;
+    };
+    if (!overlap) { vf_status st = issue_right(); if (st != VF_OK) return st; }
+    // left pyramid: an overlapped frame builds it on side B right behind its upload (it does not depend on the previous
+    // frame, so it is built while that one is still on the chain); a synchronous frame builds it on main, back to back with
+    // the temporal LK
+    if (overlap) {
+        vf_status st = run(SEQ_PYR_LEFT, b->side_b);
+        if (st != VF_OK) return st;
+        VF_CUDA(b, cudaEventRecord(b->ev_pyrl, b->side_b));
+    }
     // corner stage on side A right behind the left upload (the staging image is all it reads)
     auto issue_corner = [&]() -> vf_status {
         VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_img, 0));
@@ -428,16 +445,12 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
         VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
         { vf_status st = issue_right(); if (st != VF_OK) return st; }
-        { vf_status st = issue_right_pyramid(n_launch); if (st != VF_OK) return st; }
-        // left camera's undistortion + velocity beside the stereo pass (needs current_kps_ / ids_ only)
-        VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
-        VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_right, 0));   // the frame interval travels with the right image
-        { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity | (phase << 4), dev_dt, b->dev_n[phase % 3], b->side_e); }
-        VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
+        { vf_status st = issue_right_pyramid(); if (st != VF_OK) return st; }
+        // stereo pass on side C with the left camera's undistortion + velocity on a branch beside it (side E); both need
+        // current_kps_ / ids_ (ev_sel), the stereo pass the right pyramid, both the frame interval that travels with it
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
-        { StageTimer t(b, ST_LK_STEREO, b->side_c); launch_lk_stereo(b->d, h, parity | (phase << 4), cur, dev_dt, b->side_c); }
-        VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_un, 0));
+        { vf_status st = run(SEQ_TAIL, b->side_c); if (st != VF_OK) return st; }
         VF_CUDA(b, cudaGetLastError());
         VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->side_c));
     } else {
@@ -446,9 +459,8 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         // selection inside the same graph, the left undistortion on a branch beside it.
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
         { vf_status st = run(SEQ_HEAD_SYNC, b->main); if (st != VF_OK) return st; }
-        n_launch += b->pyr_launches;
         { vf_status st = issue_corner(); if (st != VF_OK) return st; }
-        { vf_status st = issue_right_pyramid(n_launch); if (st != VF_OK) return st; }
+        { vf_status st = issue_right_pyramid(); if (st != VF_OK) return st; }
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
         // the stereo pass / left undistortion read what the previous frame's wrote (velocity): if that frame was an
@@ -460,6 +472,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
         VF_CUDA(b, cudaEventRecord(b->ev_done[slot], b->main));
     }
+    int n_launch = 2 * b->pyr_launches;
     n_launch += 4 /* corner stage */ + 4 /* chain */ + 2 /* stereo, left undistortion */;
     // no download commands: the records and the feature counts were written to mapped pinned host memory by the kernels
     b->launches = n_launch;
@@ -567,6 +580,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
         TRYC(cudaStreamCreateWithPriority(&b->side_c, cudaStreamNonBlocking, prio_mid));
     }
     TRYC(cudaEventCreateWithFlags(&b->ev_right, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_img, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_un, cudaEventDisableTiming));
