@@ -264,6 +264,41 @@ def test_mixed_synchronous_and_overlapped_frames(lib, oracle, euroc_frames):
         batch.close()
 
 
+def test_long_run_plans_agree_bit_for_bit(lib, euroc_frames):
+    """240 frames (the 24 fixture frames played forward and backward): the synchronous plan, the overlapped plan with lag 2
+    and a second overlapped run must produce identical record bytes, frame after frame -- the buffers are rings of two /
+    three frames, so a missing dependency between streams shows up as a difference within a few hundred frames."""
+    import vins_fast_b200 as v
+    order = [k if (k // 24) % 2 == 0 else 23 - k % 24 for k in range(240)]
+    order = [o % 24 for o in order]
+    cfg = v.make_config(752, 480, 150, 30, 1, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__)
+    ptrs = [((C.c_void_p * 1)(l.ctypes.data), (C.c_void_p * 1)(r.ctypes.data)) for _, l, r in euroc_frames]
+
+    def run(lag):
+        batch = v.Batch(cfg, 1)
+        out = []
+        for i, k in enumerate(order):
+            t = i / 20.0
+            if lag < 0:
+                batch.track_ptrs(t, ptrs[k][0], 752, ptrs[k][1], 752)
+                out.append(batch._results()[0].tobytes())
+            else:
+                batch.enqueue_ptrs(t, ptrs[k][0], 752, ptrs[k][1], 752)
+                if i >= lag:
+                    out.append(batch.fetch(lag)[0].tobytes())
+        for back in range(lag - 1, -1, -1):
+            out.append(batch.fetch(back)[0].tobytes())
+        batch.close()
+        return out
+
+    want = run(-1)
+    assert len(want) == 240 and len(set(want)) > 200
+    for name, got in (("lag 2", run(2)), ("lag 2 again", run(2)), ("lag 1", run(1))):
+        assert len(got) == 240
+        bad = [i for i in range(240) if got[i] != want[i]]
+        assert not bad, f"{name}: first differing frame {bad[0]} of {len(bad)}"
+
+
 def test_4k_2000_features_level5(lib, oracle):
     """BASELINE config 5: 3840x2160 stereo, max_cnt 2000, maxLevel 5 (6 pyramid levels, 16-bit candidate buckets, the
     conflict matrix of the min_dist keep in global memory)."""
