@@ -370,7 +370,6 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     }
     double* pdt = b->pin_dt + (size_t)phase * S;                              // current_time_ - previous_time_ (feature_tracker.cpp:338)
     for (int s = 0; s < S; ++s) { pdt[s] = times[s] - b->prev_times[s]; b->prev_times[s] = times[s]; }
-    const double* dev_dt = b->dev_dt + (size_t)phase * S;
     for (int k = 0; k < ST_COUNT; ++k) b->st_used[k] = false;
     // All uploads of the frame go through side B, in the order the frame needs them: times, left image, right image.
     // The staging buffers are double-buffered by parity, so with asynchronous enqueues the upload of frame k+1 overlaps

@@ -4,6 +4,8 @@
 // (vins/estimator/feature_tracker.cpp:41,50,117,125):
 //   dst(x,y) = ( sum_{i,j in [-2,2]} k[i]k[j] src(refl101(2x+j), refl101(2y+i)) + 128 ) >> 8,  k = [1 4 6 4 1]
 // Integer, bit-exact.
+#include <type_traits>
+
 #include "vf_common.cuh"
 #include "vf_kernels.h"
 
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
     __shared__ __align__(16) uint8_t buf0[RH0 * P0];
     __shared__ __align__(16) uint8_t bufA[(NL >= 3 ? RH1 : (NL >= 2 ? RH2 : RH3)) * PI];
     __shared__ __align__(16) uint8_t bufB[(NL >= 3 ? RH2 : RH3) * PI];
-    __shared__ uint16_t tmp[RH0 * PW];
+    constexpr int PW2 = (PW + 1) / 2;                                   // horizontal sums, two columns per 32-bit word
+    __shared__ uint32_t tmp[RH0 * PW2];
 
     const int tid = threadIdx.x, img = blockIdx.z;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
@@ -68,29 +71,53 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
 
     const uint8_t* in = buf0;
     int in_pitch = P0, in_ox = ax0;
-#pragma unroll
-    for (int k = 0; k < NL; ++k) {
+    auto transition = [&](auto kc) {
+        constexpr int k = decltype(kc)::value;
         uint8_t* out = (k & 1) ? bufB : bufA;
         const int ow = hix[k + 1] - lox[k + 1] + 1, oh = hiy[k + 1] - loy[k + 1] + 1;
         const int ih = hiy[k] - loy[k] + 1;
+        // Both passes work on PAIRS of output columns (two 16-bit sums per 32-bit word: a sum is at most 16 * 255 after
+        // the first pass and 256 * 255 after the second, so the lanes never carry into each other) and index their work
+        // with compile-time extents (no runtime division); the REFLECT_101 index arithmetic only runs for taps that
+        // actually leave the image.
         // horizontal [1 4 6 4 1] at even columns of every staged input row
-        for (int i = tid; i < ih * ow; i += NT) {
-            const int r = i / ow, c = i - r * ow;
+        constexpr int OW2 = ((k == 0 ? (NL >= 3 ? RW1 : (NL >= 2 ? RW2 : RW3)) : (k == 1 ? (NL >= 3 ? RW2 : RW3) : RW3)) + 1) / 2;
+        const int wk = lw[k], hk = lh[k];
+        for (int i = tid; i < ih * OW2; i += NT) {
+            const int r = i / OW2, c = 2 * (i - r * OW2);
+            if (c >= ow) continue;
             const int gx = 2 * (lox[k + 1] + c);
             const uint8_t* row = in + r * in_pitch - in_ox;
-            const int v = row[refl101(gx - 2, lw[k])] + 4 * row[refl101(gx - 1, lw[k])] + 6 * row[gx] +
-                          4 * row[refl101(gx + 1, lw[k])] + row[refl101(gx + 2, lw[k])];
-            tmp[r * PW + c] = (uint16_t)v;
+            const bool has1 = c + 1 < ow;
+            int b0, b1, b2, b3, b4, b5 = 0, b6 = 0;
+            if (gx >= 2 && gx + 4 < wk) {
+                b0 = row[gx - 2]; b1 = row[gx - 1]; b2 = row[gx]; b3 = row[gx + 1]; b4 = row[gx + 2];
+                if (has1) { b5 = row[gx + 3]; b6 = row[gx + 4]; }
+            } else {
+                b0 = row[refl101(gx - 2, wk)]; b1 = row[refl101(gx - 1, wk)]; b2 = row[gx];
+                b3 = row[refl101(gx + 1, wk)]; b4 = row[refl101(gx + 2, wk)];
+                if (has1) { b5 = row[refl101(gx + 3, wk)]; b6 = row[refl101(gx + 4, wk)]; }
+            }
+            const uint32_t v0 = (uint32_t)(b0 + b4 + 4 * (b1 + b3) + 6 * b2);
+            const uint32_t v1 = (uint32_t)(b2 + b6 + 4 * (b3 + b5) + 6 * b4);
+            tmp[r * PW2 + (c >> 1)] = v0 | (v1 << 16);
         }
         __syncthreads();
         // vertical pass -> region of level k+1 (kept in shared memory for the next transition)
-        for (int i = tid; i < oh * ow; i += NT) {
-            const int r = i / ow, c = i - r * ow;
+        for (int i = tid; i < oh * OW2; i += NT) {
+            const int r = i / OW2, c2 = i - r * OW2;
+            if (2 * c2 >= ow || r >= oh) continue;
             const int gy = 2 * (loy[k + 1] + r);
-            const int r0 = refl101(gy - 2, lh[k]) - loy[k], r1 = refl101(gy - 1, lh[k]) - loy[k], r2 = gy - loy[k];
-            const int r3 = refl101(gy + 1, lh[k]) - loy[k], r4 = refl101(gy + 2, lh[k]) - loy[k];
-            const int v = tmp[r0 * PW + c] + 4 * tmp[r1 * PW + c] + 6 * tmp[r2 * PW + c] + 4 * tmp[r3 * PW + c] + tmp[r4 * PW + c];
-            out[r * PI + c] = (uint8_t)((v + 128) >> 8);
+            int r0, r1, r3, r4;
+            const int r2 = gy - loy[k];
+            if (gy >= 2 && gy + 2 < hk) { r0 = r2 - 2; r1 = r2 - 1; r3 = r2 + 1; r4 = r2 + 2; }
+            else {
+                r0 = refl101(gy - 2, hk) - loy[k]; r1 = refl101(gy - 1, hk) - loy[k];
+                r3 = refl101(gy + 1, hk) - loy[k]; r4 = refl101(gy + 2, hk) - loy[k];
+            }
+            const uint32_t v = tmp[r0 * PW2 + c2] + tmp[r4 * PW2 + c2] + 4u * (tmp[r1 * PW2 + c2] + tmp[r3 * PW2 + c2]) + 6u * tmp[r2 * PW2 + c2];
+            const uint32_t q = (v + 0x00800080u) >> 8;                                   // (sum + 128) >> 8 in both lanes
+            *reinterpret_cast<uint16_t*>(&out[r * PI + 2 * c2]) = (uint16_t)((q & 0xffu) | ((q >> 8) & 0xff00u));   // PI is even
         }
         __syncthreads();
         // write the part of level k+1 this CTA owns: tile scaled by 2^(NL-1-k), 8 pixels per store
@@ -116,7 +143,10 @@ __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
         in = out; in_pitch = PI; in_ox = lox[k + 1];
         if (blockIdx.z == 0 && a.trace_id == TR_PYR_LEFT) trace_phase(a.trace, 17 + k);
         // the next transition overwrites tmp and the other ping-pong buffer only after every thread passed the barriers above
-    }
+    };
+    transition(std::integral_constant<int, 0>{});
+    if constexpr (NL >= 2) transition(std::integral_constant<int, 1>{});
+    if constexpr (NL >= 3) transition(std::integral_constant<int, 2>{});
 }
 
 // Builds levels first+1 .. first+count of a pyramid (count <= 3) in one launch.
