@@ -625,7 +625,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     for (int p = 0; p < 2; ++p) {   // corner stage, double-buffered: frame k+1's response runs while frame k is on the chain
         TRY(dalloc(b, &h.eig[p], SP)); TRY(dalloc(b, &h.lmflag[p], SP));
         TRY(dalloc(b, &h.cand[p], (size_t)S * h.cand_cap)); TRY(dalloc(b, &h.cand_sorted[p], (size_t)S * h.cand_cap));
-        TRY(dalloc(b, &h.hist[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start[p], (size_t)S * (h.n_buckets + 1)));
+        TRY(dalloc(b, &h.hist[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start[p], (size_t)S * (h.n_buckets + 8)));
         TRY(dalloc(b, &h.bucket_fill[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz[p], (size_t)S * h.n_buckets));
         TRY(dalloc(b, &h.ccnt[p], (size_t)S * C_COUNT));
     }

@@ -49,7 +49,7 @@ struct DevBatch {
                                      //               reused as sort scratch by gftt_select once scattered
     unsigned long long* cand_sorted[2]; // [parity][S][cand_cap] same keys grouped by bucket, strongest bucket first
     unsigned int* hist[2];           // [parity][S][n_buckets]
-    unsigned int* bucket_start[2];   // [parity][S][n_buckets + 1] start of bucket d in cand_sorted, d = n_buckets-1-bucket (descending)
+    unsigned int* bucket_start[2];   // [parity][S][n_buckets + 8] (one entry past the end + padding that keeps every stream 16-byte aligned) start of bucket d in cand_sorted, d = n_buckets-1-bucket (descending)
     unsigned int* bucket_fill[2];    // [parity][S][n_buckets] scatter cursors (indexed by d)
     int* bucket_nz[2];               // [parity][S][n_buckets] the non-empty d, ascending (counter C_N_NZ_BUCKETS)
     int* ccnt[2];                    // [parity][S][C_COUNT] the corner stage's own counters (C_N_LOCALMAX, C_N_NZ_BUCKETS)

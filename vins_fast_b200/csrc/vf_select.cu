@@ -20,7 +20,9 @@
 
 namespace vf {
 
-constexpr int ST_THREADS = 256;
+// one warp per SM sub-partition pair is enough for the latency-bound small case; the quadratic phases (stable rank, conflict
+// matrix, rounds) of a large capacity want every thread an SM can hold
+constexpr int ST_THREADS_SMALL = 256, ST_THREADS_LARGE = 1024, ST_LARGE_CAP = 512;
 constexpr int kConflictSmemCap = 512;   // conflict matrix lives in shared memory up to this many features
 
 // dynamic shared memory layout for `cap` features
@@ -36,7 +38,8 @@ struct SelLayout {
         off_cnt = o;   o += sizeof(int) * cap;
         off_order = o; o += sizeof(int) * cap;
         off_state = o; o += sizeof(int) * cap;                  // rounded centres packed (x | y << 16) after sorting
-        off_lists = o; o += sizeof(int) * cap * 2;              // left / right stopper lists of the parallel partition
+        off_lists = o; o += sizeof(int) * (cap * 2 + 32);       // left / right stopper lists of the parallel partition; later the
+                                                                // sentinel-padded key array of the final rank (cap + 32)
         off_words = o; o += sizeof(uint32_t) * words * 4;       // accepted / undecided masks, double use
         off_conf = o;  o += (cap <= kConflictSmemCap) ? sizeof(uint32_t) * (size_t)cap * words : 0;
         total = o;
@@ -148,6 +151,7 @@ __device__ void block_introsort_loop(SortItem* v, int n, int4* queue, int* qn, i
     }
 }
 
+template <int ST_THREADS>
 __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid_constant__ DevBatch b, int parity_arg) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -200,22 +204,22 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
     // ---- 2. libstdc++ std::sort order: introsort loop (sequential replay) + stable rank (parallel) ----
     block_introsort_loop(items, n_tr, sort_queue, sort_qn, lists, lists + cap);
     trace_phase(b.trace, 9);
-    // stable rank by key (descending): r(j) = #{k : key_k > key_j} + #{k < j : key_k == key_j}; the keys go to a dense array
-    // first so that the n compares per thread run on vector loads with independent accumulators
-    int* dense = lists;                     // the partition's scratch is free again
-    for (int j = tid; j < ((n_tr + 3) & ~3); j += ST_THREADS) dense[j] = j < n_tr ? items[j].key : (int)0x80000000;
+    // What is left is std::__final_insertion_sort, a stable insertion: r(j) = #{k : key_k > key_j} + #{k < j : key_k == key_j}
+    //   = j - #{k < j : key_k < key_j} + #{k > j : key_k > key_j}.
+    // The introsort loop only leaves partitions of at most 16 elements unsorted and no key of an earlier partition is
+    // smaller (none of a later one larger), so both sets lie within 15 positions of j: 30 compares per element instead
+    // of n.  The keys go to a dense array padded with +inf / -inf sentinels on either side.
+    int* dense = lists;                     // the partition's scratch is free again (2 * cap ints; cap >= 1)
+    for (int j = tid; j < n_tr + 32; j += ST_THREADS)
+        dense[j] = j < 16 ? 0x7fffffff : (j - 16 < n_tr ? items[j - 16].key : (int)0x80000000);
     __syncthreads();
     for (int j = tid; j < n_tr; j += ST_THREADS) {
-        const int kj = dense[j];
-        int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-        for (int k = 0; k < n_tr; k += 4) {
-            const int4 q = *reinterpret_cast<const int4*>(dense + k);
-            r0 += (q.x > kj) || (q.x == kj && k + 0 < j);
-            r1 += (q.y > kj) || (q.y == kj && k + 1 < j);
-            r2 += (q.z > kj) || (q.z == kj && k + 2 < j);
-            r3 += (q.w > kj) || (q.w == kj && k + 3 < j);
-        }
-        order[(r0 + r1) + (r2 + r3)] = items[j].payload;
+        const int* kp = dense + 16 + j;
+        const int kj = kp[0];
+        int lt = 0, gt = 0;
+#pragma unroll
+        for (int d = 1; d <= 15; ++d) { lt += kp[-d] < kj; gt += kp[d] > kj; }
+        order[j - lt + gt] = items[j].payload;
     }
     __syncthreads();
     for (int r = tid; r < n_tr; r += ST_THREADS) {
@@ -235,18 +239,29 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
     trace_phase(b.trace, 10);
     // ---- 3. conflict bits: conf[r][w] bit k set iff feature 32w+k precedes r in sorted order and lies within min_dist ----
     const int R2 = b.min_dist * b.min_dist;
-    for (int i = tid; i < n_tr * words; i += ST_THREADS) {
-        const int r = i / words, w = i - r * words;
-        uint32_t bits = 0u;
-        const int cx = (int)(short)(centre[r] & 0xffff), cy = centre[r] >> 16;
-        const int kend = min(32, r - 32 * w);
+    // Work item of a WARP = (block B of 32 rows, word w <= B) of the lower triangle: the 32 lanes take the rows of the block
+    // and share the word, so centre[32w + k] is one broadcast load (lanes with different w would all hit bank k) and the
+    // upper triangle is never visited.
+    {
+        const int n_pairs = words * (words + 1) / 2, nw = ST_THREADS / 32;
+        for (int id = wid; id < n_pairs; id += nw) {
+            int B = (int)((sqrtf(8.f * (float)id + 1.f) - 1.f) * 0.5f);
+            while (B * (B + 1) / 2 > id) --B;
+            while ((B + 1) * (B + 2) / 2 <= id) ++B;
+            const int w = id - B * (B + 1) / 2, r = 32 * B + lane;
+            if (r < n_tr) {
+                uint32_t bits = 0u;
+                const int cx = (int)(short)(centre[r] & 0xffff), cy = centre[r] >> 16;
+                const int kend = w == B ? lane : 32;
 #pragma unroll 8
-        for (int k = 0; k < kend; ++k) {
-            const int c2 = centre[32 * w + k];
-            const int dx = cx - (int)(short)(c2 & 0xffff), dy = cy - (c2 >> 16);
-            if (dx * dx + dy * dy <= R2) bits |= 1u << k;
+                for (int k = 0; k < kend; ++k) {
+                    const int c2 = centre[32 * w + k];
+                    const int dx = cx - (int)(short)(c2 & 0xffff), dy = cy - (c2 >> 16);
+                    if (dx * dx + dy * dy <= R2) bits |= 1u << k;
+                }
+                conf[(size_t)r * words + w] = bits;
+            }
         }
-        conf[(size_t)r * words + w] = bits;
     }
     __syncthreads();
 
@@ -258,11 +273,13 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
             const int r = base + tid;
             int decision = 0;   // 0 none, 1 accept, 2 reject
             if (r < n_tr && ((undw[r >> 5] >> (r & 31)) & 1u)) {
-                bool hit_acc = false, hit_und = false;
+                // no short-circuit: for a large capacity the matrix lives in global memory and the loads must overlap
+                uint32_t hit_acc = 0u, hit_und = 0u;
+#pragma unroll 4
                 for (int w = 0; w <= (r >> 5); ++w) {
                     const uint32_t c = conf[(size_t)r * words + w];
-                    hit_acc = hit_acc || (c & accw[w]);
-                    hit_und = hit_und || (c & undw[w]);
+                    hit_acc |= c & accw[w];
+                    hit_und |= c & undw[w];
                 }
                 decision = hit_acc ? 2 : (hit_und ? 0 : 1);
                 any_undecided = any_undecided || decision == 0;
@@ -315,14 +332,16 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
 // outside any stream capture).
 cudaError_t select_tracked_prepare(int cap) {
     const size_t smem = select_tracked_smem_bytes(cap);
-    const cudaError_t e = cudaFuncSetAttribute(select_tracked_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout);
+    const void* fn = cap > ST_LARGE_CAP ? (const void*)select_tracked_kernel<ST_THREADS_LARGE> : (const void*)select_tracked_kernel<ST_THREADS_SMALL>;
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout);
     if (e != cudaSuccess) return e;
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(select_tracked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 void launch_select_tracked(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
-    select_tracked_kernel<<<h.n_streams, ST_THREADS, select_tracked_smem_bytes(h.cap), stream>>>(h, parity);
+    if (h.cap > ST_LARGE_CAP) select_tracked_kernel<ST_THREADS_LARGE><<<h.n_streams, ST_THREADS_LARGE, select_tracked_smem_bytes(h.cap), stream>>>(h, parity);
+    else select_tracked_kernel<ST_THREADS_SMALL><<<h.n_streams, ST_THREADS_SMALL, select_tracked_smem_bytes(h.cap), stream>>>(h, parity);
 }
 
 }  // namespace vf
