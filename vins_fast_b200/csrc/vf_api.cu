@@ -613,7 +613,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     h.stage_left[0] = b->stage[0][0]; h.stage_left[1] = b->stage[0][1]; h.stage_pitch = b->stage_pitch; h.stage_stride = (size_t)b->stage_pitch * H;
     const size_t SC = (size_t)S * cap, SP = (size_t)S * W * H;
     for (int p = 0; p < 2; ++p) {
-        TRY(dalloc(b, &h.kps[p], SC)); TRY(dalloc(b, &h.ids[p], SC)); TRY(dalloc(b, &h.cnt[p], SC));
+        TRY(dalloc(b, &h.kps[p], SC)); TRY(dalloc(b, &h.ids[p], SC)); TRY(dalloc(b, &h.cnt[p], SC)); TRY(dalloc(b, &h.prev_idx[p], SC));
         TRY(dalloc(b, &h.un_left[p], SC)); TRY(dalloc(b, &h.un_right[p], SC)); TRY(dalloc(b, &h.right_ok[p], SC));
         TRY(dalloc(b, &h.counters[p], (size_t)S * C_COUNT)); TRY(dalloc(b, &h.times[p], (size_t)S));
     }

@@ -28,6 +28,8 @@ struct DevBatch {
     float2* kps[2];                  // [parity][S][cap] current_kps_ at the end of the frame
     int* ids[2];                     // [parity][S][cap] ids_
     int* cnt[2];                     // [parity][S][cap] track_count_
+    int* prev_idx[2];                // [parity][S][cap] index of the feature in the PREVIOUS frame's arrays, -1 for a new corner:
+                                     // what the reference looks up through its id -> point maps (ComputeKpsVelocity)
     float2* un_left[2];              // [parity][S][cap] current_un_distortion_kps_ (keyed by ids[parity])
     float2* un_right[2];             // [parity][S][cap] right undistorted point where right_ok
     uint8_t* right_ok[2];            // [parity][S][cap] 1 = id has a right observation this frame

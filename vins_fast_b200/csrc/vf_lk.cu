@@ -747,8 +747,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_cons
     // everything the CTA needs from HBM goes out in one batch, beside the count (i < cap: always readable)
     const size_t o = (size_t)s * cap + i;
     const float2 p0 = b.kps[parity][o];
-    const int id = b.ids[parity][o];
-    const int n_prev = cnt_prev[C_N_TOTAL];
+    const int pidx = b.prev_idx[parity][o];
 #ifdef VF_LK_TIMING
     const unsigned long long cta_t0 = vf_globaltimer();
 #endif
@@ -758,16 +757,9 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_cons
     load_pyr(sm, 1, b.right[parity], b.lvl_stream_stride, s);          // 1 = current right
     if (tid == 0) sm.found[1] = -1;
     __syncthreads();
-    // id lookup in the previous frame's right map (previous_right_un_distortion_ids_kps_map_); independent of the LK
-    {
-        const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
-        const uint8_t* prev_ok = b.right_ok[parity ^ 1] + (size_t)s * cap;
-        for (int j = tid; j < n_prev; j += kLkThreads) {
-            const int pid = prev_ids[j];
-            const int pok = prev_ok[j];
-            if (pid == id && pok) sm.found[1] = j;
-        }
-    }
+    // previous_right_un_distortion_ids_kps_map_.find(id): select_tracked recorded where the feature sat in the previous
+    // frame's arrays (-1: new corner); it is in the right map iff it had a right observation there
+    if (tid == 0 && pidx >= 0 && b.right_ok[parity ^ 1][(size_t)s * cap + pidx]) sm.found[1] = pidx;
     const int L = min(b.lk_max_level, b.right[parity].n_levels - 1);
     const LkResult f = lk_track_point(sm, 0, 1, p0, p0, false, L, stat);
     const float2 rp = make_float2(f.x, f.y);
@@ -807,26 +799,19 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_cons
 //      Depends on current_kps_ / ids_ only, so it runs beside the stereo LK on the side stream. ----
 __global__ void __launch_bounds__(128) undistort_left_kernel(const __grid_constant__ DevBatch b, int parity_arg, const double* __restrict__ dt_host, int* __restrict__ n_host) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
-    extern __shared__ int prev_ids_sm[];   // [cap] ids_ of the previous frame
     TraceScope trace(b.trace, TR_UNDISTORT_LEFT + 16 * tphase);
     const int s = blockIdx.y, cap = b.cap;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
-    const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
-    const int* prev_ids = b.ids[parity ^ 1] + (size_t)s * cap;
-    for (int j = threadIdx.x; j < n_prev; j += blockDim.x) prev_ids_sm[j] = prev_ids[j];
     if (blockIdx.x == 0 && threadIdx.x == 0) n_host[s] = n;      // feature count of the frame, straight to pinned host memory
-    __syncthreads();
     if (i >= n) return;
     const size_t o = (size_t)s * cap + i;
     const float2 p0 = b.kps[parity][o];
     const int id = b.ids[parity][o];
     const float2 un = undistort_point(b.cam[0], p0);
-    // previous_left_un_distortion_ids_kps_map_.find(id): only features tracked from the previous frame (track count > 1)
-    // can be in it; ids are unique, so a branch-free scan of the staged id list finds the entry
-    int found = -1;
-    if (b.cnt[parity][o] > 1)
-        for (int j = 0; j < n_prev; ++j) found = prev_ids_sm[j] == id ? j : found;
+    // previous_left_un_distortion_ids_kps_map_.find(id): every feature of the previous frame is in that map, and
+    // select_tracked recorded where this one sat in the previous frame's arrays (-1: new corner)
+    const int found = b.prev_idx[parity][o];
     float2 v = make_float2(0.f, 0.f);
     if (found >= 0) v = velocity(un, b.un_left[parity ^ 1][(size_t)s * cap + found], dt_host[s]);   // dt: zero-copy read of the host's value
     vf_feature* rec = &b.out[tphase % 3][o];
@@ -893,7 +878,7 @@ void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, in
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, const double* dt_host, int* n_host, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);
-    undistort_left_kernel<<<grid, 128, sizeof(int) * (size_t)(h.cap > 0 ? h.cap : 1), stream>>>(h, parity, dt_host, n_host);
+    undistort_left_kernel<<<grid, 128, 0, stream>>>(h, parity, dt_host, n_host);
 }
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {

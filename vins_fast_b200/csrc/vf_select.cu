@@ -27,7 +27,7 @@ constexpr int kConflictSmemCap = 512;   // conflict matrix lives in shared memor
 
 // dynamic shared memory layout for `cap` features
 struct SelLayout {
-    size_t off_pts, off_ids, off_cnt, off_items, off_order, off_state, off_lists, off_words, off_conf, total;
+    size_t off_pts, off_ids, off_cnt, off_items, off_order, off_src, off_state, off_lists, off_words, off_conf, total;
     int words;
     __host__ __device__ explicit SelLayout(int cap) {
         words = (cap + 31) / 32;
@@ -37,6 +37,7 @@ struct SelLayout {
         off_ids = o;   o += sizeof(int) * cap;
         off_cnt = o;   o += sizeof(int) * cap;
         off_order = o; o += sizeof(int) * cap;
+        off_src = o;   o += sizeof(int) * cap;                  // index of the compacted feature in the previous frame's arrays
         off_state = o; o += sizeof(int) * cap;                  // rounded centres packed (x | y << 16) after sorting
         off_lists = o; o += sizeof(int) * (cap * 2 + 32);       // left / right stopper lists of the parallel partition; later the
                                                                 // sentinel-padded key array of the final rank (cap + 32)
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
     int* ids = reinterpret_cast<int*>(smem_raw + L.off_ids);
     int* cnts = reinterpret_cast<int*>(smem_raw + L.off_cnt);
     int* order = reinterpret_cast<int*>(smem_raw + L.off_order);
+    int* src = reinterpret_cast<int*>(smem_raw + L.off_src);
     int* centre = reinterpret_cast<int*>(smem_raw + L.off_state);
     int* lists = reinterpret_cast<int*>(smem_raw + L.off_lists);
     uint32_t* accw = reinterpret_cast<uint32_t*>(smem_raw + L.off_words);
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
             ids[j] = b.ids[parity ^ 1][so + i];
             const int c = b.cnt[parity ^ 1][so + i] + 1;
             cnts[j] = c;
+            src[j] = i;
             items[j].key = c; items[j].payload = j;
         }
         n_tr += tot;
@@ -317,6 +320,7 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
             b.kps[parity][so + k] = pts[j];
             b.ids[parity][so + k] = ids[j];
             b.cnt[parity][so + k] = cnts[j];
+            b.prev_idx[parity][so + k] = src[j];
         }
         n_kept += tot;
         __syncthreads();
