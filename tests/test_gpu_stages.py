@@ -101,16 +101,36 @@ def test_lk_textureless_and_empty(lib, oracle):
     assert q.shape == (0, 2) and st.shape == (0,)
 
 
-@pytest.mark.parametrize("shape", [(480, 752), (99, 131), (64, 67)])
-def test_min_eigen_bit_exact(lib, oracle, euroc_seq, shape):
+@pytest.fixture(params=[1, 2], ids=["tiles", "strips"])
+def response_kernel(request, lib):
+    """Both corner-response kernels (the library picks by frame size) must give the same bits."""
+    from vins_fast_b200 import ops
+    ops.set_response_kernel(request.param)
+    yield request.param
+    ops.set_response_kernel(0)
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (99, 131), (64, 67), (65, 120), (64, 121), (70, 244), (130, 64), (97, 362)])
+def test_min_eigen_bit_exact(lib, oracle, euroc_seq, shape, response_kernel):
     from vins_fast_b200 import ops
     img = _crop(euroc_seq.frame(5)[1], *shape)
     got, ref = ops.min_eigen(img), oracle.min_eigen_val(img)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (got != ref).mean()
 
 
+def test_min_eigen_flat_and_saturated(lib, oracle, euroc_seq, response_kernel):
+    """Constant patches make the radicand of the eigenvalue exactly 0 (the square root's special-case path)."""
+    from vins_fast_b200 import ops
+    img = _crop(euroc_seq.frame(3)[1], 200, 360).copy()
+    img[40:90, 100:260] = 255
+    img[120:124, :] = 0
+    img[:, 300:] = 17
+    got, ref = ops.min_eigen(img), oracle.min_eigen_val(img)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), (got != ref).mean()
+
+
 @pytest.mark.parametrize("n,md", [(150, 30), (200, 15), (2000, 30), (50, 7), (400, 1), (3000, 3)])
-def test_good_features_selection_order(lib, oracle, euroc_frames, n, md):
+def test_good_features_selection_order(lib, oracle, euroc_frames, n, md, response_kernel):
     from vins_fast_b200 import ops
     img = euroc_frames[2][1]
     got = ops.good_features(img, n, 0.01, md)
@@ -118,7 +138,7 @@ def test_good_features_selection_order(lib, oracle, euroc_frames, n, md):
     assert np.array_equal(got, ref)
 
 
-def test_good_features_masked(lib, oracle, euroc_frames):
+def test_good_features_masked(lib, oracle, euroc_frames, response_kernel):
     from vins_fast_b200 import ops
     img = euroc_frames[6][1]
     rng = np.random.default_rng(5)
@@ -132,7 +152,7 @@ def test_good_features_masked(lib, oracle, euroc_frames):
     assert len(ops.good_features(img, 10, 0.01, 30, mask=empty)) == 0
 
 
-def test_good_features_flat_and_plateau(lib, oracle):
+def test_good_features_flat_and_plateau(lib, oracle, response_kernel):
     from vins_fast_b200 import ops
     flat = np.full((96, 128), 10, np.uint8)
     assert len(ops.good_features(flat, 50, 0.01, 5)) == 0

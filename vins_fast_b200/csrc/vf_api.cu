@@ -988,6 +988,12 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
     return VF_OK;
 }
 
+vf_status vf_debug_set_response_kernel(int32_t mode) {
+    if (mode < 0 || mode > 2) return fail(nullptr, VF_ERR_INVALID_ARG, "response kernel mode must be 0, 1 or 2");
+    set_response_kernel_mode(mode);
+    return VF_OK;
+}
+
 vf_status vf_op_min_eigen(const uint8_t* img, int32_t w, int32_t h, int32_t device, float* out) {
     if (!img || !out) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
     BatchHolder bh;

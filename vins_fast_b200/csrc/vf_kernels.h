@@ -85,6 +85,7 @@ void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_p
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream);
 
 // ---- vf_corners.cu ----
+void set_response_kernel_mode(int mode);   // 0 auto, 1 tiles, 2 strips (parity tests)
 void launch_response_nms(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
 void launch_bucket_scan(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);
 void launch_bucket_scatter(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);

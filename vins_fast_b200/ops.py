@@ -53,6 +53,11 @@ def lk(prev, nxt, prev_pts, max_level: int = 3, init=None, device: int = -1, ret
     return (q, st, it) if return_iters else (q, st)
 
 
+def set_response_kernel(mode: int) -> None:
+    """Parity tests: 0 = pick the corner-response kernel by frame size, 1 = tiles, 2 = strips (identical results)."""
+    check(load().vf_debug_set_response_kernel(int(mode)))
+
+
 def min_eigen(img, device: int = -1) -> np.ndarray:
     """cv::cornerMinEigenVal(img, 3, ksize=3) -> float32 (h, w)."""
     a = np.ascontiguousarray(_img(img))
