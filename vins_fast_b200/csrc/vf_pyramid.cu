@@ -203,19 +203,25 @@ __global__ void __launch_bounds__(256) pad_levels_kernel(PadArgs a) {
     const int w = a.w[l], h = a.h[l], pitch = a.pitch[l], F = kPyrPadFill;
     uint8_t* base = a.lvl[l] + (size_t)img * a.stride[l];
     if (l == 0 && a.src0.p) {
-        // whole padded extent of level 0 from the staging image: rows -F..h+F-1, columns -32..w+31 (word granularity)
-        const int wpr = (w + 2 * kPyrPad + 3) / 4;
-        const int row = j / wpr - F, col = (j - (row + F) * wpr) * 4 - kPyrPad;
+        // whole padded extent of level 0 from the staging image: rows -F..h+F-1, columns -32..pitch-33, one 16-byte chunk
+        // per thread (both row bases and the chunk columns are 16-byte aligned; the chunks tile the padded pitch exactly)
+        const int cpr = pitch / 16;
+        const int row = j / cpr - F, col = (j - (row + F) * cpr) * 16 - kPyrPad;
         const uint8_t* srow = a.src0.p + (size_t)img * a.src0.stride + (size_t)refl101(row, h) * a.src0.pitch;
-        uint32_t v;
-        if (col >= 0 && col + 3 < w) {
-            v = *reinterpret_cast<const uint32_t*>(srow + col);      // staging rows are 16-byte aligned
+        uint4 v;
+        if (col >= 0 && col + 15 < w) {
+            v = *reinterpret_cast<const uint4*>(srow + col);
         } else {
-            v = 0;
+            uint32_t q[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v |= (uint32_t)srow[refl101(col + q, w)] << (8 * q);
+            for (int k = 0; k < 4; ++k) {
+                q[k] = 0;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) q[k] |= (uint32_t)srow[refl101(col + 4 * k + t, w)] << (8 * t);
+            }
+            v = make_uint4(q[0], q[1], q[2], q[3]);
         }
-        *reinterpret_cast<uint32_t*>(base + (ptrdiff_t)row * pitch + col) = v;
+        *reinterpret_cast<uint4*>(base + (ptrdiff_t)row * pitch + col) = v;
         return;
     }
     const int c0 = w & ~3;
@@ -253,7 +259,7 @@ static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_ima
         a.stride[l] = (ok && stride) ? stride[l] : 0;
         int strip;
         int items = ok ? pad_items(pv.w[l], pv.h[l], &strip) : 0;
-        if (l == 0 && src0) items = (pv.h[0] + 2 * kPyrPadFill) * ((pv.w[0] + 2 * kPyrPad + 3) / 4);
+        if (l == 0 && src0) items = (pv.h[0] + 2 * kPyrPadFill) * (pv.pitch[0] / 16);
         a.first_item[l + 1] = a.first_item[l] + items;
     }
     dim3 grid((a.first_item[pv.n_levels] + 255) / 256, n_images);
