@@ -54,14 +54,17 @@ del os.environ["VF_TRACE"]
 tnames = ("clear_frame pyrdown_left pad_left lk_temporal select_tracked response_nms bucket_scan bucket_scatter "
           "mask_and_max gftt_select pyrdown_right pad_right lk_stereo undistort_left").split()
 tbuf = (C.c_ulonglong * 256)()
-tacc = []
+tacc, sel_acc = [], []
 for k in range(n_frames):
     b.track_ptrs(frames[k][0], ptr[k][0], W, ptr[k][1], W)
     vf.load().vf_batch_trace_get(b._h, tbuf, 256)
     if k >= 3:
         a = np.array(list(tbuf), np.uint64)[:192].reshape(6, 16, 2)[k % 6, :14]
         tacc.append((a - a[:, 0].min()).astype(np.int64))
+        ph = np.array(list(tbuf), np.uint64)[224 + 8:224 + 13].astype(np.int64)   # select_tracked's phase stamps (stream 0)
+        sel_acc.append(np.diff(ph))
 tm = np.mean(tacc, 0) / 1e3
+select_phases_us = dict(zip(["introsort", "rank", "conflict_matrix", "rounds"], [round(float(v), 1) for v in np.mean(sel_acc, 0) / 1e3]))
 kernel_us = {nm: round(float(tm[i, 1] - tm[i, 0]), 1) for i, nm in enumerate(tnames)}
 frame_span_us = round(float(tm[:, 1].max()), 1)
 npx = W * H
@@ -75,4 +78,4 @@ except Exception:
 hbm = {k: {"us": kernel_us[k], "alg_bytes": int(v), "GBps": v / (kernel_us[k] * 1e-6) / 1e9,
            "frac_of_hbm_peak": v / (kernel_us[k] * 1e-6) / 1e9 / peak} for k, v in alg.items() if kernel_us.get(k)}
 print(json.dumps({"workload": name, "streams": S_, "size": [W, H], "max_cnt": cap, "lk_max_level": level, "features_last": int(n[0]),
-                  "e2e_sync_us_per_frame": e2e_us, "kernel_us": kernel_us, "frame_span_us": frame_span_us, "stages_us": us, "streaming": hbm, "hbm_peak_GBps": peak}))
+                  "e2e_sync_us_per_frame": e2e_us, "kernel_us": kernel_us, "select_tracked_phases_us": select_phases_us, "frame_span_us": frame_span_us, "stages_us": us, "streaming": hbm, "hbm_peak_GBps": peak}))

@@ -629,7 +629,6 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
         TRY(dalloc(b, &h.bucket_fill[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz[p], (size_t)S * h.n_buckets));
         TRY(dalloc(b, &h.ccnt[p], (size_t)S * C_COUNT));
     }
-    if (cap > 512) TRY(dalloc(b, &h.conflict, (size_t)S * cap * ((cap + 31) / 32)));
     // result records, feature counts and frame intervals live in mapped pinned host memory: the kernels write / read them
     // in place, no copy commands at either end of a frame
     for (int p = 0; p < 3; ++p) {

@@ -57,7 +57,6 @@ struct DevBatch {
     int* ccnt[2];                    // [parity][S][C_COUNT] the corner stage's own counters (C_N_LOCALMAX, C_N_NZ_BUCKETS)
     uint8_t* mask;                   // [S][H][W] SetFeatureExtractorMask
     unsigned long long* surv;        // [S][cand_cap] candidates outside the mask (unordered), written by mask_and_max
-    uint32_t* conflict;              // [S][cap][(cap+31)/32] min_dist conflict bit-matrix of select_tracked when cap > 512
 
     vf_feature* out[3];              // [frame % 3][S][cap] packed result records, in MAPPED PINNED HOST memory (zero-copy download);
                                      // a ring of three so that the host may collect frame k-2 while k-1 and k are in flight

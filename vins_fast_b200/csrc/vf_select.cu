@@ -23,11 +23,12 @@ namespace vf {
 // one warp per SM sub-partition pair is enough for the latency-bound small case; the quadratic phases (stable rank, conflict
 // matrix, rounds) of a large capacity want every thread an SM can hold
 constexpr int ST_THREADS_SMALL = 256, ST_THREADS_LARGE = 1024, ST_LARGE_CAP = 512;
-constexpr int kConflictSmemCap = 512;   // conflict matrix lives in shared memory up to this many features
+constexpr int kConflictSmemCap = 256;   // up to this many features: dense conflict bit-matrix in shared memory; above: spatial grid
+constexpr int kGridCells = 4096;        // cells of the spatial grid (cell edge = power of two >= min_dist, chosen so that the image fits)
 
 // dynamic shared memory layout for `cap` features
 struct SelLayout {
-    size_t off_pts, off_ids, off_cnt, off_items, off_order, off_src, off_state, off_lists, off_words, off_conf, total;
+    size_t off_pts, off_ids, off_cnt, off_items, off_order, off_src, off_state, off_lists, off_words, off_conf, off_grid, total;
     int words;
     __host__ __device__ explicit SelLayout(int cap) {
         words = (cap + 31) / 32;
@@ -43,6 +44,7 @@ struct SelLayout {
                                                                 // sentinel-padded key array of the final rank (cap + 32)
         off_words = o; o += sizeof(uint32_t) * words * 4;       // accepted / undecided masks, double use
         off_conf = o;  o += (cap <= kConflictSmemCap) ? sizeof(uint32_t) * (size_t)cap * words : 0;
+        off_grid = o;  o += (cap <= kConflictSmemCap) ? 0 : sizeof(int) * (2 * kGridCells + 2);   // cell starts (+1), fill cursors
         total = o;
     }
 };
@@ -172,8 +174,11 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
     int* lists = reinterpret_cast<int*>(smem_raw + L.off_lists);
     uint32_t* accw = reinterpret_cast<uint32_t*>(smem_raw + L.off_words);
     uint32_t* undw = accw + L.words;
-    uint32_t* conf = (cap <= kConflictSmemCap) ? reinterpret_cast<uint32_t*>(smem_raw + L.off_conf)
-                                               : b.conflict + (size_t)s * cap * L.words;
+    uint32_t* conf = reinterpret_cast<uint32_t*>(smem_raw + L.off_conf);   // dense path only (cap <= kConflictSmemCap)
+    const bool use_grid = cap > kConflictSmemCap;
+    int* cell_start = reinterpret_cast<int*>(smem_raw + L.off_grid);       // [n_cell + 1], grid path only
+    int* cell_cur = cell_start + kGridCells + 1;                           // [n_cell]
+    int* cell_items = lists;                                               // [n_tr] ranks grouped by cell (the partition scratch is free by then)
     const int words = L.words;
     int* counters = b.counters[parity] + s * C_COUNT;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
@@ -240,12 +245,46 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
     __syncthreads();
 
     trace_phase(b.trace, 10);
-    // ---- 3. conflict bits: conf[r][w] bit k set iff feature 32w+k precedes r in sorted order and lies within min_dist ----
     const int R2 = b.min_dist * b.min_dist;
+    int gsh = 0, gw = 1, gh = 1;
+    if (use_grid) {
+        // ---- 3a. many features: bin the rounded centres into a grid whose cells are at least min_dist wide -- everything
+        //          within min_dist of a feature then lies in the 3x3 cells around it, and with features that were thinned to
+        //          min_dist a frame ago that is a handful of candidates instead of a row of an n x n matrix ----
+        while ((1 << gsh) < b.min_dist || (((b.W - 1) >> gsh) + 1) * (((b.H - 1) >> gsh) + 1) > kGridCells) ++gsh;
+        gw = ((b.W - 1) >> gsh) + 1; gh = ((b.H - 1) >> gsh) + 1;
+        const int n_cell = gw * gh;
+        for (int c = tid; c <= n_cell; c += ST_THREADS) cell_start[c] = 0;
+        __syncthreads();
+        for (int r = tid; r < n_tr; r += ST_THREADS) {
+            const int cc = centre[r];
+            atomicAdd(&cell_start[(cc >> 16 >> gsh) * gw + ((int)(short)(cc & 0xffff) >> gsh) + 1], 1);   // count of cell c at c + 1
+        }
+        __syncthreads();
+        // inclusive scan of the counts: cell_start[c] = first slot of cell c
+        const int ipt = (n_cell + ST_THREADS) / ST_THREADS, i0 = min(1 + tid * ipt, n_cell + 1), i1 = min(i0 + ipt, n_cell + 1);
+        int sum = 0;
+        for (int i = i0; i < i1; ++i) sum += cell_start[i];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_cnt[wid] = incl;
+        __syncthreads();
+        int before = incl - sum;
+        for (int w = 0; w < wid; ++w) before += warp_cnt[w];
+        for (int i = i0; i < i1; ++i) { before += cell_start[i]; cell_start[i] = before; }
+        __syncthreads();
+        for (int c = tid; c < n_cell; c += ST_THREADS) cell_cur[c] = cell_start[c];
+        __syncthreads();
+        for (int r = tid; r < n_tr; r += ST_THREADS) {
+            const int cc = centre[r];
+            cell_items[atomicAdd(&cell_cur[(cc >> 16 >> gsh) * gw + ((int)(short)(cc & 0xffff) >> gsh)], 1)] = r;
+        }
+    } else {
+    // ---- 3. conflict bits: conf[r][w] bit k set iff feature 32w+k precedes r in sorted order and lies within min_dist ----
     // Work item of a WARP = (block B of 32 rows, word w <= B) of the lower triangle: the 32 lanes take the rows of the block
     // and share the word, so centre[32w + k] is one broadcast load (lanes with different w would all hit bank k) and the
     // upper triangle is never visited.
-    {
         const int n_pairs = words * (words + 1) / 2, nw = ST_THREADS / 32;
         for (int id = wid; id < n_pairs; id += nw) {
             int B = (int)((sqrtf(8.f * (float)id + 1.f) - 1.f) * 0.5f);
@@ -276,13 +315,29 @@ __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid
             const int r = base + tid;
             int decision = 0;   // 0 none, 1 accept, 2 reject
             if (r < n_tr && ((undw[r >> 5] >> (r & 31)) & 1u)) {
-                // no short-circuit: for a large capacity the matrix lives in global memory and the loads must overlap
                 uint32_t hit_acc = 0u, hit_und = 0u;
+                if (use_grid) {
+                    const int cc = centre[r], cx = (int)(short)(cc & 0xffff), cy = cc >> 16, gx = cx >> gsh, gy = cy >> gsh;
+                    for (int ny = max(gy - 1, 0); ny <= min(gy + 1, gh - 1); ++ny) {
+                        // the three cells of a grid row are neighbours in memory: one run of items
+                        const int i_end = cell_start[ny * gw + min(gx + 1, gw - 1) + 1];
+                        for (int i = cell_start[ny * gw + max(gx - 1, 0)]; i < i_end; ++i) {
+                            const int r2 = cell_items[i];
+                            const int c2 = centre[r2];
+                            const int dx = cx - (int)(short)(c2 & 0xffff), dy = cy - (c2 >> 16);
+                            if (r2 < r && dx * dx + dy * dy <= R2) {           // an earlier feature within min_dist
+                                hit_acc |= (accw[r2 >> 5] >> (r2 & 31)) & 1u;
+                                hit_und |= (undw[r2 >> 5] >> (r2 & 31)) & 1u;
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll 4
-                for (int w = 0; w <= (r >> 5); ++w) {
-                    const uint32_t c = conf[(size_t)r * words + w];
-                    hit_acc |= c & accw[w];
-                    hit_und |= c & undw[w];
+                    for (int w = 0; w <= (r >> 5); ++w) {
+                        const uint32_t c = conf[(size_t)r * words + w];
+                        hit_acc |= c & accw[w];
+                        hit_und |= c & undw[w];
+                    }
                 }
                 decision = hit_acc ? 2 : (hit_und ? 0 : 1);
                 any_undecided = any_undecided || decision == 0;
