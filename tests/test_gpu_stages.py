@@ -89,6 +89,22 @@ def test_lk_levels_and_small_images(lib, oracle, euroc_frames, level):
     assert np.array_equal(q.view(np.uint32), rq.view(np.uint32))
 
 
+def test_lk_six_levels_many_points(lib, oracle):
+    """Six pyramid levels and more points than fit on the GPU at once: the launch takes the variant of the prologue
+    that forms the terms of A on the fly instead of staging them in shared memory (vf_lk.cu: lk_plan_staged)."""
+    from vins_fast_b200 import ops
+    from vins_fast_b200.synth import StereoSequence
+    seq = StereoSequence(4, 1024, 768)
+    a, b = seq.frame(0)[1], seq.frame(1)[1]
+    pts = _lk_points(a, 500, 13)
+    q, st, it = ops.lk(a, b, pts, 5, return_iters=True)
+    rq, rst, rit = oracle.lk(oracle.Pyramid(a, 5), oracle.Pyramid(b, 5), pts, 5, 21, return_iters=True)
+    assert np.array_equal(st, rst)
+    assert np.array_equal(it, rit)
+    assert np.array_equal(q.view(np.uint32), rq.view(np.uint32)), np.abs(q - rq).max()
+    assert st.sum() > 300
+
+
 def test_lk_textureless_and_empty(lib, oracle):
     from vins_fast_b200 import ops
     flat = np.full((120, 160), 77, np.uint8)

@@ -60,10 +60,10 @@ struct alignas(16) LevelGeo {
 
 constexpr int kChainA = 108;                 // slots of one summation chain of A (84 / 105 terms, zero padded)
 constexpr int kChainsA = 15;                 // 3 matrices x (4 SIMD-lane accumulators + 1 scalar tail)
+constexpr size_t kTermsABytes = sizeof(float) * kChainsA * kChainA;   // staged terms of A per level (optional, see lk_plan_staged)
 
 // Per-level state of one pass, in dynamic shared memory (one block per pyramid level the pass uses).
 struct LevelBlock {
-    alignas(16) float termsA[kChainsA * kChainA];   // terms of A in accumulation order, chain-major
     alignas(16) short2 dI[kWinPx + 3];               // interpolated (Ix, Iy)
     alignas(16) short Iw[kWinPx + 7];                // interpolated I, 2^5 fixed point
     alignas(16) short2 dtile[kTileD * kTileD];       // Scharr (Ix, Iy) at the 22x22 tap positions
@@ -79,6 +79,10 @@ struct LkSmem {
                                               // only when the global exactness bound fails
     alignas(16) float chainB[12];
     int found[2];
+    int termsA_off;                       // byte offset (from the start of this struct) of the staged terms of A,
+                                          // [level][kChainsA * kChainA] behind the level blocks, or 0: the chains then form their
+                                          // terms on the fly (launches with many CTAs, see lk_plan_staged).  An offset rather than
+                                          // a pointer, so that the accesses stay shared-memory instructions
 #ifdef VF_LK_TIMING
     unsigned long long tacc[16], tcnt[16];
     int tbase;
@@ -86,7 +90,22 @@ struct LkSmem {
     alignas(16) LevelBlock lv[1];         // [n_levels of the launch]
 };
 
-static size_t lk_smem_bytes(int n_levels) { return sizeof(LkSmem) + sizeof(LevelBlock) * (size_t)(n_levels > 1 ? n_levels - 1 : 0); }
+static size_t lk_smem_bytes(int n_levels, bool staged) {
+    const size_t nl = (size_t)(n_levels > 1 ? n_levels : 1);
+    return sizeof(LkSmem) + sizeof(LevelBlock) * (nl - 1) + (staged ? kTermsABytes * nl : 0);
+}
+// Staging the terms of A in accumulation order makes the chain phase of the prologue a pure load + add loop (0.8 us per
+// kernel at 752x480, where the launch is one wave of 150 CTAs and only latency counts) but costs 6.5 KB of shared memory per
+// level.  When the launch has more CTAs than fit at once and dropping the staging area at least doubles the resident CTAs
+// per SM (six pyramid levels: 2 -> 5), the chains form their terms on the fly instead.
+static bool lk_plan_staged(int n_levels, long long n_ctas) {
+    const size_t sm_bytes = 228 * 1024, per_cta = 1024;
+    const int regs_limit = 65536 / (96 * kLkThreads);   // 5 CTAs per SM by registers
+    int staged = (int)(sm_bytes / (lk_smem_bytes(n_levels, true) + per_cta)), compact = (int)(sm_bytes / (lk_smem_bytes(n_levels, false) + per_cta));
+    staged = staged < regs_limit ? staged : regs_limit; compact = compact < regs_limit ? compact : regs_limit;
+    if (staged < 1) return false;
+    return n_ctas <= (long long)staged * kNumSms || compact < 2 * staged;
+}
 
 #ifndef VF_LK_ABLATE
 #define VF_LK_ABLATE 0
@@ -181,10 +200,16 @@ __device__ __forceinline__ float chain_value(int n, F term) {
     return acc;
 }
 
+extern __shared__ __align__(16) unsigned char lk_smem_raw[];
+__device__ __forceinline__ float* lk_terms_a(LkSmem&, int off) { return reinterpret_cast<float*>(lk_smem_raw + off); }   // LkSmem sits at offset 0
+
 // One calcOpticalFlowPyrLK for one point, executed cooperatively by the CTA (all threads pass identical
 // arguments and return identical results).  ia / ja select the source and target pyramids in sm.pyr.
 // Not inlined: the two passes of a kernel share one copy of this code.
-__device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init,
+// STAGED: the terms of A are staged in shared memory (sm.termsA_off != 0); two instantiations, so that neither variant of
+// the prologue pays for the other (a launch runs one of them).
+template <bool STAGED>
+__device__ __noinline__ LkResult lk_track_point_impl(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init,
                                                 int max_level, int* iters_io) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float half = 10.f;
@@ -192,6 +217,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     const int nlv = max_level + 1;
     int status = 1, iters = 0, fast = 0;
     float outx = init_pt.x, outy = init_pt.y;
+    const int tA_off = sm.termsA_off;
     LK_T_DECL
 
     // ================= prologue: everything that depends on the source point only, all levels at once =================
@@ -281,9 +307,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     }
     __syncthreads();
     LK_T(1);
-    // ---- P3: 21x21 bilinear patches (I in 2^5, derivatives in Scharr units) of every level + the terms of A, stored
-    //      in OpenCV's accumulation order: SIMD lane l = x & 3 sees columns l, 4+l, 8+l, 12+l of every row in turn
-    //      (slot y*4 + x/4 of chain l), the scalar tail sees columns 16..20 of every row (slot y*5 + x-16 of chain 4) ----
+    // ---- P3: 21x21 bilinear patches (I in 2^5, derivatives in Scharr units) of every level ----
     {
         constexpr int R3 = (kWinPx + kLkThreads - 1) / kLkThreads;
         int ioff[R3], doff[R3], aoff[R3];
@@ -292,7 +316,7 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
             const int e = min(tid + r * kLkThreads, kWinPx - 1);
             const int y = e / kWin, x = e - y * kWin;
             ioff[r] = (y + 1) * kTileI + (x + 1); doff[r] = y * kTileD + x;
-            aoff[r] = x < 16 ? (x & 3) * kChainA + y * 4 + (x >> 2) : 4 * kChainA + y * 5 + (x - 16);
+            aoff[r] = x < 16 ? (x & 3) * kChainA + y * 4 + (x >> 2) : 4 * kChainA + y * 5 + (x - 16);   // slot of the staged terms
         }
 #pragma unroll 1
         for (int level = 0; level < nlv; ++level) {
@@ -316,26 +340,46 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
                 if (e < kWinPx) {
                     B.Iw[e] = (short)ival;
                     B.dI[e] = make_short2((short)ixval, (short)iyval);
-                    float* ta = B.termsA + aoff[r];                    // |ixval|, |iyval| <= 4080: products < 2^24, exact in float
-                    ta[0] = (float)(ixval * ixval);
-                    ta[5 * kChainA] = (float)(ixval * iyval);
-                    ta[10 * kChainA] = (float)(iyval * iyval);
+                    if (STAGED) {                                      // |ixval|, |iyval| <= 4080: products < 2^24, exact in float
+                        float* ta = lk_terms_a(sm, tA_off) + level * (kChainsA * kChainA) + aoff[r];
+                        ta[0] = (float)(ixval * ixval);
+                        ta[5 * kChainA] = (float)(ixval * iyval);
+                        ta[10 * kChainA] = (float)(iyval * iyval);
+                    }
                 }
             }
         }
     }
     __syncthreads();
     LK_T(2);
-    // ---- P4: the 15 ordered float chains of A on every level, one LANE per chain (acc = ((0 + t0) + t1) + ...):
-    //      27 vector loads and 108 dependent FADDs per lane, all chains of all levels side by side ----
+    // ---- P4: the 15 ordered float chains of A on every level, one LANE per chain (acc = ((0 + t0) + t1) + ...), in
+    //      OpenCV's accumulation order: SIMD lane l = x & 3 sees columns l, 4+l, 8+l, 12+l of every row in turn, the scalar
+    //      tail sees columns 16..20 of every row.  Either from the terms P3 staged in that order, or (launches with many CTAs,
+    //      lk_plan_staged) formed on the fly from the interpolated derivatives: every lane then takes five steps per row and
+    //      the fifth step of a four-column chain adds +0 (an exact identity). ----
     for (int level = wid; level < nlv; level += kLkWarps) {
         LevelBlock& B = sm.lv[level];
-        const float4* src = reinterpret_cast<const float4*>(B.termsA + min(lane, kChainsA - 1) * kChainA);
+        const int ch = min(lane, kChainsA - 1), m = ch / 5, c = ch - 5 * m;   // matrix entry (xx, xy, yy), chain
         float acc = 0.f;
+        if (STAGED) {               // staged: 27 vector loads and 108 dependent FADDs per lane (the padding slots hold +0)
+            const float4* src = reinterpret_cast<const float4*>(lk_terms_a(sm, tA_off) + level * (kChainsA * kChainA) + ch * kChainA);
 #pragma unroll
-        for (int i = 0; i < kChainA / 4; ++i) {
-            const float4 v = src[i];
-            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+            for (int i = 0; i < kChainA / 4; ++i) {
+                const float4 v = src[i];
+                acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+            }
+        } else {
+            const int xstep = c < 4 ? 4 : 1;
+            const short2* dIp = B.dI + (c < 4 ? c : 16);
+#pragma unroll 3
+            for (int y = 0; y < kWin; ++y) {
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    const short2 d = dIp[y * kWin + t * xstep];               // columns c + 16 <= 19 and 16 + 4 = 20: in range
+                    const int fa = m < 2 ? d.x : d.y, fb = m == 0 ? d.x : d.y;
+                    acc = __fadd_rn(acc, (c < 4 && t == 4) ? 0.f : (float)(fa * fb));
+                }
+            }
         }
         // iA += v_reduce_sum(qA): tail + ((q0 + q2) + (q1 + q3)); then the 2x2 system of the level
         float r[3];
@@ -617,6 +661,12 @@ __device__ __noinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, floa
     return res;
 }
 
+__device__ __forceinline__ LkResult lk_track_point(LkSmem& sm, int ia, int ja, float2 prev_pt, float2 init_pt, bool use_init,
+                                                   int max_level, int* iters_io) {
+    return sm.termsA_off ? lk_track_point_impl<true>(sm, ia, ja, prev_pt, init_pt, use_init, max_level, iters_io)
+                         : lk_track_point_impl<false>(sm, ia, ja, prev_pt, init_pt, use_init, max_level, iters_io);
+}
+
 // Fill sm.pyr[slot] with stream s of a pyramid (threads 0..kMaxLevels-1 of the given quarter).
 __device__ __forceinline__ void load_pyr(LkSmem& sm, int slot, const PyrView& pv, const size_t* stride, int s) {
     const int l = threadIdx.x - slot * kMaxLevels;
@@ -629,13 +679,18 @@ __device__ __forceinline__ void load_pyr(LkSmem& sm, int slot, const PyrView& pv
     }
 }
 
-// Zero the padding slots of the A chains once per kernel: the terms never overwrite them, and adding +0.0f to a chain
-// value is an exact identity (a chain of non-negative-zero integer-valued floats can never be -0.0f).
-__device__ __forceinline__ void lk_smem_init(LkSmem& sm, int* counters2, int n_levels) {
-    constexpr int kPad = kChainA - 84;   // slots 84..107 (the tails' real terms 84..104 are written later, every pass)
-    for (int i = threadIdx.x; i < n_levels * kChainsA * kPad; i += kLkThreads) {
-        const int level = i / (kChainsA * kPad), r = i - level * (kChainsA * kPad);
-        sm.lv[level].termsA[(r / kPad) * kChainA + 84 + (r % kPad)] = 0.f;
+// Zero the staging area of the b chains once per kernel: the terms never overwrite its padding slots, and adding +0.0f
+// to a chain value is an exact identity (a chain of integer-valued floats that starts at +0 can never be -0.0f).
+__device__ __forceinline__ void lk_smem_init(LkSmem& sm, int* counters2, int n_levels, bool staged) {
+    const int off = staged ? (int)(sizeof(LkSmem) + sizeof(LevelBlock) * (size_t)(n_levels > 1 ? n_levels - 1 : 0)) : 0;
+    if (threadIdx.x == 0) sm.termsA_off = off;
+    if (staged) {
+        float* tA = lk_terms_a(sm, off);                        // slots 84..107 of every chain (the tails' real terms 84..104 are written every pass)
+        constexpr int kPad = kChainA - 84;
+        for (int i = threadIdx.x; i < n_levels * kChainsA * kPad; i += kLkThreads) {
+            const int level = i / (kChainsA * kPad), r = i - level * (kChainsA * kPad);
+            tA[level * (kChainsA * kChainA) + (r / kPad) * kChainA + 84 + (r % kPad)] = 0.f;
+        }
     }
     for (int i = threadIdx.x; i < 10 * kChainA; i += kLkThreads) sm.termsB[i] = 0.f;
     if (threadIdx.x == 0) { counters2[0] = 0; counters2[1] = 0; }
@@ -667,7 +722,6 @@ __device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // f
     return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
-extern __shared__ __align__(16) unsigned char lk_smem_raw[];
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
 __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
@@ -682,7 +736,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_co
     const unsigned long long cta_t0 = vf_globaltimer();
 #endif
     if (i >= n_prev) return;
-    lk_smem_init(sm, stat, b.n_levels);
+    lk_smem_init(sm, stat, b.n_levels, (parity_arg & 2) != 0);
     load_pyr(sm, 0, b.left[prev], b.lvl_stream_stride, s);   // 0 = previous left
     load_pyr(sm, 1, b.left[cur], b.lvl_stream_stride, s);    // 1 = current left
     __syncthreads();
@@ -752,7 +806,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_cons
     const unsigned long long cta_t0 = vf_globaltimer();
 #endif
     if (i >= n) return;
-    lk_smem_init(sm, stat, b.n_levels);
+    lk_smem_init(sm, stat, b.n_levels, (parity_arg & 2) != 0);
     load_pyr(sm, 0, b.left[cur], b.lvl_stream_stride, s);   // 0 = current left
     load_pyr(sm, 1, b.right[parity], b.lvl_stream_stride, s);          // 1 = current right
     if (tid == 0) sm.found[1] = -1;
@@ -829,11 +883,11 @@ __global__ void __launch_bounds__(kLkThreads) lk_op_kernel(PyrView prev, PyrView
     const int i = blockIdx.x;
     if (i >= n) return;
     const int L = min(max_level, min(prev.n_levels, next.n_levels) - 1);
-    lk_smem_init(sm, stat, L + 1);
+    lk_smem_init(sm, stat, L + 1, (use_init & 2) != 0);
     load_pyr(sm, 0, prev, nullptr, 0);
     load_pyr(sm, 1, next, nullptr, 0);
     __syncthreads();
-    const LkResult r = lk_track_point(sm, 0, 1, prev_pts[i], next_pts[i], use_init != 0, L, stat);
+    const LkResult r = lk_track_point(sm, 0, 1, prev_pts[i], next_pts[i], (use_init & 1) != 0, L, stat);
     __syncthreads();
     if (threadIdx.x == 0) {
         next_pts[i] = make_float2(r.x, r.y); status[i] = (uint8_t)r.status;
@@ -853,7 +907,7 @@ void launch_undistort(const CamParams& cam, const float2* uv, float2* out, int n
 
 // The LK kernels keep all per-level state of a pass in (dynamic) shared memory: opt in above 48 KB once per device.
 cudaError_t lk_prepare() {
-    const int bytes = (int)lk_smem_bytes(kMaxLevels);
+    const int bytes = (int)lk_smem_bytes(kMaxLevels, true);
     cudaError_t e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -870,11 +924,13 @@ cudaError_t lk_prepare() {
 
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(h, parity, cur, prev);
+    const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);   // bit 1 of the parity argument
+    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels, staged), stream>>>(h, parity | (staged ? 2 : 0), cur, prev);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
-    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels), stream>>>(h, parity, cur, dt_host);
+    const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);
+    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels, staged), stream>>>(h, parity | (staged ? 2 : 0), cur, dt_host);
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, const double* dt_host, int* n_host, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);
@@ -884,7 +940,9 @@ void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_p
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {
     if (n <= 0) return;
     const int nlv = (max_level < prev.n_levels - 1 ? max_level : prev.n_levels - 1) + 1;
-    lk_op_kernel<<<n, kLkThreads, lk_smem_bytes(nlv > 1 ? nlv : 1), stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow);
+    const bool staged = lk_plan_staged(nlv, n);                                     // bit 1 of the flow flag
+    lk_op_kernel<<<n, kLkThreads, lk_smem_bytes(nlv, staged), stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level,
+                                                                        (use_initial_flow ? 1 : 0) | (staged ? 2 : 0));
 }
 
 }  // namespace vf
