@@ -30,6 +30,11 @@ b = vf.Batch(cfg, S_)
 import torch                                                  # noqa: E402  (pinned host memory only)
 pin = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) for _, l, r in frames]
 ptr = [((C.c_void_p * S_)(*([a.data_ptr()] * S_)), (C.c_void_p * S_)(*([c.data_ptr()] * S_))) for a, c in pin]
+t_warm = time.perf_counter()                                  # bring the clocks up before anything is timed (short runs
+while time.perf_counter() - t_warm < 1.5:                     # otherwise measure the GPU's idle clocks)
+    for k in range(n_frames):
+        b.track_ptrs(frames[k][0], ptr[k][0], W, ptr[k][1], W)
+b.reset()
 for k in range(min(7, n_frames - 1)):
     b.track_ptrs(frames[k][0], ptr[k][0], W, ptr[k][1], W)
 t0 = time.perf_counter()

@@ -417,7 +417,6 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
         return VF_OK;
     };
-    if (!overlap) { vf_status st = issue_right(); if (st != VF_OK) return st; }
     // left pyramid: an overlapped frame builds it on side B right behind its upload (it does not depend on the previous
     // frame, so it is built while that one is still on the chain); a synchronous frame builds it on main, back to back with
     // the temporal LK
@@ -456,8 +455,11 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         // Synchronous frame: nothing to overlap with, so the temporal LK starts as soon as the left pyramid stands (the
         // corner stage runs beside it and is joined before select_tracked) and the stereo pass follows the corner
         // selection inside the same graph, the left undistortion on a branch beside it.
+        // host order = how soon each piece reaches the GPU: the head of the critical path first (it must be queued before
+        // the left upload completes), then the right image (its upload queues behind the left one anyway)
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
         { vf_status st = run(SEQ_HEAD_SYNC, b->main); if (st != VF_OK) return st; }
+        { vf_status st = issue_right(); if (st != VF_OK) return st; }
         { vf_status st = issue_corner(); if (st != VF_OK) return st; }
         { vf_status st = issue_right_pyramid(); if (st != VF_OK) return st; }
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
