@@ -268,6 +268,20 @@ vf_status reset_state(vf_batch* b) {
 //  launch 3.5 us whatever it holds.)
 enum { SEQ_CORNER = 0, SEQ_CHAIN = 1, SEQ_REST_SYNC = 2, SEQ_HEAD_SYNC = 3, SEQ_PYR_LEFT = 4, SEQ_PYR_RIGHT = 5, SEQ_TAIL = 6, SEQ_COUNT = 7 };
 
+}  // namespace
+namespace vf { bool& pdl_hint() { static thread_local bool on = false; return on; } }
+namespace {
+// Turns the hint on for the launches of its scope: kernels that directly follow another kernel of ours in their stream.
+// Off while profiling (the stage timers' events sit between the kernels) and when VF_NO_PDL is set (A/B measurements).
+struct PdlScope {
+    bool prev;
+    PdlScope(const vf_batch* b, bool on) : prev(pdl_hint()) {
+        static const bool disabled = getenv("VF_NO_PDL") != nullptr;
+        pdl_hint() = on && !b->profiling && !disabled;
+    }
+    ~PdlScope() { pdl_hint() = prev; }
+};
+
 vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev, int phase) {
     const DevBatch& h = b->h;
     const int parity = parity_ | (phase << 4);   // kernels take the frame parity in bit 0 and the trace slot above it
@@ -275,14 +289,16 @@ vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev,
     if (which == SEQ_HEAD_SYNC) {
         {
             StageTimer t(b, ST_PYR_LEFT, b->main);
+            PdlScope pdl(b, true);   // the border kernel follows the pyramid kernel
             const Level0Src src = {b->stage[0][parity_], b->stage_pitch, (size_t)b->stage_pitch * h.H};
             b->pyr_launches = launch_pyramid(h.left[cur], h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT + 16 * phase);
         }
-        { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); }
+        { StageTimer t(b, ST_LK_TEMPORAL, b->main); PdlScope pdl(b, true); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); }
     } else if (which == SEQ_PYR_LEFT || which == SEQ_PYR_RIGHT) {
         const int cam = which == SEQ_PYR_RIGHT;
         cudaStream_t st = cam ? b->side_d : b->side_b;
         StageTimer t(b, cam ? ST_PYR_RIGHT : ST_PYR_LEFT, st);
+        PdlScope pdl(b, true);
         const Level0Src src = {b->stage[cam][parity_], b->stage_pitch, (size_t)b->stage_pitch * h.H};
         b->pyr_launches = launch_pyramid(cam ? h.right[parity_] : h.left[cur], h.lvl_stream_stride, b->S, st, &src, h.trace,
                                          (cam ? TR_PYR_RIGHT : TR_PYR_LEFT) + 16 * phase);
@@ -300,15 +316,15 @@ vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev,
         { StageTimer t(b, ST_BUCKET_SCATTER, b->side_a); launch_bucket_scatter(b->d, h, parity, b->side_a); }
     } else {
         if (which == SEQ_CHAIN) { StageTimer t(b, ST_LK_TEMPORAL, b->main); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); }
-        { StageTimer t(b, ST_SELECT_TRACKED, b->main); launch_select_tracked(b->d, h, parity, b->main); }
-        { StageTimer t(b, ST_MASK_AND_MAX, b->main); launch_mask_and_max(b->d, h, parity, b->main); }
-        { StageTimer t(b, ST_GFTT_SELECT, b->main); launch_gftt_select(b->d, h, parity, b->main); }
+        { StageTimer t(b, ST_SELECT_TRACKED, b->main); PdlScope pdl(b, which == SEQ_CHAIN); launch_select_tracked(b->d, h, parity, b->main); }
+        { StageTimer t(b, ST_MASK_AND_MAX, b->main); PdlScope pdl(b, true); launch_mask_and_max(b->d, h, parity, b->main); }
+        { StageTimer t(b, ST_GFTT_SELECT, b->main); PdlScope pdl(b, true); launch_gftt_select(b->d, h, parity, b->main); }
         if (which == SEQ_REST_SYNC) {
             VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
             VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
             { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity, dev_dt, b->dev_n[phase % 3], b->side_e); }
             VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
-            { StageTimer t(b, ST_LK_STEREO, b->main); launch_lk_stereo(b->d, h, parity, cur, dev_dt, b->main); }
+            { StageTimer t(b, ST_LK_STEREO, b->main); PdlScope pdl(b, true); launch_lk_stereo(b->d, h, parity, cur, dev_dt, b->main); }
             VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_un, 0));
         }
     }

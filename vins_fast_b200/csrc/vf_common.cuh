@@ -84,7 +84,25 @@ enum Counter {
 // kernel's start (first CTA) and last end on the GPU's nanosecond timer (the latest launch that used the slot wins): [id + 16 * (frame % 6)][0] = min start, [..][1] = max end.
 enum TraceId { TR_CLEAR = 0, TR_PYR_LEFT, TR_PAD_LEFT, TR_LK_TEMPORAL, TR_SELECT, TR_RESPONSE, TR_SCAN, TR_SCATTER, TR_MASK,
                TR_GFTT, TR_PYR_RIGHT, TR_PAD_RIGHT, TR_LK_STEREO, TR_UNDISTORT_LEFT, TR_COUNT };
+// Programmatic dependent launch (sm_90+).  A kernel launched with the programmatic-serialization attribute (launch_kernel
+// below, while vf::pdl_hint() is on) may be scheduled while its predecessor in the stream still runs: its CTAs sit at
+// pdl_wait() until that grid has completed and its writes are visible, so the launch latency of every kernel on the frame's
+// dependent chain hides behind the kernel before it.  A kernel lets its successor in as soon as it is itself past its
+// wait (pdl_release).  Both are no-ops for a kernel launched without the attribute.
+bool& pdl_hint();   // host, vf_api.cu: set around the launches whose predecessor in the stream is one of our kernels
 #if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at = {};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = pdl_hint() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 struct TraceScope {
     unsigned long long* slot;
     __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }

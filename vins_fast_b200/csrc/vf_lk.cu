@@ -725,6 +725,7 @@ __device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // f
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
 __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
+    pdl_wait(); pdl_release();
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
@@ -791,6 +792,7 @@ __device__ __forceinline__ float2 velocity(float2 cur, float2 prev, double dt) {
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
 //      RemoveDistortion + ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
 __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
+    pdl_wait(); pdl_release();
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
@@ -925,12 +927,12 @@ cudaError_t lk_prepare() {
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);   // bit 1 of the parity argument
-    lk_temporal_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels, staged), stream>>>(h, parity | (staged ? 2 : 0), cur, prev);
+    launch_kernel(lk_temporal_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, prev);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);
-    lk_stereo_kernel<<<grid, kLkThreads, lk_smem_bytes(h.n_levels, staged), stream>>>(h, parity | (staged ? 2 : 0), cur, dt_host);
+    launch_kernel(lk_stereo_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, dt_host);
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, const double* dt_host, int* n_host, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);

@@ -29,6 +29,7 @@ struct FusedPyrArgs {
 template <int NL, int TW, int TH>
 __global__ void __launch_bounds__(256) pyr_fused_kernel(FusedPyrArgs a) {
     constexpr int NT = 256;
+    pdl_release();                                   // the border kernel behind this one may be scheduled (it waits for this grid)
     TraceScope trace(a.trace, a.trace_id);
     // maximal region extents per relative level k (k = 0 input ... NL top)
     constexpr int RW3 = TW, RH3 = TH;
@@ -194,6 +195,7 @@ __host__ __device__ inline int pad_items(int w, int h, int* strip_words) {
 }
 
 __global__ void __launch_bounds__(256) pad_levels_kernel(PadArgs a) {
+    pdl_wait(); pdl_release();
     TraceScope trace(a.trace, a.trace_id);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
     if (idx >= a.first_item[a.n_levels]) return;
@@ -263,7 +265,7 @@ static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_ima
         a.first_item[l + 1] = a.first_item[l] + items;
     }
     dim3 grid((a.first_item[pv.n_levels] + 255) / 256, n_images);
-    pad_levels_kernel<<<grid, 256, 0, stream>>>(a);
+    launch_kernel(pad_levels_kernel, grid, dim3(256), 0, stream, a);   // behind pyr_fused: programmatic launch when hinted
 }
 
 // All levels 1..n_levels-1 of a pyramid from its level 0, in ceil((n_levels-1)/3) launches, then the REFLECT_101

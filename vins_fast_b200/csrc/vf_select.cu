@@ -156,6 +156,7 @@ __device__ void block_introsort_loop(SortItem* v, int n, int4* queue, int* qn, i
 
 template <int ST_THREADS>
 __global__ void __launch_bounds__(ST_THREADS) select_tracked_kernel(const __grid_constant__ DevBatch b, int parity_arg) {
+    pdl_wait(); pdl_release();
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int warp_cnt[ST_THREADS / 32];
@@ -399,8 +400,8 @@ cudaError_t select_tracked_prepare(int cap) {
 }
 
 void launch_select_tracked(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream) {
-    if (h.cap > ST_LARGE_CAP) select_tracked_kernel<ST_THREADS_LARGE><<<h.n_streams, ST_THREADS_LARGE, select_tracked_smem_bytes(h.cap), stream>>>(h, parity);
-    else select_tracked_kernel<ST_THREADS_SMALL><<<h.n_streams, ST_THREADS_SMALL, select_tracked_smem_bytes(h.cap), stream>>>(h, parity);
+    if (h.cap > ST_LARGE_CAP) launch_kernel(select_tracked_kernel<ST_THREADS_LARGE>, dim3(h.n_streams), dim3(ST_THREADS_LARGE), select_tracked_smem_bytes(h.cap), stream, h, parity);
+    else launch_kernel(select_tracked_kernel<ST_THREADS_SMALL>, dim3(h.n_streams), dim3(ST_THREADS_SMALL), select_tracked_smem_bytes(h.cap), stream, h, parity);
 }
 
 }  // namespace vf
