@@ -376,9 +376,6 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         if (!a || !c) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
     }
     if (b->frame >= 2) {
-        // frame k-2 (same parity) must be complete on the GPU before the chain and the right pyramid overwrite its buffers
-        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 2) & 3], 0));
-        VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_done[(slot + 2) & 3], 0));
         // the left upload + pyramid only reuse what the CHAIN of frame k-2 read (staging image) and what the stereo pass of
         // frame k-3 read (slot k % 3 of the pyramid ring): they may run while frame k-2's stereo pass is still going
         VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_chain[parity], 0));
@@ -403,8 +400,14 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         }
         return cudaSuccess;
     };
+    // the left upload is the first command of the frame to reach the GPU: everything on the critical path waits for it
     { StageTimer t(b, ST_H2D_LEFT, b->side_b); VF_CUDA(b, upload(0, img0, base0, stride0, b->side_b)); }
     VF_CUDA(b, cudaEventRecord(b->ev_img, b->side_b));
+    if (b->frame >= 2) {
+        // frame k-2 (same parity) must be complete on the GPU before the chain and the right pyramid overwrite its buffers
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 2) & 3], 0));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_done[(slot + 2) & 3], 0));
+    }
     // right image on side D; its upload queues behind the left one so that the left image (which the frame's critical path
     // waits for) has the link to itself.  A synchronous frame issues it now (the stereo pass is part of its chain); an
     // overlapped one issues it after the chain -- host order is how soon the chain reaches the GPU.

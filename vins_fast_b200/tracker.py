@@ -185,6 +185,8 @@ class Batch:
         check(self._lib.vf_batch_create(C.byref(self.cfg), n_streams, C.byref(self._h)))
         self._out = np.zeros((n_streams, max(config.max_cnt, 1)), FEATURE_DTYPE)
         self._n = np.zeros(n_streams, np.int32)
+        self._tbuf = np.zeros(n_streams, np.float64)           # per-call scratch of the fast path (addresses taken once)
+        self._tbuf_p, self._out_p, self._n_p = self._tbuf.ctypes.data, self._out.ctypes.data, self._n.ctypes.data
 
     def last_error(self) -> str:
         return (self._lib.vf_batch_last_error(self._h) or b"").decode()
@@ -212,10 +214,10 @@ class Batch:
 
     def track_ptrs(self, times, ptrs0, stride0: int, ptrs1, stride1: int):
         """Host pointer arrays prepared once by the caller (ctypes arrays of c_void_p): the per-frame fast path."""
-        t = self._times(times)
-        st = self._lib.vf_batch_track(self._h, t.ctypes.data, ptrs0, stride0, ptrs1, stride1, self._out.ctypes.data,
-                                      self._n.ctypes.data)
-        check(st, self.last_error)
+        self._tbuf[:] = times
+        st = self._lib.vf_batch_track(self._h, self._tbuf_p, ptrs0, stride0, ptrs1, stride1, self._out_p, self._n_p)
+        if st:
+            check(st, self.last_error)
         return self._n
 
     def enqueue_device(self, times, d_img0: int, d_img1: int, row_stride: int, image_stride: int):
