@@ -375,11 +375,14 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         // the reference asserts both images are non-empty (stereo only): feature_tracker.cpp:30
         if (!a || !c) return fail(b, VF_ERR_INVALID_ARG, "img0/img1 must both be non-null (stereo is mandatory)");
     }
+    // GPU-side waits for the frames whose buffers this one reuses -- skipped when the host has already seen those frames
+    // complete (synchronous use: every wait in front of the left upload is on the critical path)
+    const bool done2 = b->known_done >= b->frame - 2, done3 = b->known_done >= b->frame - 3;
     if (b->frame >= 2) {
         // the left upload + pyramid only reuse what the CHAIN of frame k-2 read (staging image) and what the stereo pass of
         // frame k-3 read (slot k % 3 of the pyramid ring): they may run while frame k-2's stereo pass is still going
-        VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_chain[parity], 0));
-        if (b->frame >= 3) VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_done[(slot + 1) & 3], 0));
+        if (!done2) VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_chain[parity], 0));
+        if (b->frame >= 3 && !done3) VF_CUDA(b, cudaStreamWaitEvent(b->side_b, b->ev_done[(slot + 1) & 3], 0));
     }
     double* pdt = b->pin_dt + (size_t)phase * S;                              // current_time_ - previous_time_ (feature_tracker.cpp:338)
     for (int s = 0; s < S; ++s) { pdt[s] = times[s] - b->prev_times[s]; b->prev_times[s] = times[s]; }
@@ -403,7 +406,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     // the left upload is the first command of the frame to reach the GPU: everything on the critical path waits for it
     { StageTimer t(b, ST_H2D_LEFT, b->side_b); VF_CUDA(b, upload(0, img0, base0, stride0, b->side_b)); }
     VF_CUDA(b, cudaEventRecord(b->ev_img, b->side_b));
-    if (b->frame >= 2) {
+    if (b->frame >= 2 && !done2) {
         // frame k-2 (same parity) must be complete on the GPU before the chain and the right pyramid overwrite its buffers
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 2) & 3], 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_done[(slot + 2) & 3], 0));
@@ -480,12 +483,15 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         { vf_status st = run(SEQ_HEAD_SYNC, b->main); if (st != VF_OK) return st; }
         { vf_status st = issue_right(); if (st != VF_OK) return st; }
         { vf_status st = issue_corner(); if (st != VF_OK) return st; }
-        { vf_status st = issue_right_pyramid(); if (st != VF_OK) return st; }
-        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
+        // ONE join in front of the rest of the frame (every wait the main stream meets there sits on the critical path): the
+        // right pyramid's stream also waits for the corner stage before it records its event
+        { vf_status st = run(SEQ_PYR_RIGHT, b->side_d); if (st != VF_OK) return st; }
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_scat, 0));
+        VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
         // the stereo pass / left undistortion read what the previous frame's wrote (velocity): if that frame was an
-        // overlapped one they ran on other streams
-        if (b->frame >= 1) VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 3) & 3], 0));
+        // overlapped one they ran on other streams -- unless the host has already seen it complete
+        if (b->frame >= 1 && b->known_done < b->frame - 1) VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 3) & 3], 0));
         { vf_status st = run(SEQ_REST_SYNC, b->main); if (st != VF_OK) return st; }
         VF_CUDA(b, cudaGetLastError());
         VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
