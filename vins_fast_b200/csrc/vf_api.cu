@@ -448,27 +448,27 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaEventRecord(b->ev_pyrl, b->side_b));
     }
     // corner stage on side A right behind the left upload (the staging image is all it reads)
-    auto issue_corner = [&]() -> vf_status {
+    auto issue_corner = [&](bool join_left_pyramid) -> vf_status {
         VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_img, 0));
         vf_status st = run(SEQ_CORNER, b->side_a);
         if (st != VF_OK) return st;
+        if (join_left_pyramid) VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->ev_pyrl, 0));   // ev_scat then stands for both
         VF_CUDA(b, cudaEventRecord(b->ev_scat, b->side_a));
         return VF_OK;
     };
     if (overlap) {
-        { vf_status st = issue_corner(); if (st != VF_OK) return st; }
-        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_pyrl, 0));
-        // Asynchronous enqueue: the corner stage ran while the previous frame was on the chain, so the chain joins it up
-        // front (for free) and is four kernels in a row; the stereo pass gets its own stream and overlaps the next chain.
+        // Asynchronous enqueue: the corner stage and the left pyramid ran while the previous frame was on the chain, so the
+        // chain joins them up front (ONE event: what sits between two chains on the main stream is on the critical path of
+        // the frame rate) and is four kernels in a row; the stereo pass gets its own stream and overlaps the next chain.
+        { vf_status st = issue_corner(true); if (st != VF_OK) return st; }
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
         { vf_status st = run(SEQ_CHAIN, b->main); if (st != VF_OK) return st; }
-        VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
         VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
         { vf_status st = issue_right(); if (st != VF_OK) return st; }
         { vf_status st = issue_right_pyramid(); if (st != VF_OK) return st; }
         // stereo pass on side C with the left camera's undistortion + velocity on a branch beside it (side E); both need
-        // current_kps_ / ids_ (ev_sel), the stereo pass the right pyramid, both the frame interval that travels with it
-        VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_sel, 0));
+        // current_kps_ / ids_ (the chain's event), the stereo pass the right pyramid, both the frame interval that travels with it
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_chain[parity], 0));
         VF_CUDA(b, cudaStreamWaitEvent(b->side_c, b->ev_right, 0));
         { vf_status st = run(SEQ_TAIL, b->side_c); if (st != VF_OK) return st; }
         VF_CUDA(b, cudaGetLastError());
@@ -482,7 +482,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
         { vf_status st = run(SEQ_HEAD_SYNC, b->main); if (st != VF_OK) return st; }
         { vf_status st = issue_right(); if (st != VF_OK) return st; }
-        { vf_status st = issue_corner(); if (st != VF_OK) return st; }
+        { vf_status st = issue_corner(false); if (st != VF_OK) return st; }
         // ONE join in front of the rest of the frame (every wait the main stream meets there sits on the critical path): the
         // right pyramid's stream also waits for the corner stage before it records its event
         { vf_status st = run(SEQ_PYR_RIGHT, b->side_d); if (st != VF_OK) return st; }
