@@ -10,7 +10,7 @@ Follows, expression by expression (same association order, no FMA):
                                  CameraFactory.cc:96-136 (model_type, case-insensitive)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference leg may import this.
-Pinned by the known answers of SURVEY.md §8c (see tests/test_oracle_camera.py).
+Pinned by the known answers of SURVEY.md §8c (tests/test_oracle_golden.py::test_lift_projective_known_answers).
 """
 from __future__ import annotations
 
@@ -77,6 +77,35 @@ class Camera:
         """RemoveDistortion (feature_tracker.cpp:310-321): (x/z, y/z) in float64 (caller casts to f32)."""
         x, y, z = self.lift_projective(float(u), float(v))
         return x / z, y / z
+
+    def undistort_many(self, uv):
+        """RemoveDistortion for an [N,2] float32 array -> [N,2] float32.  The same float64 expressions as
+        lift_projective / distortion, evaluated element-wise by numpy in the same association order (no FMA), so every
+        element is bit-identical to the scalar path (tests/test_oracle_golden.py checks it)."""
+        import numpy as np
+        uv = np.asarray(uv, np.float32).reshape(-1, 2)
+        u = uv[:, 0].astype(np.float64)
+        v = uv[:, 1].astype(np.float64)
+        i11, i13, i22, i23 = self.inv_k()
+        mx_d = i11 * u + i13
+        my_d = i22 * v + i23
+        if self.no_distortion:
+            mx_u, my_u = mx_d, my_d
+        else:
+            dx, dy = self.distortion(mx_d, my_d)
+            mx_u, my_u = mx_d - dx, my_d - dy
+            for _ in range(1, 8):
+                dx, dy = self.distortion(mx_u, my_u)
+                mx_u, my_u = mx_d - dx, my_d - dy
+        if self.model == PINHOLE:
+            z = np.ones_like(mx_u)
+        elif self.xi == 1.0:
+            z = (1.0 - mx_u * mx_u - my_u * my_u) / 2.0
+        else:
+            xi = self.xi
+            rho2 = mx_u * mx_u + my_u * my_u
+            z = 1.0 - xi * (rho2 + 1.0) / (xi + np.sqrt(1.0 + (1.0 - xi * xi) * rho2))
+        return np.stack([(mx_u / z).astype(np.float32), (my_u / z).astype(np.float32)], 1)
 
 
 def parse_opencv_yaml_scalars(text: str) -> dict:

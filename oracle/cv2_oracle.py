@@ -29,6 +29,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
+import time
 from typing import Optional
 
 import numpy as np
@@ -67,46 +68,64 @@ def stdsort_perm(track_count) -> np.ndarray:
     return perm
 
 
-def _in_border(pt, rows: int, cols: int) -> bool:
-    x = int(np.rint(np.float32(pt[0])))
-    y = int(np.rint(np.float32(pt[1])))
-    return 1 <= x < cols - 1 and 1 <= y < rows - 1
+def _in_border(pts, rows: int, cols: int) -> np.ndarray:
+    """InBorder (feature_tracker.cpp:20-25) for an [N,2] float32 array: cvRound = round-half-even = np.rint."""
+    p = np.asarray(pts, np.float32).reshape(-1, 2)
+    x = np.rint(p[:, 0]).astype(np.int64)
+    y = np.rint(p[:, 1]).astype(np.int64)
+    return (1 <= x) & (x < cols - 1) & (1 <= y) & (y < rows - 1)
 
 
-def _pt_distance(a, b) -> float:
-    dx = float(np.float32(a[0]) - np.float32(b[0]))  # float subtraction, then widened (feature_tracker.cpp:457-462)
-    dy = float(np.float32(a[1]) - np.float32(b[1]))
-    return float(np.sqrt(dx * dx + dy * dy))
+def _pt_distance(a, b) -> np.ndarray:
+    """PtDistance (feature_tracker.cpp:457-462) row-wise: float subtraction, then widened to double."""
+    a = np.asarray(a, np.float32).reshape(-1, 2)
+    b = np.asarray(b, np.float32).reshape(-1, 2)
+    dx = (a[:, 0] - b[:, 0]).astype(np.float64)
+    dy = (a[:, 1] - b[:, 1]).astype(np.float64)
+    return np.sqrt(dx * dx + dy * dy)
 
 
 class Cv2FeatureTracker:
-    """Line-by-line restatement of estimator::FeatureTracker over cv2."""
+    """Line-by-line restatement of estimator::FeatureTracker over cv2.
+
+    The glue between the OpenCV calls is vectorised with numpy (same float32 / float64 expressions, element-wise, so the
+    results are bit-identical to a per-point loop): the C++ reference has no interpreter between its OpenCV calls, so a
+    CPU baseline timed through this class must not carry one either.  `cv2_seconds` accumulates the time spent INSIDE the
+    OpenCV routines (4x calcOpticalFlowPyrLK, goodFeaturesToTrack, the circles of SetFeatureExtractorMask);
+    `calls` counts the frames, so bench.py can report "cv2 calls only" beside the inclusive figure.
+    """
 
     LK_WIN = (21, 21)
 
     def __init__(self, cam0: Camera, cam1: Camera, max_cnt: int = 150, min_dist: int = 30,
-                 flow_back: int = 1, lk_max_level: int = 3, quality: float = 0.01):
+                 flow_back: int = 1, lk_max_level: int = 3, quality: float = 0.01, keep_debug: bool = True):
         if cv2 is None:
             raise RuntimeError("cv2 is not importable; use oracle.c_oracle instead")
         self.cams = [cam0, cam1]
         self.MAX_CNT, self.MIN_DIST, self.FLOW_BACK = int(max_cnt), int(min_dist), int(flow_back)
         self.lk_max_level, self.quality = int(lk_max_level), float(quality)
+        self.keep_debug = bool(keep_debug)
         self.landmark_id = 0
         self.prev_time = 0.0
         self.cur_time = 0.0
         self.prev_img: Optional[np.ndarray] = None
         self.prev_kps = np.zeros((0, 2), np.float32)
-        self.ids: list[int] = []
-        self.track_count: list[int] = []
-        self.prev_left_un: dict[int, tuple] = {}
-        self.prev_right_un: dict[int, tuple] = {}
+        self.ids = np.zeros(0, np.int64)
+        self.track_count = np.zeros(0, np.int32)
+        self.prev_left_un: dict = {}      # id -> row of prev_left_un_pts (ComputeKpsVelocity's previous map)
+        self.prev_right_un: dict = {}
+        self.prev_left_un_pts = np.zeros((0, 2), np.float32)
+        self.prev_right_un_pts = np.zeros((0, 2), np.float32)
         self.debug: dict = {}
+        self.cv2_seconds = 0.0
+        self.calls = 0
 
     # -- helpers ---------------------------------------------------------------------------------------
     def _lk(self, a, b, pts, max_level, init=None):
         p = np.ascontiguousarray(pts, np.float32).reshape(-1, 1, 2)
         if len(p) == 0:
             return np.zeros((0, 2), np.float32), np.zeros((0,), np.uint8)
+        t0 = time.perf_counter()
         if init is None:
             nxt, st, _ = cv2.calcOpticalFlowPyrLK(a, b, p, None, winSize=self.LK_WIN, maxLevel=max_level)
         else:
@@ -115,123 +134,128 @@ class Cv2FeatureTracker:
                 a, b, p, q, winSize=self.LK_WIN, maxLevel=max_level,
                 criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
                 flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        self.cv2_seconds += time.perf_counter() - t0
         return nxt.reshape(-1, 2), st.reshape(-1)
 
     def _undistort(self, pts, cam: Camera) -> np.ndarray:
-        out = np.zeros((len(pts), 2), np.float32)
-        for i, p in enumerate(pts):
-            x, y = cam.undistort(float(np.float32(p[0])), float(np.float32(p[1])))
-            out[i] = (np.float32(x), np.float32(y))
-        return out
+        return cam.undistort_many(np.asarray(pts, np.float32).reshape(-1, 2))
 
-    def _velocity(self, ids, un, prev_map):
+    def _velocity(self, ids, un, prev_map, prev_pts):
+        """ComputeKpsVelocity (feature_tracker.cpp:323-363): v = (f32 cur - f32 prev) / (double) dt for ids found in the
+        previous map, else 0; the current map keeps the FIRST point seen for an id (std::map::insert)."""
+        ids_l = [int(v) for v in ids]
         cur_map = {}
-        for i, fid in enumerate(ids):
-            cur_map.setdefault(fid, (un[i, 0], un[i, 1]))
-        vel = np.zeros((len(ids), 2), np.float32)
-        if prev_map:
+        for i, fid in enumerate(ids_l):
+            cur_map.setdefault(fid, i)
+        vel = np.zeros((len(ids_l), 2), np.float32)
+        if prev_map and len(ids_l):
             dt = self.cur_time - self.prev_time
-            for i, fid in enumerate(ids):
-                if fid in prev_map:
-                    px, py = prev_map[fid]
-                    vx = float(np.float32(un[i, 0]) - np.float32(px)) / dt
-                    vy = float(np.float32(un[i, 1]) - np.float32(py)) / dt
-                    vel[i] = (np.float32(vx), np.float32(vy))
+            hit = np.fromiter((prev_map.get(f, -1) for f in ids_l), np.int64, len(ids_l))
+            sel = hit >= 0
+            d = (un[sel] - prev_pts[hit[sel]]).astype(np.float64)      # float32 subtraction, then widened
+            with np.errstate(divide="ignore", invalid="ignore"):
+                vel[sel] = (d / dt).astype(np.float32)
         return vel, cur_map
 
     def _set_mask(self, img_shape, cur_kps):
         rows, cols = img_shape
         mask = np.full((rows, cols), 255, np.uint8)
         perm = stdsort_perm(self.track_count)
-        kps, ids, cnt = [], [], []
-        for j in perm:
-            pt = cur_kps[j]
-            cx, cy = int(np.rint(np.float32(pt[0]))), int(np.rint(np.float32(pt[1])))
+        centres = np.rint(np.asarray(cur_kps, np.float32).reshape(-1, 2)).astype(np.int64)
+        kept = []
+        r = self.MIN_DIST
+        t0 = time.perf_counter()
+        for j in perm.tolist():
+            cx, cy = int(centres[j, 0]), int(centres[j, 1])
             if mask[cy, cx] == 255:
-                kps.append(pt)
-                ids.append(self.ids[j])
-                cnt.append(self.track_count[j])
-                cv2.circle(mask, (cx, cy), self.MIN_DIST, 0, -1)
-        self.ids, self.track_count = ids, cnt
-        return np.array(kps, np.float32).reshape(-1, 2), mask, perm
+                kept.append(j)
+                cv2.circle(mask, (cx, cy), r, 0, -1)
+        self.cv2_seconds += time.perf_counter() - t0                       # the loop is the reference's own (its C++ twin is free)
+        kept = np.asarray(kept, np.int64)
+        self.ids, self.track_count = self.ids[kept], self.track_count[kept]
+        return np.asarray(cur_kps, np.float32).reshape(-1, 2)[kept], mask, perm
 
     # -- TrackImage ------------------------------------------------------------------------------------
     def track_image(self, t: float, img0: np.ndarray, img1: np.ndarray) -> dict:
         assert img0 is not None and img1 is not None and img0.size and img1.size
         dbg = self.debug = {}
+        keep_dbg = self.keep_debug
+        self.calls += 1
         self.cur_time = float(t)
         rows, cols = img0.shape
         cur_kps = np.zeros((0, 2), np.float32)
 
         if len(self.prev_kps):
             cur_kps, status = self._lk(self.prev_img, img0, self.prev_kps, self.lk_max_level)
-            status = status.copy()
-            dbg["fwd_pts"], dbg["fwd_status"] = cur_kps.copy(), status.copy()
+            status = status != 0
+            if keep_dbg:
+                dbg["fwd_pts"], dbg["fwd_status"] = cur_kps.copy(), status.astype(np.uint8)
             if self.FLOW_BACK:
                 rev, rstatus = self._lk(img0, self.prev_img, cur_kps, 1, init=self.prev_kps)
-                dbg["rev_pts"], dbg["rev_status"] = rev.copy(), rstatus.copy()
-                for i in range(len(status)):
-                    if not (status[i] and rstatus[i] and _pt_distance(self.prev_kps[i], rev[i]) <= 0.5):
-                        status[i] = 0
-            for i in range(len(cur_kps)):
-                if status[i] and not _in_border(cur_kps[i], rows, cols):
-                    status[i] = 0
-            dbg["temporal_status"] = status.copy()
-            keep = status.astype(bool)
-            cur_kps = cur_kps[keep]
-            self.ids = [v for v, k in zip(self.ids, keep) if k]
-            self.track_count = [v for v, k in zip(self.track_count, keep) if k]
+                if keep_dbg:
+                    dbg["rev_pts"], dbg["rev_status"] = rev.copy(), rstatus.copy()
+                status = status & (rstatus != 0) & (_pt_distance(self.prev_kps, rev) <= 0.5)
+            status = status & _in_border(cur_kps, rows, cols)
+            if keep_dbg:
+                dbg["temporal_status"] = status.astype(np.uint8)
+            cur_kps = cur_kps[status]
+            self.ids = self.ids[status]
+            self.track_count = self.track_count[status]
 
-        self.track_count = [n + 1 for n in self.track_count]
+        self.track_count = self.track_count + 1
 
         cur_kps, mask, perm = self._set_mask((rows, cols), cur_kps)
-        dbg["sort_perm"], dbg["mask"] = perm, mask
-        dbg["n_kept"] = len(cur_kps)
+        if keep_dbg:
+            dbg["sort_perm"], dbg["mask"] = perm, mask
+            dbg["n_kept"] = len(cur_kps)
         n_new = self.MAX_CNT - len(cur_kps)
         new_pts = np.zeros((0, 2), np.float32)
         if n_new > 0:
+            t0 = time.perf_counter()
             r = cv2.goodFeaturesToTrack(img0, n_new, self.quality, self.MIN_DIST, mask=mask)
+            self.cv2_seconds += time.perf_counter() - t0
             if r is not None:
                 new_pts = r.reshape(-1, 2).astype(np.float32)
-        dbg["new_pts"] = new_pts.copy()
-        for p in new_pts:
-            self.track_count.append(1)
-            self.ids.append(self.landmark_id)
-            self.landmark_id = (self.landmark_id + 1) & 0xFFFFFFFF
+        if keep_dbg:
+            dbg["new_pts"] = new_pts.copy()
+        k = len(new_pts)
+        if k:
+            self.track_count = np.concatenate([self.track_count, np.ones(k, np.int32)])
+            self.ids = np.concatenate([self.ids, (self.landmark_id + np.arange(k, dtype=np.int64)) & 0xFFFFFFFF])
+            self.landmark_id = (self.landmark_id + k) & 0xFFFFFFFF
         cur_kps = np.concatenate([cur_kps, new_pts], axis=0).astype(np.float32)
 
         cur_un = self._undistort(cur_kps, self.cams[0])
-        vel, cur_left_map = self._velocity(self.ids, cur_un, self.prev_left_un)
+        vel, cur_left_map = self._velocity(self.ids, cur_un, self.prev_left_un, self.prev_left_un_pts)
 
         # stereo
         right_kps, status = self._lk(img0, img1, cur_kps, self.lk_max_level)
-        status = status.copy()
-        dbg["lr_pts"], dbg["lr_status"] = right_kps.copy(), status.copy()
+        status = status != 0
+        if keep_dbg:
+            dbg["lr_pts"], dbg["lr_status"] = right_kps.copy(), status.astype(np.uint8)
         if self.FLOW_BACK and len(cur_kps):
             rev_left, rstatus = self._lk(img1, img0, right_kps, self.lk_max_level)
-            dbg["rl_pts"], dbg["rl_status"] = rev_left.copy(), rstatus.copy()
-            for i in range(len(status)):
-                if not (status[i] and rstatus[i] and _in_border(right_kps[i], rows, cols)
-                        and _pt_distance(cur_kps[i], rev_left[i]) <= 0.5):
-                    status[i] = 0
-        dbg["stereo_status"] = status.copy()
-        keep = status.astype(bool)
-        ids_right = [v for v, k in zip(self.ids, keep) if k]
-        right_kps = right_kps[keep]
+            if keep_dbg:
+                dbg["rl_pts"], dbg["rl_status"] = rev_left.copy(), rstatus.copy()
+            status = status & (rstatus != 0) & _in_border(right_kps, rows, cols) & (_pt_distance(cur_kps, rev_left) <= 0.5)
+        if keep_dbg:
+            dbg["stereo_status"] = status.astype(np.uint8)
+        ids_right = self.ids[status]
+        right_kps = right_kps[status]
         right_un = self._undistort(right_kps, self.cams[1])
-        rvel, cur_right_map = self._velocity(ids_right, right_un, self.prev_right_un)
+        rvel, cur_right_map = self._velocity(ids_right, right_un, self.prev_right_un, self.prev_right_un_pts)
 
         # roll state
         self.prev_img = img0
         self.prev_kps = cur_kps
-        self.prev_left_un = cur_left_map
-        self.prev_right_un = cur_right_map
+        self.prev_left_un, self.prev_left_un_pts = cur_left_map, cur_un
+        self.prev_right_un, self.prev_right_un_pts = cur_right_map, right_un
         self.prev_time = self.cur_time
 
         frame = {
-            "ids": np.array(self.ids, np.int32), "track_cnt": np.array(self.track_count, np.int32),
+            "ids": self.ids.astype(np.int32), "track_cnt": self.track_count.astype(np.int32),
             "uv": cur_kps.copy(), "un": cur_un, "vel": vel,
-            "ids_right": np.array(ids_right, np.int32), "uv_right": right_kps.copy(),
+            "ids_right": ids_right.astype(np.int32), "uv_right": right_kps.copy(),
             "un_right": right_un, "vel_right": rvel,
         }
         return frame

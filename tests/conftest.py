@@ -135,3 +135,28 @@ def assert_frames_equal(a: dict, b: dict, ctx: str = ""):
                 f"{ctx}: {key} differs, max abs diff {np.abs(x.astype(np.float64) - y).max()}"
         else:
             assert np.array_equal(x, y), f"{ctx}: {key} differs"
+
+
+FRAME_KEYS = ("ids", "track_cnt", "uv", "un", "vel", "ids_right", "uv_right", "un_right", "vel_right")
+
+
+def frame_digest(frame: dict) -> bytes:
+    """SHA-256 over the nine arrays of one TrackImage result (int32 / float32 bytes, fixed key order): the compact form
+    in which the long cv2 sequences are kept under tests/golden/ (a checksum per frame instead of the arrays)."""
+    import hashlib
+    h = hashlib.sha256()
+    for key in FRAME_KEYS:
+        a = np.asarray(frame[key])
+        a = a.astype(np.float32) if a.dtype.kind == "f" else a.astype(np.int32)
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.digest()
+
+
+def first_divergence(frames_a, frames_b):
+    """(frame index, key) of the first difference between two lists of tracker outputs, or None."""
+    for k, (a, b) in enumerate(zip(frames_a, frames_b)):
+        for key in FRAME_KEYS:
+            x, y = np.asarray(a[key]), np.asarray(b[key])
+            if x.shape != y.shape or x.tobytes() != y.astype(x.dtype).tobytes():
+                return k, key
+    return None

@@ -209,3 +209,43 @@ def test_oracle_vs_live_cv2_track_image(oracle):
         fa, fb = a.track_image(t, l, r), b.track_image(t, l, r)
         for key in fa:
             assert np.asarray(fa[key]).tobytes() == np.asarray(fb[key]).astype(np.asarray(fa[key]).dtype).tobytes(), f"frame {k} {key}"
+
+
+# ---- long sequences (>= 100 frames): one digest per frame, generated by tests/golden/make_golden_long.py with cv2 ------
+LONG = [("euroc_mei_120", (EUROC_CAM0, EUROC_CAM1)), ("720p_pinhole_100", (pinhole_for(1280, 720), pinhole_for(1280, 720)))]
+
+
+@pytest.mark.parametrize("name,cams", LONG)
+def test_long_sequences_match_the_cv2_digests(oracle, name, cams):
+    """The plain-C oracle against the cv2 restatement of the reference over 120 / 100 consecutive frames (track counts up
+    to the sequence length, hundreds of ids issued and dropped): every frame's digest equal."""
+    from conftest import frame_digest
+    from vins_fast_b200.synth import StereoSequence
+    g = np.load(os.path.join(GOLD, f"digest_{name}_cv2_4_13.npz"))
+    w, h, max_cnt, min_dist, flow_back, level, n_frames, seed = (int(v) for v in g["params"])
+    seq = StereoSequence(seed, w, h)
+    tr = oracle.CFeatureTracker(cams[0], cams[1], w, h, max_cnt, min_dist, flow_back, level)
+    for k in range(n_frames):
+        f = tr.track_image(*seq.frame(k))
+        assert (len(f["ids"]), len(f["ids_right"])) == tuple(int(v) for v in g["counts"][k, :2]), f"first divergence at frame {k} (counts)"
+        assert frame_digest(f) == g["digest"][k].tobytes(), f"first divergence at frame {k}"
+    assert int(g["counts"][:, 2].max()) >= n_frames // 2 and int(g["counts"][-1, 3]) > 2 * max_cnt
+
+
+def test_vectorised_glue_of_the_cv2_oracle_is_bit_identical():
+    """oracle/cv2_oracle.py vectorises the reference's per-point glue with numpy; the per-point forms must give the same bits."""
+    rng = np.random.default_rng(5)
+    for cam in (EUROC_CAM0, EUROC_CAM1, D435_CAM0, pinhole_for(1280, 720)):
+        uv = (rng.uniform(-20, 780, (300, 2))).astype(np.float32)
+        many = cam.undistort_many(uv)
+        one = np.array([[np.float32(v) for v in cam.undistort(float(p[0]), float(p[1]))] for p in uv], np.float32)
+        assert many.tobytes() == one.tobytes()
+    from oracle.cv2_oracle import _in_border, _pt_distance
+    p = (rng.uniform(-3, 760, (500, 2))).astype(np.float32)
+    p[:8] = [[0.5, 0.5], [1.5, 2.5], [750.5, 478.5], [749.5, 477.5], [1.0, 1.0], [750.0, 478.0], [751.0, 479.0], [0.4999, 1.5]]
+    q = (p + rng.uniform(-0.6, 0.6, p.shape)).astype(np.float32)
+    for i in range(len(p)):
+        x, y = int(np.rint(p[i, 0])), int(np.rint(p[i, 1]))
+        assert bool(_in_border(p, 480, 752)[i]) == (1 <= x < 751 and 1 <= y < 479)
+        dx, dy = float(p[i, 0] - q[i, 0]), float(p[i, 1] - q[i, 1])
+        assert float(_pt_distance(p, q)[i]) == float(np.sqrt(dx * dx + dy * dy))
