@@ -55,12 +55,19 @@ typedef struct {
     int32_t min_dist;             /* MIN_DIST                                                        */
     int32_t flow_back;            /* OPTICAL_FLOW_BACK                                               */
     int32_t lk_max_level;         /* default 3   (maxLevel of the forward and stereo LK calls)       */
-    int32_t lk_win;               /* 21 only (window is compiled into the kernel)                    */
+    int32_t lk_win;               /* 21 only: the reference passes the literal cv::Size(21, 21) at all four call sites
+                                   * (feature_tracker.cpp:42,51,119,127) and has no key for it.  The LK kernels reproduce
+                                   * OpenCV's float summation ORDER for that width (two 8-wide SIMD groups + a 5-column scalar
+                                   * tail per row, lkpyramid.cpp), which is what makes positions bit-identical; another width
+                                   * is another accumulation order and another tile plan, so it is a compile-time constant
+                                   * (csrc/vf_common.cuh: kWin) and any other value returns VF_ERR_INVALID_ARG             */
     double quality_level;         /* default 0.01                                                    */
     vf_camera cam[2];             /* [0] left, [1] right  (ReadIntrinsicParameter order, :301-308)   */
     int32_t device;               /* CUDA device ordinal, -1 = current device                        */
     int32_t use_cuda_graph;       /* 1 = replay the frame as a captured CUDA graph (default), 0 = plain launches */
-    void* cuda_stream;            /* optional cudaStream_t the frame work is ordered on (0 = library-owned stream) */
+    void* cuda_stream;            /* optional cudaStream_t the frame-to-frame chain runs on (0 = library-owned stream).  With a
+                                   * caller-supplied stream, device-resident input images are read only after everything
+                                   * already queued on that stream (see vf_batch_set_input_event)                          */
 } vf_config;
 
 /* One tracked feature = one entry of the featureFrame map (feature_tracker.cpp:173-213):
@@ -102,7 +109,9 @@ vf_status vf_tracker_reset(vf_tracker* t);                                    /*
  * inside the call and keeps nothing of the caller's memory. */
 vf_status vf_tracker_track(vf_tracker* t, double time_s, const uint8_t* img0, size_t stride0,
                            const uint8_t* img1, size_t stride1, vf_feature* out, int32_t* n_out);
-/* Same, images already resident on the device (device pointers, same layout). */
+/* Same, images already resident on the device (device pointers, same layout).  Device images are copied by the
+ * library's own streams: they must be COMPLETE when the call is made -- or be ordered by vf_batch_set_input_event, or be
+ * produced on the caller-supplied vf_config.cuda_stream -- and must stay unmodified until the frame has been fetched. */
 vf_status vf_tracker_track_device(vf_tracker* t, double time_s, const uint8_t* d_img0, size_t stride0,
                                   const uint8_t* d_img1, size_t stride1, vf_feature* out, int32_t* n_out);
 const char* vf_last_error(const vf_tracker* t);
@@ -124,6 +133,9 @@ vf_status vf_batch_track_device(vf_batch* b, const double* times, const uint8_t*
 vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
                                   size_t row_stride, size_t image_stride_bytes);
 vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out);
+/* Orders the device images of the NEXT vf_batch_enqueue_device / vf_*_track_device call behind `cuda_event` (a cudaEvent_t the
+ * caller recorded after the work that produces them, on any stream).  One-shot; the event is not owned by the library. */
+vf_status vf_batch_set_input_event(vf_batch* b, void* cuda_event);
 /* Pipelined front-end (Estimator::FrontendTracker pushes results into feature_buf_ and the back-end consumes them later,
  * estimator.cpp:143-158): vf_batch_enqueue starts frame k from HOST images and returns at once (the host runs at most
  * four frames ahead of the GPU); vf_batch_fetch_lagged(b, lag, ...) then returns frame k-lag, lag = 0 (= vf_batch_fetch),

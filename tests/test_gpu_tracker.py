@@ -325,3 +325,46 @@ def test_cpp_frontend_pipeline_feeds_feature_buf(lib, oracle, euroc_frames, tmp_
         res = subprocess.run([exe, "pipe", str(tmp_path / "cam0_mei.yaml"), str(tmp_path / "cam1_mei.yaml"),
                               str(tmp_path / "frames.bin"), "752", "480", str(n), depth], capture_output=True, text=True, timeout=300)
         assert res.returncode == 0 and "pipe ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_device_input_ordering_event_and_caller_stream(lib, oracle, euroc_frames):
+    """Device-resident images produced by work still in flight when the frame is enqueued: ordered either by an
+    event handed in with vf_batch_set_input_event, or by producing them on the caller-supplied vf_config.cuda_stream."""
+    torch = pytest.importorskip("torch")
+    import vins_fast_b200 as v
+    frames = euroc_frames[:5]
+    want = []
+    ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
+    for t, l, r in frames:
+        want.append(ref.track_image(t, l, r))
+    pin = [(torch.from_numpy(l).pin_memory(), torch.from_numpy(r).pin_memory()) for _, l, r in frames]
+    big = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")          # a slow producer in front of the images
+
+    # (a) producer on an unrelated stream + event
+    prod = torch.cuda.Stream()
+    batch = v.Batch(v.make_config(752, 480, 150, 30, 1, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__), 1)
+    for k, (t, _, _) in enumerate(frames):
+        dl, dr = torch.zeros(480, 752, dtype=torch.uint8, device="cuda"), torch.zeros(480, 752, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(prod):
+            big.add_(1)                                                     # ~100 us of work the copies queue behind
+            dl.copy_(pin[k][0], non_blocking=True); dr.copy_(pin[k][1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(prod)
+        v.load().vf_batch_set_input_event(batch._h, ev.cuda_event)
+        res = batch.track_device(t, dl.data_ptr(), dr.data_ptr(), 752, 752 * 480)
+        assert_frames_equal(oracle.records_to_frame(res[0]), want[k], f"event-ordered frame {k}")
+    batch.close()
+
+    # (b) the frame work runs on the caller's stream, which also produces the images
+    mine = torch.cuda.Stream()
+    batch = v.Batch(v.make_config(752, 480, 150, 30, 1, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__, cuda_stream=mine.cuda_stream), 1)
+    for k, (t, _, _) in enumerate(frames):
+        dl, dr = torch.zeros(480, 752, dtype=torch.uint8, device="cuda"), torch.zeros(480, 752, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        with torch.cuda.stream(mine):
+            big.add_(1)
+            dl.copy_(pin[k][0], non_blocking=True); dr.copy_(pin[k][1], non_blocking=True)
+        res = batch.track_device(t, dl.data_ptr(), dr.data_ptr(), 752, 752 * 480)
+        assert_frames_equal(oracle.records_to_frame(res[0]), want[k], f"caller-stream frame {k}")
+    batch.close()

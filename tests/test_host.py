@@ -150,6 +150,13 @@ def test_estimator_yaml(lib, tmp_path):
     with pytest.raises(v.VfError) as e:
         v.load_config_yaml(str(missing))
     assert e.value.status == _lib.VF_ERR_PARSE
+    # a calibration file the YAML lists but nobody can open is an error, as in CameraFactory::generateCameraFromYamlFile
+    # (the shipped configs carry absolute /home/weihao/... paths): never a silent default pinhole
+    (tmp_path / "lost").mkdir()
+    lost = write_estimator_yaml(tmp_path / "lost" / "est.yaml", 150, 30, 1)
+    with pytest.raises(v.VfError) as e:
+        v.load_config_yaml(str(lost))
+    assert e.value.status == _lib.VF_ERR_IO and "cam0_mei.yaml" in e.value.message
 
 
 # ---- libstdc++ introsort replay (host build of the device code) ---------------------------------------------------

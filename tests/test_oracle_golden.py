@@ -80,6 +80,22 @@ def test_mask_disc_equals_cv_circle(oracle, stages):
     assert np.array_equal(mask, stages["mask"])
 
 
+@pytest.mark.skipif(os.environ.get("VF_SKIP_CV2") is not None, reason="cv2 disabled")
+def test_mask_disc_equals_cv_circle_over_the_accepted_min_dist_range(oracle):
+    """min_dist is accepted up to 1024 (vf_api.cu validate_config); SetFeatureExtractorMask's cv::circle(FILLED) must be the
+    Euclidean disc dx^2 + dy^2 <= r^2 over that whole range, clipped centres included (live cv2)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    w, h = 1300, 900
+    for r in (0, 1, 2, 15, 30, 119, 120, 121, 200, 255, 256, 257, 400, 511, 512, 640, 1000, 1023, 1024):
+        for cx, cy in ((w // 2, h // 2), (0, 0), (w - 1, h - 1), (3, h - 2), (int(rng.integers(0, w)), int(rng.integers(0, h)))):
+            a = np.full((h, w), 255, np.uint8)
+            b = a.copy()
+            cv2.circle(a, (cx, cy), r, 0, -1)
+            oracle.mask_disc(b, cx, cy, r)
+            assert np.array_equal(a, b), f"r={r} centre=({cx},{cy})"
+
+
 @pytest.mark.parametrize("pair", ["temporal", "stereo"])
 def test_lk_golden(oracle, stages, crops, pair):
     a, b, c = crops

@@ -49,7 +49,7 @@ EXPORTS = [
     "vf_tracker_create", "vf_tracker_destroy", "vf_tracker_reset", "vf_tracker_track", "vf_tracker_track_device",
     "vf_last_error",
     "vf_batch_create", "vf_batch_destroy", "vf_batch_reset", "vf_batch_size", "vf_batch_track", "vf_batch_track_device",
-    "vf_batch_enqueue_device", "vf_batch_fetch", "vf_batch_enqueue", "vf_batch_fetch_lagged", "vf_batch_last_error", "vf_batch_cuda_stream",
+    "vf_batch_enqueue_device", "vf_batch_set_input_event", "vf_batch_fetch", "vf_batch_enqueue", "vf_batch_fetch_lagged", "vf_batch_last_error", "vf_batch_cuda_stream",
     "vf_batch_launches_per_frame", "vf_batch_host_times", "vf_batch_stream",
     "vf_batch_set_profiling", "vf_batch_stage_count", "vf_batch_stage_name", "vf_batch_stage_times", "vf_batch_trace_get",
     "vf_tracker_debug_get",
@@ -99,6 +99,7 @@ def load() -> C.CDLL:
         "vf_batch_track_device": (I32, [P, P, P, P, SZ, SZ, P, P]),
         "vf_batch_enqueue_device": (I32, [P, P, P, P, SZ, SZ]),
         "vf_batch_fetch": (I32, [P, P, P]),
+        "vf_batch_set_input_event": (I32, [P, P]),
         "vf_batch_enqueue": (I32, [P, P, P, SZ, P, SZ]),
         "vf_batch_fetch_lagged": (I32, [P, I32, P, P]),
         "vf_batch_last_error": (C.c_char_p, [P]),

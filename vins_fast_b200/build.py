@@ -6,6 +6,7 @@ The .so is git-ignored but travels to the GPU box with the repository snapshot.
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import subprocess
 import sys
@@ -24,18 +25,32 @@ NVCC_FLAGS = [
 ]
 
 
+STAMP = LIB + ".hash"      # sha256 of every source + the flags the library was built from (travels with the .so)
+
+
 def _deps():
-    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    out = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
     out.append(os.path.join(ROOT, "include", "vins_fast_b200.h"))
-    out.append(os.path.abspath(__file__))
     return out
 
 
+def source_hash() -> str:
+    """Identity of a build: the bytes of every file under csrc/, the C header and the nvcc flags.  File times mean nothing on
+    a fresh snapshot of the repository, so the decision to rebuild is taken on this hash, stored beside the library."""
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -52,6 +67,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libvinsfast_b200.so")
     if verbose:
         print(res.stdout + res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

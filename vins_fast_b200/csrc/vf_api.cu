@@ -22,6 +22,7 @@
 // undistorted points, landmark id, time) lives in HBM, double-buffered by parity; nothing but the two images
 // goes up and nothing but the <= max_cnt records comes down.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges around the host-side stages of a frame (free when no tool is attached)
 
 #include <chrono>
 #include <cstdio>
@@ -55,6 +56,8 @@ struct vf_batch {
     cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr, side_d = nullptr, side_e = nullptr;
     bool own_main = false, serialized = false;
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
+    cudaEvent_t ev_input = nullptr;        // device-input ordering: recorded on the caller's stream / handed in by the caller
+    cudaEvent_t ev_user_input = nullptr;   // vf_batch_set_input_event: the next frame's uploads wait for it (not owned)
     cudaEvent_t ev_fork = nullptr, ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
                 ev_sel = nullptr, ev_un = nullptr, ev_pyrl = nullptr, ev_scat = nullptr,
                 ev_chain[2] = {nullptr, nullptr};
@@ -100,6 +103,11 @@ struct StageTimer {   // records begin/end events on `st` around a scope when pr
 };
 
 namespace {
+
+struct NvtxRange {   // RAII range in the "vins_fast_b200" view of nsys / ncu timelines
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -219,6 +227,7 @@ void destroy_batch(vf_batch* b) {
     for (int p = 0; p < 4; ++p) if (b->ev_done[p]) cudaEventDestroy(b->ev_done[p]);
     if (b->pin_dt) cudaFreeHost(b->pin_dt);
     if (b->ev_right) cudaEventDestroy(b->ev_right);
+    if (b->ev_input) cudaEventDestroy(b->ev_input);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->ev_img) cudaEventDestroy(b->ev_img);
     if (b->ev_sel) cudaEventDestroy(b->ev_sel);
@@ -354,6 +363,7 @@ vf_status build_graph(vf_batch* b, int phase, int which) {
 vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* img0, const uint8_t* const* img1,
                         const uint8_t* base0, const uint8_t* base1, size_t image_stride, size_t stride0, size_t stride1,
                         cudaMemcpyKind kind, bool overlap) {
+    NvtxRange nvtx_frame(overlap ? "vf.enqueue_frame(overlapped)" : "vf.enqueue_frame(synchronous)");
     DeviceGuard g(b->device);
     if (!g.ok) return fail(b, VF_ERR_CUDA, "cudaSetDevice failed");
     const DevBatch& h = b->h;
@@ -393,7 +403,30 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     // the images go up as ONE linear copy each into unpadded staging buffers (a pitched 2-D copy of 480 short rows is
     // several times slower over PCIe); the pyramid launches read them there and move level 0 into its padded home
     const size_t SP = (size_t)b->stage_pitch, simg = SP * H;
+    // Device images are read by copies on the library's internal streams.  They are ordered behind (a) the event the caller
+    // handed in with vf_batch_set_input_event, if any, and (b) when the frame work runs on a caller-supplied stream
+    // (vf_config.cuda_stream), everything already queued on that stream -- a debayer / rectify kernel there that produces
+    // the images cannot race with the copy.  With a library-owned stream and no event the images must be complete when the
+    // call is made (include/vins_fast_b200.h); waiting for the own chain stream here would serialise the upload of frame
+    // k+1 behind the chain of frame k.
+    if (kind == cudaMemcpyDeviceToDevice) {
+        cudaEvent_t in = b->ev_user_input;
+        b->ev_user_input = nullptr;
+        if (!in && !b->own_main) { VF_CUDA(b, cudaEventRecord(b->ev_input, b->main)); in = b->ev_input; }
+        if (in) {
+            VF_CUDA(b, cudaStreamWaitEvent(b->side_b, in, 0));
+            VF_CUDA(b, cudaStreamWaitEvent(b->side_d, in, 0));
+        }
+    }
     auto upload = [&](int cam, const uint8_t* const* imgs, const uint8_t* base, size_t stride, cudaStream_t st) -> cudaError_t {
+        NvtxRange r(cam ? "vf.upload_right" : "vf.upload_left");
+        // images back to back at a fixed distance: ONE copy command for the whole batch (a copy command costs the host ~4 us;
+        // per-image commands would dominate a frame of a large batch)
+        if (base && S > 1 && stride == SP) {
+            uint8_t* dst = b->stage[cam][parity];
+            if (image_stride == simg) return cudaMemcpyAsync(dst, base, simg * (size_t)S, kind, st);
+            if (image_stride > simg) return cudaMemcpy2DAsync(dst, simg, base, image_stride, simg, (size_t)S, kind, st);
+        }
         for (int s = 0; s < S; ++s) {
             const uint8_t* a = base ? base + (size_t)s * image_stride : imgs[s];
             uint8_t* dst = b->stage[cam][parity] + (size_t)s * simg;
@@ -422,7 +455,10 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         return VF_OK;
     };
     const bool use_graph = b->cfg.use_cuda_graph && !b->profiling;
+    static const char* const kSeqNames[SEQ_COUNT] = {"vf.corner_stage", "vf.chain", "vf.rest_sync", "vf.head_sync", "vf.pyramid_left",
+                                                     "vf.pyramid_right", "vf.stereo_tail"};
     auto run = [&](int which, cudaStream_t st) -> vf_status {   // one of the captured kernel sequences, as a graph or directly
+        NvtxRange r(kSeqNames[which]);
         if (use_graph) {
             if (!b->graph[which][phase]) {
                 vf_status r = build_graph(b, phase, which);
@@ -509,6 +545,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
 }
 
 vf_status fetch_frame(vf_batch* b, vf_feature* out, int32_t* n_out, int lag = 0) {
+    NvtxRange nvtx_fetch("vf.fetch_frame");
     if (lag < 0 || lag > 2) return fail(b, VF_ERR_INVALID_ARG, "lag must be 0 (last enqueued frame), 1 or 2 (the ones before)");
     if (b->last_parity < 0 || b->frame <= lag) return fail(b, VF_ERR_STATE, "that frame has not been enqueued");
     DeviceGuard g(b->device);
@@ -634,6 +671,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
         TRYC(cudaStreamCreateWithPriority(&b->side_c, cudaStreamNonBlocking, prio_mid));
     }
     TRYC(cudaEventCreateWithFlags(&b->ev_right, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_input, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_img, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_sel, cudaEventDisableTiming));
@@ -782,6 +820,12 @@ static vf_status enqueue_device(vf_batch* b, const double* times, const uint8_t*
 vf_status vf_batch_enqueue_device(vf_batch* b, const double* times, const uint8_t* d_img0, const uint8_t* d_img1,
                                   size_t row_stride, size_t image_stride_bytes) {
     return enqueue_device(b, times, d_img0, d_img1, row_stride, image_stride_bytes, true);
+}
+
+vf_status vf_batch_set_input_event(vf_batch* b, void* cuda_event) {
+    if (!b) return fail(nullptr, VF_ERR_INVALID_ARG, "batch is null");
+    b->ev_user_input = (cudaEvent_t)cuda_event;
+    return VF_OK;
 }
 
 vf_status vf_batch_fetch(vf_batch* b, vf_feature* out, int32_t* n_out) {

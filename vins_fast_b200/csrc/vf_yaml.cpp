@@ -150,7 +150,7 @@ extern "C" vf_status vf_config_load_yaml(const char* estimator_yaml, vf_config* 
     get_int(m, "lk_max_level", cfg->lk_max_level);       // optional keys; defaults = the reference's literals
     get_int(m, "lk_win", cfg->lk_win);
     get_double(m, "quality_level", cfg->quality_level);
-    // cam0_calib / cam1_calib (estimator.cpp:95-99): loaded when the files exist; otherwise the caller fills cfg->cam
+    // cam0_calib / cam1_calib (estimator.cpp:95-99): a listed file must be readable; a YAML without the keys leaves cfg->cam to the caller
     for (int k = 0; k < 2; ++k) {
         const std::string key = k == 0 ? "cam0_calib" : "cam1_calib";
         if (!m.count(key)) continue;
@@ -161,10 +161,15 @@ extern "C" vf_status vf_config_load_yaml(const char* estimator_yaml, vf_config* 
             p = dir + p.substr(p.find_last_of('/') + 1);
             probe.open(p.c_str());
         }
-        if (probe.is_open()) {
-            vf_status st = vf_camera_load_yaml(p.c_str(), &cfg->cam[k]);
-            if (st != VF_OK) return st;
+        // the reference aborts in CameraFactory::generateCameraFromYamlFile when a listed file cannot be read
+        // (CameraFactory.cc:96-110); keeping the default pinhole instead would silently corrupt the undistorted points
+        if (!probe.is_open()) {
+            g_yaml_error = "calibration file '" + m[key] + "' (key " + key + " of " + estimator_yaml + ") cannot be opened, neither at that "
+                           "path nor as " + p;
+            return VF_ERR_IO;
         }
+        vf_status st = vf_camera_load_yaml(p.c_str(), &cfg->cam[k]);
+        if (st != VF_OK) return st;
     }
     return VF_OK;
 }
