@@ -17,7 +17,8 @@
 //   * a failure inside the library is fatal like the reference's assert / LOG(FATAL) (VF_FATAL: abort, or an exception
 //     under VINS_FAST_B200_THROW); there is no CPU fallback;
 //   * the image window of DrawTracker (cv::imshow when frontend_wait_key == 0) is not reproduced; the track image is
-//     rendered on the host into draw_track_img_result_ only when show_track != 0.
+//     rendered on the host into draw_track_img_result_ only when show_track != 0 (draw.hpp: pixel-identical to the
+//     reference's cv::circle / cv::arrowedLine calls).
 #pragma once
 
 #include <algorithm>
@@ -31,6 +32,7 @@
 
 #include "../vins_fast_b200.h"
 #include "compat.hpp"
+#include "draw.hpp"
 #ifndef VF_USE_EXTERNAL_SETTING   // define it when the including project brings its own common::Setting (vins/common/parameter.hpp)
 #include "parameter.hpp"
 #endif
@@ -200,28 +202,26 @@ public:
         v.resize(j);
     }
 
-    /// Draw tracker result (feature_tracker.cpp:267-299): left|right side by side as RGB, a ring per left feature coloured
-    /// by track age (blue = new, red = >= 20 frames), a green ring per right feature, a green segment to the previous
-    /// position.  Host-side visualisation, only run when show_track != 0; not pixel-identical to cv::circle/arrowedLine.
+    /// Draw tracker result (feature_tracker.cpp:267-299): left|right side by side as RGB, a circle per left feature coloured
+    /// by track age (blue = new, red = >= 20 frames), a green circle per right feature, a green arrow to the previous
+    /// position.  Host-side, only run when show_track != 0; the rasterisation is pixel-identical to the reference's
+    /// cv::circle / cv::arrowedLine calls (draw.hpp; checked against cv2 by the tests).
     void DrawTracker() {
-        const int W = current_img_.cols, H = current_img_.rows;
+        const int W = current_img_.cols, H = current_img_.rows, n = (int)current_kps_.size();
         cv::Mat out(H, 2 * W, CV_8UC3);
-        for (int y = 0; y < H; ++y) {
-            unsigned char* d = out.ptr<unsigned char>(y);
-            const unsigned char* a = current_img_.ptr<unsigned char>(y);
-            const unsigned char* b = current_right_img_.ptr<unsigned char>(y);
-            for (int x = 0; x < W; ++x) { d[3 * x] = d[3 * x + 1] = d[3 * x + 2] = a[x]; }
-            for (int x = 0; x < W; ++x) { d[3 * (W + x)] = d[3 * (W + x) + 1] = d[3 * (W + x) + 2] = b[x]; }
-        }
-        for (size_t j = 0; j < current_kps_.size(); j++) {
-            const double len = std::min(1.0, 1.0 * track_count_[j] / 20);
-            Ring(out, current_kps_[j].x, current_kps_[j].y, (unsigned char)(255 * (1 - len)), 0, (unsigned char)(255 * len));
-        }
-        for (const auto& kp : current_right_img_kps_) Ring(out, kp.x + (float)W, kp.y, 0, 255, 0);
-        for (size_t i = 0; i < current_kps_.size(); i++) {
+        std::vector<float> prev_xy(2 * (size_t)n + 2, 0.f);
+        std::vector<unsigned char> has_prev((size_t)n + 1, 0);
+        for (int i = 0; i < n; ++i) {
             auto iter = previous_left_ids_kps_map_.find(ids_[i]);
-            if (iter != previous_left_ids_kps_map_.end()) Segment(out, current_kps_[i], iter->second, 0, 255, 0);
+            if (iter == previous_left_ids_kps_map_.end()) continue;
+            has_prev[i] = 1; prev_xy[2 * i] = iter->second.x; prev_xy[2 * i + 1] = iter->second.y;
         }
+        static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "Point2f must be two packed floats");
+        const vf_draw::Canvas canvas = {out.data, 2 * W, H, (size_t)out.step};
+        vf_draw::DrawTrackImage(current_img_.data, current_img_.step, current_right_img_.data, current_right_img_.step, W, H,
+                                n ? &current_kps_[0].x : nullptr, n ? track_count_.data() : nullptr, n,
+                                current_right_img_kps_.empty() ? nullptr : &current_right_img_kps_[0].x, (int)current_right_img_kps_.size(),
+                                prev_xy.data(), has_prev.data(), canvas);
         draw_track_img_result_ = out;
     }
 
@@ -256,23 +256,6 @@ private:
         cfg_.cam[0] = cameras_[0]; cfg_.cam[1] = cameras_[1];
         if (vf_tracker_create(&cfg_, &handle_) != VF_OK) VF_FATAL(std::string("vf_tracker_create: ") + vf_last_global_error());
         records_.resize((size_t)std::max(1, cfg_.max_cnt));
-    }
-    static void Put(cv::Mat& m, int x, int y, unsigned char r, unsigned char g, unsigned char b) {
-        if (x < 0 || y < 0 || x >= m.cols || y >= m.rows) return;
-        unsigned char* p = m.ptr<unsigned char>(y) + 3 * x;
-        p[0] = r; p[1] = g; p[2] = b;
-    }
-    static void Ring(cv::Mat& m, float fx, float fy, unsigned char r, unsigned char g, unsigned char b) {
-        const int cx = cvRound(fx), cy = cvRound(fy);
-        for (int dy = -3; dy <= 3; ++dy)
-            for (int dx = -3; dx <= 3; ++dx) {
-                const int d2 = dx * dx + dy * dy;
-                if (d2 >= 2 && d2 <= 10) Put(m, cx + dx, cy + dy, r, g, b);
-            }
-    }
-    static void Segment(cv::Mat& m, const cv::Point2f& a, const cv::Point2f& c, unsigned char r, unsigned char g, unsigned char b) {
-        const int n = std::max(1, (int)std::ceil(std::max(std::fabs(a.x - c.x), std::fabs(a.y - c.y))));
-        for (int k = 0; k <= n; ++k) Put(m, cvRound(a.x + (c.x - a.x) * k / n), cvRound(a.y + (c.y - a.y) * k / n), r, g, b);
     }
 
     vf_config cfg_;

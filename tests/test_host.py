@@ -339,3 +339,45 @@ def test_feature_frames_feed_the_reference_consumer_types(tmp_path):
         rec_sum += sum(float(np.float64(g[f"f{k}_{n}_right"][:, 0]).sum()) for n in ("un", "uv", "vel"))
         assert abs(float(l[4]) - rec_sum) < 1e-6 * max(1.0, abs(rec_sum))
     assert want[0][1] == len(g["f0_ids"]) and any(w[2] > 0 for w in want)      # all new on frame 0, long tracks later
+
+
+def test_draw_tracker_is_pixel_identical_to_opencv(tmp_path):
+    """DrawTracker (feature_tracker.cpp:267-299).  The C++ renderer (include/vins_fast_b200/draw.hpp) on
+    random tracker-like scenes against the same cv2 calls the reference makes: hconcat, cvtColor(GRAY2RGB),
+    circle(r 2, thickness 2), arrowedLine(thickness 1, LINE_8, tipLength 0.2)."""
+    cv2 = pytest.importorskip("cv2")
+    from conftest import build_cpp_test
+    exe = build_cpp_test("test_draw", link_lib=False)
+    rng = np.random.default_rng(17)
+    for case, (w, h, n) in enumerate(((752, 480, 150), (320, 240, 60), (97, 64, 25))):
+        left = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        right = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        # in-border points (InBorder, feature_tracker.cpp:20-25), half-pixel cases included
+        kps = np.stack([rng.uniform(1, w - 2, n), rng.uniform(1, h - 2, n)], 1).astype(np.float32)
+        kps[:6] = np.floor(kps[:6]) + 0.5
+        cnt = rng.integers(1, 40, n).astype(np.int32)
+        cnt[:4] = (1, 10, 20, 21)
+        nr = n - n // 5
+        rk = np.stack([rng.uniform(1, w - 2, nr), rng.uniform(1, h - 2, nr)], 1).astype(np.float32)
+        step = rng.uniform(-9, 9, (n, 2)) * rng.choice([0.0, 0.3, 1.0, 4.0, 12.0], (n, 1))   # long arrows: tips leave the image
+        prev = np.clip(kps + step, 1, [w - 2, h - 2]).astype(np.float32)
+        has_prev = (rng.uniform(0, 1, n) < 0.85).astype(np.uint8)
+        scene = tmp_path / f"scene{case}.bin"
+        with open(scene, "wb") as f:
+            f.write(np.array([w, h, n, nr], np.int32).tobytes() + left.tobytes() + right.tobytes() + kps.tobytes() + cnt.tobytes()
+                    + rk.tobytes() + prev.tobytes() + has_prev.tobytes())
+        out = tmp_path / f"out{case}.rgb"
+        subprocess.check_call([exe, str(scene), str(out)])
+        got = np.fromfile(out, np.uint8).reshape(h, 2 * w, 3)
+        # the reference's calls, verbatim (Point2f arguments are rounded by cv::Point's converting constructor = cvRound)
+        rnd = lambda p: (int(np.rint(np.float32(p[0]))), int(np.rint(np.float32(p[1]))))
+        img = cv2.cvtColor(cv2.hconcat([left, right]), cv2.COLOR_GRAY2RGB)
+        for j in range(n):
+            ln = min(1.0, 1.0 * int(cnt[j]) / 20)
+            cv2.circle(img, rnd(kps[j]), 2, (255 * (1 - ln), 0, 255 * ln), 2)
+        for j in range(nr):
+            cv2.circle(img, rnd((np.float32(rk[j, 0]) + np.float32(w), rk[j, 1])), 2, (0, 255, 0), 2)
+        for i in range(n):
+            if has_prev[i]:
+                cv2.arrowedLine(img, rnd(kps[i]), rnd(prev[i]), (0, 255, 0), 1, 8, 0, 0.2)
+        assert np.array_equal(got, img), f"case {case}: {int((got != img).any(axis=2).sum())} pixels differ"
