@@ -218,6 +218,37 @@ vf_status vf_op_set_mask(const float* pts, const int32_t* track_cnt, int32_t n, 
 /* RemoveDistortion (feature_tracker.cpp:310-321): out_xy float 2*n. */
 vf_status vf_op_undistort(const vf_camera* cam, const float* uv, int32_t n, int32_t device, float* out_xy);
 
+/* ---- next data-parallel step after the front-end: landmark triangulation + outlier rejection ---- */
+/* The sliding window the estimator keeps on the host (arguments of TriangulatePts / OutliersRejection,
+ * feature_manager.cpp:202-203, 379-380): Ps[window][3] = P_wi, Rs[window][9] = R_wi (row-major), camera-to-IMU
+ * extrinsics tic[c][3], ric[c][9] for the left (0) and right (1) camera. */
+typedef struct {
+    int32_t window;
+    const double* Ps;
+    const double* Rs;
+    double tic[2][3];
+    double ric[2][9];
+} vf_window;
+/* FeatureManager::TriangulateOnePoint (feature_manager.cpp:277-293) for n landmarks: pose0 / pose1 = n x 12 (row-major
+ * 3x4 T_cw), point0 / point1 = n x 2 normalised coordinates, point_3d = n x 3 (world frame). */
+vf_status vf_op_triangulate_one_point(const double* pose0, const double* pose1, const double* point0, const double* point1,
+                                      int32_t n, int32_t device, double* point_3d);
+/* Landmark table = FeatureManager::features_ flattened: landmark i was first seen in window frame start_frame[i] and has
+ * n_obs[i] consecutive observations in rows obs_offset[i] .. obs_offset[i] + n_obs[i] - 1 of `obs` (n_obs_rows rows of 7
+ * doubles: point_.x, point_.y, point_.z, track_right_success_ (0 / 1), point_right_.x, .y, .z).
+ * FeatureManager::TriangulatePts (feature_manager.cpp:202-275): depth_io[i] = estimated_depth_ (input: <= 0 = not yet
+ * triangulated; those are filled from the stereo pair of the first frame, else from the first two frames; a
+ * non-positive depth becomes init_depth = INIT_DEPTH, feature_manager.hpp:88). */
+vf_status vf_op_triangulate_pts(const vf_window* w, int32_t n, const int32_t* start_frame, const int32_t* n_obs,
+                                const int32_t* obs_offset, const double* obs, int32_t n_obs_rows, double init_depth,
+                                int32_t device, double* depth_io);
+/* FeatureManager::OutliersRejection (feature_manager.cpp:379-429): mean ReProjectionError (:365-377) of landmark i over its
+ * observations (landmarks with fewer than 4 are skipped: remove_out 0, ave_err_out 0); remove_out[i] = 1 iff
+ * ave_err * focal_length > 3.  ave_err_out may be null. */
+vf_status vf_op_outliers_rejection(const vf_window* w, int32_t n, const int32_t* start_frame, const int32_t* n_obs,
+                                   const int32_t* obs_offset, const double* obs, int32_t n_obs_rows, const double* depth,
+                                   double focal_length, int32_t device, double* ave_err_out, uint8_t* remove_out);
+
 /* Pinned host memory helpers (so callers can hand page-locked images to vf_tracker_track). */
 vf_status vf_host_alloc(size_t bytes, void** out);
 void vf_host_free(void* p);

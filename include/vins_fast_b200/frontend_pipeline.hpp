@@ -10,8 +10,12 @@
 // busy back to back, for replaying recorded sequences).  Results are bit-identical to the synchronous
 // FeatureTracker::TrackImage.
 //
-// The images of a frame are referenced (cv::Mat shallow copies, like the reference's current_img_) until that frame has
-// been collected.
+// Input side: Push copies the two images into a ring of page-locked slots and uploads from there, so
+// the H2D copy is a true asynchronous DMA whatever memory the caller's cv::Mat lives in (a cudaMemcpyAsync from pageable
+// memory is staged synchronously by the driver and would serialise the "asynchronous" enqueue), and the caller's buffers
+// are free again when Push returns -- the same ownership the reference gets from GetImageFromROSMsg's clone()
+// (vins/common/utils.hpp:17-37).  Sources that can write in place (a ROS callback, a file reader) skip the copy:
+// AcquireLeft() / AcquireRight() hand out the slot of the next frame as cv::Mat views, PushAcquired(t) starts it.
 #pragma once
 
 #include <mutex>
@@ -21,6 +25,7 @@
 #include <vector>
 
 #include "feature_tracker.hpp"
+#include "image_source.hpp"
 
 namespace estimator {
 
@@ -40,17 +45,34 @@ public:
     FrontendPipeline(const FrontendPipeline&) = delete;
     FrontendPipeline& operator=(const FrontendPipeline&) = delete;
 
-    /// Estimator::FrontendTracker(t, img0, img1), asynchronous: starts frame k, hands frame k-1 to the queue
+    /// Estimator::FrontendTracker(t, img0, img1), asynchronous: starts frame k, hands frame k-depth to the queue.
+    /// The pixels are copied into the pinned slot of frame k; img0 / img1 may be released as soon as this returns.
     void Push(double t, const cv::Mat& img0, const cv::Mat& img1) {
         if (img0.empty() || img1.empty()) VF_FATAL("FrontendPipeline::Push: !img0.empty() && !img1.empty()");
         if (img0.type() != CV_8UC1 || img1.type() != CV_8UC1 || img0.rows != img1.rows || img0.cols != img1.cols)
             VF_FATAL("FrontendPipeline::Push: both images must be CV_8UC1 of one size");
         Ensure(img0.cols, img0.rows);
-        const int slot = (int)(input_image_cnt_ % 3);
-        held_[slot][0] = img0; held_[slot][1] = img1; times_[slot] = t;      // keep the pixels alive while the frame is in flight
-        const uint8_t* p0 = img0.data;
-        const uint8_t* p1 = img1.data;
-        if (vf_batch_enqueue(batch_, &t, &p0, img0.step, &p1, img1.step) != VF_OK)
+        CopyRows(img0, ring_.Slot(input_image_cnt_, 0));
+        CopyRows(img1, ring_.Slot(input_image_cnt_, 1));
+        PushAcquired(t);
+    }
+    /// Same from image messages (common::GetImageFromROSMsg, utils.hpp:17-37): mono8 / 8UC1 pixels straight into the slot
+    void Push(const common::ImageMsg& msg0, const common::ImageMsg& msg1) {
+        if (msg0.width != msg1.width || msg0.height != msg1.height) VF_FATAL("FrontendPipeline::Push: the two messages differ in size");
+        Ensure(msg0.width, msg0.height);
+        common::CopyMono8(msg0, ring_.Slot(input_image_cnt_, 0), (size_t)msg0.width);
+        common::CopyMono8(msg1, ring_.Slot(input_image_cnt_, 1), (size_t)msg1.width);
+        PushAcquired(msg0.stamp);
+    }
+    /// Zero-copy ingestion: continuous CV_8UC1 views of the NEXT frame's page-locked slot (valid until PushAcquired)
+    cv::Mat AcquireLeft(int width, int height) { Ensure(width, height); return ring_.Left(input_image_cnt_); }
+    cv::Mat AcquireRight(int width, int height) { Ensure(width, height); return ring_.Right(input_image_cnt_); }
+    void PushAcquired(double t) {
+        if (!batch_) VF_FATAL("FrontendPipeline::PushAcquired: no slot has been acquired");
+        times_[input_image_cnt_ % kSlots] = t;
+        const uint8_t* p0 = ring_.Slot(input_image_cnt_, 0);
+        const uint8_t* p1 = ring_.Slot(input_image_cnt_, 1);
+        if (vf_batch_enqueue(batch_, &t, &p0, (size_t)cfg_.width, &p1, (size_t)cfg_.width) != VF_OK)
             VF_FATAL(std::string("vf_batch_enqueue: ") + vf_batch_last_error(batch_));
         input_image_cnt_++;
         if (input_image_cnt_ > depth_) Collect(depth_);
@@ -84,6 +106,12 @@ private:
         if (vf_batch_create(&cfg_, 1, &batch_) != VF_OK) VF_FATAL(std::string("vf_batch_create: ") + vf_last_global_error());
         records_.resize((size_t)(cfg_.max_cnt > 0 ? cfg_.max_cnt : 1));
         input_image_cnt_ = 0; collected_ = 0;
+        // slot k % 4 is rewritten by frame k + 4: by then frame k has been collected (depth <= 2), so its upload has long completed
+        ring_.Ensure(width, height, kSlots);
+    }
+    static void CopyRows(const cv::Mat& m, unsigned char* dst) {
+        if (m.isContinuous()) { std::memcpy(dst, m.data, (size_t)m.cols * m.rows); return; }
+        for (int y = 0; y < m.rows; ++y) std::memcpy(dst + (size_t)y * m.cols, m.ptr<unsigned char>(y), (size_t)m.cols);
     }
     // featureFrame of the frame `lag` behind the last enqueued one (feature_tracker.cpp:173-213) -> queue
     void Collect(int lag) {
@@ -91,14 +119,13 @@ private:
         if (vf_batch_fetch_lagged(batch_, lag, records_.data(), &n) != VF_OK)
             VF_FATAL(std::string("vf_batch_fetch_lagged: ") + vf_batch_last_error(batch_));
         const long index = input_image_cnt_ - 1 - lag;          // 0-based index of the collected frame
-        const int slot = (int)(index % 3);
+        const int slot = (int)(index % kSlots);
         collected_ = index + 1;
         if (collected_ % every_nth_ == 0) {                       // input_image_cnt_ % 2 == 0 in the reference (1-based count)
             FeatureFrame ff = FeatureTracker::ToFeatureFrame(records_.data(), n);
             std::unique_lock<std::mutex> lck(feature_buf_mutex_);
             feature_buf_.push(std::make_pair(times_[slot], std::move(ff)));
         }
-        held_[slot][0] = cv::Mat(); held_[slot][1] = cv::Mat();
     }
 
     vf_config cfg_;
@@ -106,8 +133,9 @@ private:
     int every_nth_, depth_;
     long input_image_cnt_ = 0, collected_ = 0;
     std::vector<vf_feature> records_;
-    cv::Mat held_[3][2];
-    double times_[3] = {0, 0, 0};
+    static constexpr int kSlots = 4;
+    PinnedImageRing ring_;
+    double times_[kSlots] = {0, 0, 0, 0};
     std::mutex feature_buf_mutex_;
     std::queue<std::pair<double, FeatureFrame>> feature_buf_;
 };

@@ -160,3 +160,33 @@ def first_divergence(frames_a, frames_b):
             if x.shape != y.shape or x.tobytes() != y.astype(x.dtype).tobytes():
                 return k, key
     return None
+
+
+def write_euroc_dir(root, frames, jitter_ns=(0, 0), drop_right=(), extra_left=()):
+    """An EuRoC-ASL-like directory: <root>/cam{0,1}/data.csv (timestamp [ns], filename) + binary PGM images.
+    frames: [(t, left, right)].  jitter_ns: per-camera stamp offsets; drop_right: frame indices whose right image is lost;
+    extra_left: indices after which an unpaired left image (stamp + 25 ms) is inserted.  Returns the expected pairs
+    [(stamp0, left, right)] under the 3 ms rule of Estimator::tFrontendProcess (estimator.cpp:103-141)."""
+    import os
+    expect = []
+    lists = {0: [], 1: []}
+    for cam in (0, 1):
+        os.makedirs(os.path.join(root, f"cam{cam}", "data"), exist_ok=True)
+
+    def put(cam, ns, img):
+        name = f"{ns}.pgm"
+        with open(os.path.join(root, f"cam{cam}", "data", name), "wb") as f:
+            f.write(f"P5\n# synthetic\n{img.shape[1]} {img.shape[0]}\n255\n".encode() + np.ascontiguousarray(img).tobytes())
+        lists[cam].append((ns, name))
+    for k, (t, l, r) in enumerate(frames):
+        ns = int(round(t * 1e9)) + 1_403_636_579_000_000_000
+        put(0, ns + jitter_ns[0], l)
+        if k not in drop_right:
+            put(1, ns + jitter_ns[1], r)
+            expect.append(((ns + jitter_ns[0]) * 1e-9, l, r))
+        if k in extra_left:
+            put(0, ns + 25_000_000, 255 - l)
+    for cam in (0, 1):
+        with open(os.path.join(root, f"cam{cam}", "data.csv"), "w") as f:
+            f.write("#timestamp [ns],filename\n" + "".join(f"{ns},{name}\n" for ns, name in lists[cam]))
+    return expect

@@ -368,3 +368,35 @@ def test_device_input_ordering_event_and_caller_stream(lib, oracle, euroc_frames
         res = batch.track_device(t, dl.data_ptr(), dr.data_ptr(), 752, 752 * 480)
         assert_frames_equal(oracle.records_to_frame(res[0]), want[k], f"caller-stream frame {k}")
     batch.close()
+
+
+def test_cpp_replay_from_euroc_listing_through_the_pinned_ring(lib, oracle, euroc_frames, tmp_path):
+    """SURVEY 8(f) rank 2: EuRoC listing + PGM files -> StereoSync -> FrontendPipeline::Push / AcquireLeft+PushAcquired (pinned
+    ingest ring, caller's buffers wiped right after Push) -> feature_buf_; every queued featureFrame equals the oracle's."""
+    import struct
+    import subprocess
+    from conftest import build_cpp_test, write_camera_yaml, write_euroc_dir
+    from oracle.cv2_oracle import Cv2FeatureTracker
+    exe = build_cpp_test("test_image_source")
+    write_camera_yaml(tmp_path / "cam0_mei.yaml", EUROC_CAM0, 752, 480)
+    write_camera_yaml(tmp_path / "cam1_mei.yaml", EUROC_CAM1, 752, 480)
+    expect = write_euroc_dir(str(tmp_path / "mav0"), euroc_frames[:10], jitter_ns=(0, -1_500_000), drop_right=(4,))
+    res = subprocess.run([exe, "replay", str(tmp_path / "mav0"), str(tmp_path / "cam0_mei.yaml"), str(tmp_path / "cam1_mei.yaml"),
+                          str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "replay ok: 9 pairs, thrown 1 0" in res.stdout, res.stdout + res.stderr
+    buf = open(tmp_path / "out.bin", "rb").read()
+    off = 0
+    ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
+    for k, (t, l, r) in enumerate(expect):
+        ns = int(round(t * 1e9))
+        want = Cv2FeatureTracker.feature_frame(ref.track_image(ns * 1e-9, l, r))     # the reader's stamp: ns * 1e-9
+        (gt, n_ids) = struct.unpack_from("<di", buf, off); off += 12
+        assert gt == ns * 1e-9 and n_ids == len(want)
+        for fid in sorted(want):
+            gid, n_obs = struct.unpack_from("<ii", buf, off); off += 8
+            assert gid == fid and n_obs == len(want[fid])
+            for cam_id, vec in want[fid]:
+                (gcam,) = struct.unpack_from("<i", buf, off); off += 4
+                v = np.frombuffer(buf, np.float64, 7, off); off += 56
+                assert gcam == cam_id and v.tobytes() == vec.tobytes(), f"pair {k} id {fid} cam {cam_id}"
+    assert off == len(buf)

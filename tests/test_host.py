@@ -381,3 +381,22 @@ def test_draw_tracker_is_pixel_identical_to_opencv(tmp_path):
             if has_prev[i]:
                 cv2.arrowedLine(img, rnd(kps[i]), rnd(prev[i]), (0, 255, 0), 1, 8, 0, 0.2)
         assert np.array_equal(got, img), f"case {case}: {int((got != img).any(axis=2).sum())} pixels differ"
+
+
+def test_input_side_pgm_euroc_listing_and_stereo_sync(tmp_path):
+    """SURVEY 8(f) rank 2 on the host: EuRoC data.csv listings + raw PGM images -> StereoSync (the 3 ms pairing rule of
+    Estimator::tFrontendProcess, estimator.cpp:103-141) -> synchronised pairs; GetImageFromROSMsg's mono8 / 8UC1 copy
+    (vins/common/utils.hpp:17-37)."""
+    from conftest import build_cpp_test, write_euroc_dir
+    from vins_fast_b200.synth import StereoSequence
+    exe = build_cpp_test("test_image_source")
+    seq = StereoSequence(4, 160, 120)
+    frames = [seq.frame(k) for k in range(9)]
+    expect = write_euroc_dir(str(tmp_path), frames, jitter_ns=(0, 2_000_000), drop_right=(3,), extra_left=(6,))
+    res = subprocess.run([exe, "host", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "host ok" in res.stdout, res.stdout + res.stderr
+    pairs = [ln.split() for ln in res.stdout.splitlines() if ln.startswith("pair")]
+    assert len(pairs) == len(expect) == 8
+    for got, (t, l, r) in zip(pairs, expect):
+        assert abs(float(got[1]) - t) < 1e-6 and int(got[2]) == int(l.sum()) and int(got[3]) == int(r.sum())
+    assert "thrown 2 0" in res.stdout          # the left image whose partner was lost + the unpaired extra one

@@ -265,3 +265,22 @@ def test_vectorised_glue_of_the_cv2_oracle_is_bit_identical():
         assert bool(_in_border(p, 480, 752)[i]) == (1 <= x < 751 and 1 <= y < 479)
         dx, dy = float(p[i, 0] - q[i, 0]), float(p[i, 1] - q[i, 1])
         assert float(_pt_distance(p, q)[i]) == float(np.sqrt(dx * dx + dy * dy))
+
+
+def test_geometry_fixture_is_what_the_reference_code_computes():
+    """tests/golden/geometry_reference_eigen_3_3_7.npz against the reference's own FeatureManager functions (oracle/_ref, built
+    from /root/reference by oracle/build_ref.py); skipped where neither the reference nor the prebuilt library exists."""
+    from oracle import ref_geometry as R
+    if not R.available():
+        pytest.skip("reference not available")
+    from geometry_scene import make_scene, stereo_pairs
+    g = np.load(os.path.join(GOLD, "geometry_reference_eigen_3_3_7.npz"))
+    sc = make_scene(0, 600)
+    P0, P1, a, b = stereo_pairs(sc)
+    assert np.array_equal(R.triangulate_one_point(P0, P1, a, b), g["s0_point3d"])
+    d = R.triangulate_pts(sc["Ps"], sc["Rs"], sc["tic"], sc["ric"], sc["start_frame"], sc["n_obs"], sc["obs_offset"], sc["obs"], sc["depth"])
+    assert np.array_equal(d, g["s0_depth"])
+    rm = R.outliers_rejection(sc["Ps"], sc["Rs"], sc["tic"], sc["ric"], sc["start_frame"], sc["n_obs"], sc["obs_offset"], sc["obs"], d)
+    assert np.array_equal(rm, g["s0_remove"])
+    # sanity of the scene: triangulated depths of clean stereo landmarks are the true depths to ~1 %
+    assert np.median(d[d > 0]) > 1.0

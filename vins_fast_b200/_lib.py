@@ -34,6 +34,10 @@ class VfConfig(C.Structure):
                 ("use_cuda_graph", C.c_int32), ("cuda_stream", C.c_void_p)]
 
 
+class VfWindow(C.Structure):
+    _fields_ = [("window", C.c_int32), ("Ps", C.c_void_p), ("Rs", C.c_void_p), ("tic", (C.c_double * 3) * 2), ("ric", (C.c_double * 9) * 2)]
+
+
 class VfFeature(C.Structure):
     _fields_ = [("id", C.c_int32), ("track_cnt", C.c_int32), ("has_right", C.c_int32)] + \
                [(n, C.c_float) for n in ("x", "y", "u", "v", "vx", "vy", "xr", "yr", "ur", "vr", "vxr", "vyr")]
@@ -55,7 +59,7 @@ EXPORTS = [
     "vf_tracker_debug_get",
     "vf_debug_set_response_kernel",
     "vf_op_build_pyramid", "vf_op_scharr", "vf_op_lk", "vf_op_min_eigen", "vf_op_good_features", "vf_op_set_mask",
-    "vf_op_undistort",
+    "vf_op_undistort", "vf_op_triangulate_one_point", "vf_op_triangulate_pts", "vf_op_outliers_rejection",
     "vf_host_alloc", "vf_host_free", "vf_device_count",
 ]
 
@@ -121,6 +125,9 @@ def load() -> C.CDLL:
         "vf_op_good_features": (I32, [P, I32, I32, I32, F64, I32, P, I32, P, P]),
         "vf_op_set_mask": (I32, [P, P, I32, I32, I32, I32, I32, P, P, P, P]),
         "vf_op_undistort": (I32, [P, P, I32, I32, P]),
+        "vf_op_triangulate_one_point": (I32, [P, P, P, P, I32, I32, P]),
+        "vf_op_triangulate_pts": (I32, [P, I32, P, P, P, P, I32, F64, I32, P]),
+        "vf_op_outliers_rejection": (I32, [P, I32, P, P, P, P, I32, P, F64, I32, P, P]),
         "vf_host_alloc": (I32, [SZ, P]),
         "vf_host_free": (None, [P]),
         "vf_device_count": (I32, []),

@@ -100,3 +100,62 @@ def undistort(cam, uv, device: int = -1) -> np.ndarray:
     out = np.zeros_like(p)
     check(load().vf_op_undistort(C.byref(c), p.ctypes.data, len(p), device, out.ctypes.data))
     return out
+
+
+# ---- landmark geometry -----------------------------------------------------------------------------
+def _window(Ps, Rs, tic, ric):
+    from ._lib import VfWindow
+    Ps = np.ascontiguousarray(Ps, np.float64).reshape(-1, 3)
+    Rs = np.ascontiguousarray(Rs, np.float64).reshape(-1, 9)
+    assert len(Ps) == len(Rs)
+    w = VfWindow()
+    w.window, w.Ps, w.Rs = len(Ps), Ps.ctypes.data, Rs.ctypes.data
+    t = np.ascontiguousarray(tic, np.float64).reshape(2, 3)
+    r = np.ascontiguousarray(ric, np.float64).reshape(2, 9)
+    for c in range(2):
+        for k in range(3):
+            w.tic[c][k] = t[c, k]
+        for k in range(9):
+            w.ric[c][k] = r[c, k]
+    return w, (Ps, Rs)          # keep the arrays alive while the struct points at them
+
+
+def _table(start_frame, n_obs, obs_offset, obs):
+    sf = np.ascontiguousarray(start_frame, np.int32)
+    no = np.ascontiguousarray(n_obs, np.int32)
+    oo = np.ascontiguousarray(obs_offset, np.int32)
+    ob = np.ascontiguousarray(obs, np.float64).reshape(-1, 7)
+    return sf, no, oo, ob
+
+
+def triangulate_one_point(pose0, pose1, point0, point1, device: int = -1) -> np.ndarray:
+    """FeatureManager::TriangulateOnePoint (feature_manager.cpp:277-293) for n landmarks -> float64 (n, 3)."""
+    a = np.ascontiguousarray(pose0, np.float64).reshape(-1, 12)
+    b = np.ascontiguousarray(pose1, np.float64).reshape(-1, 12)
+    p0 = np.ascontiguousarray(point0, np.float64).reshape(-1, 2)
+    p1 = np.ascontiguousarray(point1, np.float64).reshape(-1, 2)
+    out = np.zeros((len(a), 3), np.float64)
+    check(load().vf_op_triangulate_one_point(a.ctypes.data, b.ctypes.data, p0.ctypes.data, p1.ctypes.data, len(a), device, out.ctypes.data))
+    return out
+
+
+def triangulate_pts(Ps, Rs, tic, ric, start_frame, n_obs, obs_offset, obs, depth, init_depth: float = 5.0, device: int = -1) -> np.ndarray:
+    """FeatureManager::TriangulatePts (feature_manager.cpp:202-275) -> estimated_depth_ per landmark (float64)."""
+    w, keep = _window(Ps, Rs, tic, ric)
+    sf, no, oo, ob = _table(start_frame, n_obs, obs_offset, obs)
+    d = np.ascontiguousarray(depth, np.float64).copy()
+    check(load().vf_op_triangulate_pts(C.byref(w), len(sf), sf.ctypes.data, no.ctypes.data, oo.ctypes.data, ob.ctypes.data, len(ob),
+                                       float(init_depth), device, d.ctypes.data))
+    return d
+
+
+def outliers_rejection(Ps, Rs, tic, ric, start_frame, n_obs, obs_offset, obs, depth, focal_length: float = 460.0, device: int = -1):
+    """FeatureManager::OutliersRejection (feature_manager.cpp:379-429) -> (mean reprojection error, remove flags)."""
+    w, keep = _window(Ps, Rs, tic, ric)
+    sf, no, oo, ob = _table(start_frame, n_obs, obs_offset, obs)
+    d = np.ascontiguousarray(depth, np.float64)
+    ave = np.zeros(len(sf), np.float64)
+    rm = np.zeros(len(sf), np.uint8)
+    check(load().vf_op_outliers_rejection(C.byref(w), len(sf), sf.ctypes.data, no.ctypes.data, oo.ctypes.data, ob.ctypes.data, len(ob),
+                                          d.ctypes.data, float(focal_length), device, ave.ctypes.data, rm.ctypes.data))
+    return ave, rm
