@@ -205,6 +205,9 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
 /* Which corner-response kernel the library launches (process-wide; parity tests only): 0 = by frame size (default),
  * 1 = tiles (small frames), 2 = strips (large frames / batches).  Both give identical results. */
 vf_status vf_debug_set_response_kernel(int32_t mode);
+/* Which pyramid kernel the library launches (process-wide; parity tests only; takes effect for handles created afterwards):
+ * 0 = by size (default), 1 = fused multi-level kernel only, 2 = streaming TMA kernel for every level transition. */
+vf_status vf_debug_set_pyramid_kernel(int32_t mode);
 /* cornerMinEigenVal(img, 3, ksize 3): out float w*h. */
 vf_status vf_op_min_eigen(const uint8_t* img, int32_t w, int32_t h, int32_t device, float* out);
 /* goodFeaturesToTrack(img, max_corners, quality, min_dist, mask): out_xy capacity 2*max_corners floats. */

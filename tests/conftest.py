@@ -166,7 +166,7 @@ def write_euroc_dir(root, frames, jitter_ns=(0, 0), drop_right=(), extra_left=()
     """An EuRoC-ASL-like directory: <root>/cam{0,1}/data.csv (timestamp [ns], filename) + binary PGM images.
     frames: [(t, left, right)].  jitter_ns: per-camera stamp offsets; drop_right: frame indices whose right image is lost;
     extra_left: indices after which an unpaired left image (stamp + 25 ms) is inserted.  Returns the expected pairs
-    [(stamp0, left, right)] under the 3 ms rule of Estimator::tFrontendProcess (estimator.cpp:103-141)."""
+    [(stamp0, left, right, stamp0 in ns)] under the 3 ms rule of Estimator::tFrontendProcess (estimator.cpp:103-141)."""
     import os
     expect = []
     lists = {0: [], 1: []}
@@ -183,7 +183,7 @@ def write_euroc_dir(root, frames, jitter_ns=(0, 0), drop_right=(), extra_left=()
         put(0, ns + jitter_ns[0], l)
         if k not in drop_right:
             put(1, ns + jitter_ns[1], r)
-            expect.append(((ns + jitter_ns[0]) * 1e-9, l, r))
+            expect.append(((ns + jitter_ns[0]) * 1e-9, l, r, ns + jitter_ns[0]))
         if k in extra_left:
             put(0, ns + 25_000_000, 255 - l)
     for cam in (0, 1):

@@ -13,8 +13,17 @@ def _crop(img, h, w, y0=3, x0=5):
     return np.ascontiguousarray(img[y0:y0 + h, x0:x0 + w])
 
 
-@pytest.mark.parametrize("shape", [(480, 752), (479, 751), (240, 376), (97, 131), (64, 64), (720, 1280)])
-def test_pyramid_bit_exact(lib, oracle, euroc_seq, shape):
+@pytest.fixture(params=[1, 2], ids=["fused", "tma"])
+def pyramid_kernel(request, lib):
+    """Both pyramid kernels (fused multi-level / streaming TMA; the library picks by size) must give the same bytes."""
+    from vins_fast_b200 import ops
+    ops.set_pyramid_kernel(request.param)
+    yield request.param
+    ops.set_pyramid_kernel(0)
+
+
+@pytest.mark.parametrize("shape", [(480, 752), (479, 751), (240, 376), (97, 131), (64, 64), (720, 1280), (193, 385), (200, 191), (1083, 1925)])
+def test_pyramid_bit_exact(lib, oracle, euroc_seq, shape, pyramid_kernel):
     from vins_fast_b200 import ops
     from vins_fast_b200.synth import StereoSequence
     h, w = shape

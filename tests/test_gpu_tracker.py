@@ -59,6 +59,21 @@ def test_flow_back_off(lib, oracle, euroc_frames):
     _run_pair(oracle, euroc_frames[:8], 752, 480, 150, 30, 0, EUROC_CAM0, EUROC_CAM1)
 
 
+@pytest.mark.parametrize("mode", [1, 2], ids=["fused", "tma"])
+def test_euroc_sequence_with_either_pyramid_kernel(lib, oracle, euroc_frames, mode):
+    """The whole frame (level 0 moved into its padded home by the pyramid launch, borders, both cameras) with the pyramid
+    kernel forced: 752x480 normally takes the fused kernel, 4K and batches the streaming TMA kernel."""
+    from vins_fast_b200 import ops
+    ops.set_pyramid_kernel(mode)
+    try:
+        _run_pair(oracle, euroc_frames[:6], 752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1, check_debug=(mode == 2))
+        frames = [(t, np.ascontiguousarray(l[:301, :433]), np.ascontiguousarray(r[:301, :433])) for t, l, r in euroc_frames[:4]]
+        cam = pinhole_for(433, 301, distorted=False)
+        _run_pair(oracle, frames, 433, 301, 40, 25, 1, cam, cam)
+    finally:
+        ops.set_pyramid_kernel(0)
+
+
 def test_pinhole_720p_level4(lib, oracle):
     from vins_fast_b200.synth import StereoSequence
     seq = StereoSequence(2, 1280, 720)
@@ -387,8 +402,7 @@ def test_cpp_replay_from_euroc_listing_through_the_pinned_ring(lib, oracle, euro
     buf = open(tmp_path / "out.bin", "rb").read()
     off = 0
     ref = oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1)
-    for k, (t, l, r) in enumerate(expect):
-        ns = int(round(t * 1e9))
+    for k, (t, l, r, ns) in enumerate(expect):
         want = Cv2FeatureTracker.feature_frame(ref.track_image(ns * 1e-9, l, r))     # the reader's stamp: ns * 1e-9
         (gt, n_ids) = struct.unpack_from("<di", buf, off); off += 12
         assert gt == ns * 1e-9 and n_ids == len(want)

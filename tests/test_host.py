@@ -397,6 +397,6 @@ def test_input_side_pgm_euroc_listing_and_stereo_sync(tmp_path):
     assert res.returncode == 0 and "host ok" in res.stdout, res.stdout + res.stderr
     pairs = [ln.split() for ln in res.stdout.splitlines() if ln.startswith("pair")]
     assert len(pairs) == len(expect) == 8
-    for got, (t, l, r) in zip(pairs, expect):
+    for got, (t, l, r, _) in zip(pairs, expect):
         assert abs(float(got[1]) - t) < 1e-6 and int(got[2]) == int(l.sum()) and int(got[3]) == int(r.sum())
     assert "thrown 2 0" in res.stdout          # the left image whose partner was lost + the unpaired extra one

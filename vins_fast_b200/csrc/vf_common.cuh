@@ -107,7 +107,8 @@ struct TraceScope {
     unsigned long long* slot;
     __device__ __forceinline__ static unsigned long long now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
     __device__ __forceinline__ TraceScope(unsigned long long* buf, int id) : slot(buf ? buf + 2 * id : nullptr) {
-        if (slot && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *slot = now();   // first CTA
+        // first CTA; min over the launches that share the id within a frame (a pyramid is several launches)
+        if (slot && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicMin(slot, now());
     }
     __device__ __forceinline__ ~TraceScope() { if (slot && threadIdx.x == 0) atomicMax(slot + 1, now()); }
 };

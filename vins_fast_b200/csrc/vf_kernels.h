@@ -70,6 +70,13 @@ struct Level0Src {   // unpadded staging image(s): rows 16-byte aligned
 int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0 = nullptr,
                    unsigned long long* trace = nullptr, int trace_id = 0);
 void launch_scharr(const uint8_t* src, int w, int h, int pitch, int16_t* dst, cudaStream_t stream);
+void set_pyramid_kernel_mode(int mode);   // 0 by size, 1 fused kernel only, 2 streaming (TMA) kernel everywhere (parity tests)
+
+// ---- vf_pyramid_tma.cu ----
+bool pyramid_tma_available();
+cudaError_t pyramid_tma_prepare();
+bool launch_pyr_tma(const uint8_t* src, int sw, int sh, int spitch, size_t s_stride, uint8_t* dst, int dw, int dh, int dpitch, size_t d_stride,
+                    uint8_t* home, int hpitch, size_t h_stride, int n_images, cudaStream_t stream, unsigned long long* trace, int trace_id);
 
 // ---- vf_lk.cu ----
 // `cur` / `prev`: slots of the current and of the previous left pyramid in DevBatch::left

@@ -268,19 +268,47 @@ static void launch_pad_levels(const PyrView& pv, const size_t* stride, int n_ima
     launch_kernel(pad_levels_kernel, grid, dim3(256), 0, stream, a);   // behind pyr_fused: programmatic launch when hinted
 }
 
-// All levels 1..n_levels-1 of a pyramid from its level 0, in ceil((n_levels-1)/3) launches, then the REFLECT_101
-// borders of all levels in one more.  With src0 the image still sits in an unpadded staging buffer (one linear upload):
-// the first pyramid launch reads it there and the border launch also moves it into the padded level 0.
-// Returns the launch count.
+static int g_pyramid_mode = 0;   // 0 = by size, 1 = fused kernel only, 2 = streaming (TMA) kernel for every transition
+void set_pyramid_kernel_mode(int mode) { g_pyramid_mode = mode; }
+
+// A transition is a throughput problem (streaming kernel, vf_pyramid_tma.cu) once its source level holds this many pixels
+// over the whole batch; below, the fused kernel's single launch for three levels wins on latency.
+static bool want_streaming(const PyrView& pv, int level, int n_images) {
+    if (g_pyramid_mode == 1 || !pyramid_tma_available()) return false;
+    if (g_pyramid_mode == 2) return true;
+    return (long long)pv.w[level] * pv.h[level] * n_images >= 600000;
+}
+
+// All levels 1..n_levels-1 of a pyramid from its level 0, then the REFLECT_101 borders of all levels in one more launch.
+// Large source levels (4K frames, batches of streams) go through the streaming kernel, one transition per launch; the
+// rest through the fused kernel, up to three levels per launch.  With src0 the image still sits in an unpadded staging
+// buffer (one linear upload): the first pyramid launch reads it there, and level 0 is moved into its padded home either by
+// the streaming kernel itself or, on the fused path, by the border launch.  Returns the launch count.
 int launch_pyramid(const PyrView& pv, const size_t* stride, int n_images, cudaStream_t stream, const Level0Src* src0,
                    unsigned long long* trace, int trace_id) {
     int first = 0, left = pv.n_levels - 1, n = 0;
+    bool home_done = false;
+    const bool hint = pdl_hint();
+    while (left > 0 && want_streaming(pv, first, n_images)) {
+        const bool staged = first == 0 && src0;
+        const uint8_t* src = staged ? src0->p : pv.lvl[first];
+        const int spitch = staged ? src0->pitch : pv.pitch[first];
+        const size_t sstride = staged ? src0->stride : (stride ? stride[first] : 0);
+        pdl_hint() = hint && n > 0;                    // only behind a kernel of this pyramid
+        const bool ok = launch_pyr_tma(src, pv.w[first], pv.h[first], spitch, sstride, pv.lvl[first + 1], pv.w[first + 1], pv.h[first + 1],
+                                       pv.pitch[first + 1], stride ? stride[first + 1] : 0, staged ? pv.lvl[0] : nullptr, pv.pitch[0],
+                                       stride ? stride[0] : 0, n_images, stream, trace, trace_id);
+        pdl_hint() = hint;
+        if (!ok) break;
+        if (staged) home_done = true;
+        ++first; --left; ++n;
+    }
     while (left > 0) {
         const int cnt = (left == 4) ? 2 : (left < 3 ? left : 3);
-        launch_pyr_fused(pv, stride, first, cnt, n_images, stream, src0, trace, trace_id);
+        launch_pyr_fused(pv, stride, first, cnt, n_images, stream, home_done ? nullptr : src0, trace, trace_id);
         first += cnt; left -= cnt; ++n;
     }
-    launch_pad_levels(pv, stride, n_images, stream, src0, trace, trace_id + 1);
+    launch_pad_levels(pv, stride, n_images, stream, home_done ? nullptr : src0, trace, trace_id + 1);
     return n + 1;
 }
 
@@ -314,7 +342,7 @@ cudaError_t pyramid_prepare() {
     if ((e = cudaFuncSetAttribute(pyr_fused_kernel<1, 32, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(pad_levels_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(scharr_s16x2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
-    return e;
+    return pyramid_tma_prepare();
 }
 
 }  // namespace vf

@@ -58,6 +58,11 @@ def set_response_kernel(mode: int) -> None:
     check(load().vf_debug_set_response_kernel(int(mode)))
 
 
+def set_pyramid_kernel(mode: int) -> None:
+    """Parity tests: 0 = pick the pyramid kernel by size, 1 = fused multi-level kernel, 2 = streaming TMA kernel (identical results)."""
+    check(load().vf_debug_set_pyramid_kernel(int(mode)))
+
+
 def min_eigen(img, device: int = -1) -> np.ndarray:
     """cv::cornerMinEigenVal(img, 3, ksize=3) -> float32 (h, w)."""
     a = np.ascontiguousarray(_img(img))
