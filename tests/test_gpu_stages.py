@@ -59,8 +59,17 @@ def _lk_points(img, n, seed):
     return np.concatenate([pts, edge])
 
 
+@pytest.fixture(params=[0, 1], ids=["warp", "cta"])
+def lk_kernel(request, lib):
+    """Both Lucas-Kanade kernels (one warp per feature: default; one 4-warp CTA per feature) must give the same bits."""
+    from vins_fast_b200 import ops
+    ops.set_lk_kernel(request.param)
+    yield request.param
+    ops.set_lk_kernel(0)
+
+
 @pytest.mark.parametrize("pair", ["temporal", "stereo"])
-def test_lk_forward_bit_exact(lib, oracle, euroc_frames, pair):
+def test_lk_forward_bit_exact(lib, oracle, euroc_frames, pair, lk_kernel):
     from vins_fast_b200 import ops
     _, l0, r0 = euroc_frames[0]
     _, l1, _ = euroc_frames[1]
@@ -74,7 +83,7 @@ def test_lk_forward_bit_exact(lib, oracle, euroc_frames, pair):
     assert st.sum() > 400
 
 
-def test_lk_reverse_initial_flow_bit_exact(lib, oracle, euroc_frames):
+def test_lk_reverse_initial_flow_bit_exact(lib, oracle, euroc_frames, lk_kernel):
     from vins_fast_b200 import ops
     _, l0, _ = euroc_frames[0]
     _, l1, _ = euroc_frames[1]
@@ -87,7 +96,7 @@ def test_lk_reverse_initial_flow_bit_exact(lib, oracle, euroc_frames):
 
 
 @pytest.mark.parametrize("level", [0, 1, 4])
-def test_lk_levels_and_small_images(lib, oracle, euroc_frames, level):
+def test_lk_levels_and_small_images(lib, oracle, euroc_frames, level, lk_kernel):
     from vins_fast_b200 import ops
     a = _crop(euroc_frames[3][1], 200, 260)
     b = _crop(euroc_frames[4][1], 200, 260)
@@ -98,7 +107,7 @@ def test_lk_levels_and_small_images(lib, oracle, euroc_frames, level):
     assert np.array_equal(q.view(np.uint32), rq.view(np.uint32))
 
 
-def test_lk_six_levels_many_points(lib, oracle):
+def test_lk_six_levels_many_points(lib, oracle, lk_kernel):
     """Six pyramid levels and more points than fit on the GPU at once: the launch takes the variant of the prologue
     that forms the terms of A on the fly instead of staging them in shared memory (vf_lk.cu: lk_plan_staged)."""
     from vins_fast_b200 import ops
@@ -114,7 +123,7 @@ def test_lk_six_levels_many_points(lib, oracle):
     assert st.sum() > 300
 
 
-def test_lk_textureless_and_empty(lib, oracle):
+def test_lk_textureless_and_empty(lib, oracle, lk_kernel):
     from vins_fast_b200 import ops
     flat = np.full((120, 160), 77, np.uint8)
     pts = np.array([[50, 50], [80.5, 60.25]], np.float32)
@@ -124,6 +133,21 @@ def test_lk_textureless_and_empty(lib, oracle):
     assert np.array_equal(q.view(np.uint32), rq.view(np.uint32))
     q, st = ops.lk(flat, flat, np.zeros((0, 2), np.float32), 3)
     assert q.shape == (0, 2) and st.shape == (0,)
+
+
+def test_lk_high_contrast_takes_the_ordered_chains(lib, oracle, lk_kernel):
+    """A black / white checker moved by half a pixel: |J - I| |grad| sums far beyond 2^24, so the iterations leave the
+    exact-integer shortcut and run OpenCV's ordered float chains; positions, status and iteration counts still bit-equal."""
+    from vins_fast_b200 import ops
+    yy, xx = np.mgrid[0:240, 0:320]
+    a = (((xx // 5 + yy // 5) & 1) * 255).astype(np.uint8)
+    b = np.roll(a, (1, 2), (0, 1))
+    b[::2] = (b[::2].astype(np.int32) * 3 // 4).astype(np.uint8)
+    pts = _lk_points(a, 300, 5)
+    q, st, it = ops.lk(a, b, pts, 3, return_iters=True)
+    rq, rst, rit = oracle.lk(oracle.Pyramid(a), oracle.Pyramid(b), pts, 3, 21, return_iters=True)
+    assert np.array_equal(st, rst) and np.array_equal(it, rit)
+    assert np.array_equal(q.view(np.uint32), rq.view(np.uint32)), np.abs(q - rq).max()
 
 
 @pytest.fixture(params=[1, 2], ids=["tiles", "strips"])

@@ -74,6 +74,16 @@ def test_euroc_sequence_with_either_pyramid_kernel(lib, oracle, euroc_frames, mo
         ops.set_pyramid_kernel(0)
 
 
+def test_euroc_sequence_with_the_cta_lk_kernels(lib, oracle, euroc_frames):
+    """The tracker on the 4-warp-per-feature LK kernels (vf_lk.cu), kept as the A/B partner of the default warp-per-feature ones."""
+    from vins_fast_b200 import ops
+    ops.set_lk_kernel(1)
+    try:
+        _run_pair(oracle, euroc_frames[:8], 752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1)
+    finally:
+        ops.set_lk_kernel(0)
+
+
 def test_pinhole_720p_level4(lib, oracle):
     from vins_fast_b200.synth import StereoSequence
     seq = StereoSequence(2, 1280, 720)

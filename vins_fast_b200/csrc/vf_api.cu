@@ -1091,6 +1091,12 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
     return VF_OK;
 }
 
+vf_status vf_debug_set_lk_kernel(int32_t mode) {
+    if (mode < 0 || mode > 1) return fail(nullptr, VF_ERR_INVALID_ARG, "LK kernel mode must be 0 or 1");
+    set_lk_kernel_mode(mode);
+    return VF_OK;
+}
+
 vf_status vf_debug_set_pyramid_kernel(int32_t mode) {
     if (mode < 0 || mode > 2) return fail(nullptr, VF_ERR_INVALID_ARG, "pyramid kernel mode must be 0, 1 or 2");
     set_pyramid_kernel_mode(mode);

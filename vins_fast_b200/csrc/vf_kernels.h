@@ -90,6 +90,15 @@ cudaError_t lk_prepare();   // opt in to the LK kernels' dynamic shared memory (
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream);
 
+// ---- vf_lk_warp.cu: the same passes with one warp per feature ----
+void set_lk_kernel_mode(int mode);        // 0 = one warp per feature (default), 1 = one 4-warp CTA per feature (A/B, parity tests)
+bool lk_use_warp_kernel();
+cudaError_t lk_warp_prepare();
+void launch_lk_temporal_warp(const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream);
+void launch_lk_stereo_warp(const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream);
+void launch_lk_op_warp(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status, int* iters, int n,
+                       int max_level, int use_initial_flow, cudaStream_t stream);
+
 // ---- vf_corners.cu ----
 void set_response_kernel_mode(int mode);   // 0 auto, 1 tiles, 2 strips (parity tests)
 void launch_response_nms(const DevBatch* d_batch, const DevBatch& h, int parity, cudaStream_t stream);

@@ -28,6 +28,7 @@
 #include "vf_camera.cuh"
 #include "vf_common.cuh"
 #include "vf_kernels.h"
+#include "vf_lk_common.cuh"
 
 namespace vf {
 
@@ -36,18 +37,7 @@ constexpr int kLkThreads = 128;              // 4 warps: one per SM sub-partitio
 constexpr int kLkWarps = kLkThreads / 32;
 constexpr int kLkItems = 256;                // work items of a pass are numbered 0..255; thread t owns items t, t + kLkThreads, ...
 constexpr int kIpt = kLkItems / kLkThreads;  // items per thread
-constexpr int kTileI = 24;                   // staged I tile (window + bilinear tap + Scharr ring)
-constexpr int kTileD = 22;                   // derivative tile (window + bilinear tap)
-constexpr int kJMargin = 5;                  // staged J tile = 22x22 taps + this margin on every side
-constexpr int kTileJ = 22 + 2 * kJMargin;    // 32
 constexpr int kTail = 105;                   // 21 rows x 5 tail columns
-constexpr int kExact = 1 << 24;              // below this every integer is a float
-
-struct LevelRef {
-    const uint8_t* p;
-    int w, h, pitch;
-};
-
 // Per-level quantities that depend on the source point only (computed once per pass by the prologue).
 struct alignas(16) LevelGeo {
     int w00, w01, w10, w11;        // bilinear weights of the source point
@@ -110,8 +100,6 @@ static bool lk_plan_staged(int n_levels, long long n_ctas) {
 #ifndef VF_LK_ABLATE
 #define VF_LK_ABLATE 0
 #endif
-#define VF_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
-
 // Optional phase timing (build with -DVF_LK_TIMING): every thread reads the clock at a mark (no divergence), thread 0
 // accumulates per-phase cycles in shared memory and flushes them to vf_lk_timing[k] / vf_lk_timing[16 + k] at the end.
 #ifdef VF_LK_TIMING
@@ -131,52 +119,6 @@ __device__ __forceinline__ unsigned int vf_smid() { unsigned int r; asm volatile
 #else
 #define LK_TF(k) do { } while (0)
 #endif
-
-// 1.f / (1 << level), exactly (OpenCV: (float)(1. / (1 << level))), without an IEEE division on the level chain
-__device__ __forceinline__ float pow2_neg(int level) { return __int_as_float((127 - level) << 23); }
-
-__device__ __forceinline__ void bilinear_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
-    const float one_a = __fsub_rn(1.f, a), one_b = __fsub_rn(1.f, b);
-    w00 = __float2int_rn(__fmul_rn(__fmul_rn(one_a, one_b), 16384.f));
-    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, one_b), 16384.f));
-    w10 = __float2int_rn(__fmul_rn(__fmul_rn(one_a, b), 16384.f));
-    w11 = 16384 - w00 - w01 - w10;
-}
-
-// One row of NW*4 pixels of a level starting at column x0 of row y, as NW packed words.  The levels carry a REFLECT_101
-// border in HBM (vf_common.cuh: kPyrPad), so any row a window can touch is fetched with NW (+1 when unaligned) aligned
-// 32-bit loads and realigned with funnel shifts.  Callers keep -26 <= x0, x0 + 4*NW <= w + 26 (+-3 for the alignment)
-// and -26 <= y < h + 26.
-template <int NW>
-__device__ __forceinline__ void load_row_words(const LevelRef& L, int x0, int y, uint32_t (&out)[NW]) {
-    const uint8_t* row = L.p + (ptrdiff_t)y * L.pitch;
-    const int m = x0 & 3;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row + (x0 - m));   // level origin and pitch are 16-byte aligned
-    uint32_t w[NW + 1];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) w[k] = __ldg(wp + k);
-    w[NW] = m ? __ldg(wp + NW) : 0u;
-#pragma unroll
-    for (int k = 0; k < NW; ++k) out[k] = __funnelshift_r(w[k], w[k + 1], 8 * m);
-}
-// The same fetch in two halves for a prefetch: issue_row_words only issues the loads (the raw words stay in flight while
-// the caller does other work -- realigning them at once would stall the warp on the memory round trip), align_row_word
-// realigns one word when the data is finally consumed.  Reads one word more than load_row_words (inside the border).
-template <int NW>
-__device__ __forceinline__ void issue_row_words(const LevelRef& L, int x0, int y, uint32_t (&raw)[NW + 1]) {
-    const uint8_t* row = L.p + (ptrdiff_t)y * L.pitch;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row + (x0 - (x0 & 3)));
-#pragma unroll
-    for (int k = 0; k <= NW; ++k) raw[k] = __ldg(wp + k);
-}
-
-// Origin of a speculative (prefetched) J tile, clamped so that the 32x32 tile stays inside the filled border.
-__device__ __forceinline__ int clamp_tile_origin(int o, int n) { return min(max(o, -(kPyrPadFill - 2)), n + kPyrPadFill - 2 - kTileJ); }
-
-struct LkResult {
-    float x, y;
-    int status;
-};
 
 // Warp-level value of one summation chain whose `n` integer terms are produced by term(k), k = 0..n-1 in OpenCV's
 // accumulation order.  Exact integer path when sum|t| < 2^24, else the ordered float chain (all lanes run it
@@ -713,16 +655,6 @@ __device__ __forceinline__ void lk_timing_flush(LkSmem& sm) {
 #endif
 }
 
-__device__ __forceinline__ bool in_border(float2 p, int rows, int cols) {   // feature_tracker.cpp:20-25
-    const int x = __float2int_rn(p.x), y = __float2int_rn(p.y);
-    return 1 <= x && x < cols - 1 && 1 <= y && y < rows - 1;
-}
-__device__ __forceinline__ double pt_distance(float2 a, float2 b) {         // feature_tracker.cpp:457-462
-    const double dx = (double)__fsub_rn(a.x, b.x), dy = (double)__fsub_rn(a.y, b.y);
-    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-}
-
-
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
 __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
     pdl_wait(); pdl_release();
@@ -782,11 +714,6 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_co
 #endif
     }
     lk_timing_flush(sm);
-}
-
-// velocity of ComputeKpsVelocity (:323-363): (cur - prev) as float, / dt as double, stored as float.
-__device__ __forceinline__ float2 velocity(float2 cur, float2 prev, double dt) {
-    return make_float2((float)((double)__fsub_rn(cur.x, prev.x) / dt), (float)((double)__fsub_rn(cur.y, prev.y) / dt));
 }
 
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
@@ -916,6 +843,7 @@ cudaError_t lk_prepare() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
+    if ((e = lk_warp_prepare()) != cudaSuccess) return e;
     // same carveout as every other kernel of the library (see corners_prepare)
     if ((e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
@@ -925,11 +853,13 @@ cudaError_t lk_prepare() {
 }
 
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
+    if (lk_use_warp_kernel()) { launch_lk_temporal_warp(h, parity, cur, prev, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);   // bit 1 of the parity argument
     launch_kernel(lk_temporal_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, prev);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
+    if (lk_use_warp_kernel()) { launch_lk_stereo_warp(h, parity, cur, dt_host, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);
     launch_kernel(lk_stereo_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, dt_host);
@@ -941,6 +871,7 @@ void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parit
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {
     if (n <= 0) return;
+    if (lk_use_warp_kernel()) { launch_lk_op_warp(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow, stream); return; }
     const int nlv = (max_level < prev.n_levels - 1 ? max_level : prev.n_levels - 1) + 1;
     const bool staged = lk_plan_staged(nlv, n);                                     // bit 1 of the flow flag
     lk_op_kernel<<<n, kLkThreads, lk_smem_bytes(nlv, staged), stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level,

@@ -58,6 +58,11 @@ def set_response_kernel(mode: int) -> None:
     check(load().vf_debug_set_response_kernel(int(mode)))
 
 
+def set_lk_kernel(mode: int) -> None:
+    """A/B and parity tests: 0 = one warp per feature (default), 1 = one 4-warp CTA per feature (identical results)."""
+    check(load().vf_debug_set_lk_kernel(int(mode)))
+
+
 def set_pyramid_kernel(mode: int) -> None:
     """Parity tests: 0 = pick the pyramid kernel by size, 1 = fused multi-level kernel, 2 = streaming TMA kernel (identical results)."""
     check(load().vf_debug_set_pyramid_kernel(int(mode)))
