@@ -206,7 +206,9 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
  * 1 = tiles (small frames), 2 = strips (large frames / batches).  Both give identical results. */
 vf_status vf_debug_set_response_kernel(int32_t mode);
 /* Which Lucas-Kanade kernels the library launches (process-wide; A/B measurements and parity tests; takes effect for handles
- * created afterwards): 0 = one warp per feature (default), 1 = one 4-warp CTA per feature.  Identical results. */
+ * created afterwards): 0 = by launch size (default: one 4-warp CTA per feature with a block barrier per iteration while every
+ * feature has an SM to itself, one warp per feature once features queue up per SM); 1 = the former whatever the size; 2 / 3 =
+ * warp-level passes with one warp per feature / with a cooperating 4-warp CTA per feature whatever the size.  Identical results. */
 vf_status vf_debug_set_lk_kernel(int32_t mode);
 /* Which pyramid kernel the library launches (process-wide; parity tests only; takes effect for handles created afterwards):
  * 0 = by size (default), 1 = fused multi-level kernel only, 2 = streaming TMA kernel for every level transition. */

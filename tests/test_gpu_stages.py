@@ -59,9 +59,10 @@ def _lk_points(img, n, seed):
     return np.concatenate([pts, edge])
 
 
-@pytest.fixture(params=[0, 1], ids=["warp", "cta"])
+@pytest.fixture(params=[2, 3, 1], ids=["warp", "coop", "cta"])
 def lk_kernel(request, lib):
-    """Both Lucas-Kanade kernels (one warp per feature: default; one 4-warp CTA per feature) must give the same bits."""
+    """All Lucas-Kanade kernels (warp-level passes with one warp / one cooperating CTA per feature -- the library picks by launch
+    size -- and the block-barrier kernels of vf_lk.cu) must give the same bits."""
     from vins_fast_b200 import ops
     ops.set_lk_kernel(request.param)
     yield request.param

@@ -74,10 +74,12 @@ def test_euroc_sequence_with_either_pyramid_kernel(lib, oracle, euroc_frames, mo
         ops.set_pyramid_kernel(0)
 
 
-def test_euroc_sequence_with_the_cta_lk_kernels(lib, oracle, euroc_frames):
-    """The tracker on the 4-warp-per-feature LK kernels (vf_lk.cu), kept as the A/B partner of the default warp-per-feature ones."""
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["cta", "warp", "coop"])
+def test_euroc_sequence_with_either_lk_kernel(lib, oracle, euroc_frames, mode):
+    """The tracker with the LK kernels forced: block-barrier kernels of vf_lk.cu / warp-level passes with one warp per feature
+    (what batches take) / with one cooperating CTA per feature (what a single stream takes)."""
     from vins_fast_b200 import ops
-    ops.set_lk_kernel(1)
+    ops.set_lk_kernel(mode)
     try:
         _run_pair(oracle, euroc_frames[:8], 752, 480, 150, 30, 1, EUROC_CAM0, EUROC_CAM1)
     finally:

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvinsfast_b200.so")
+LIB_PATH = os.environ.get("VF_LIB") or os.path.join(HERE, "libvinsfast_b200.so")   # VF_LIB: a measurement build of the same library
 
 VF_OK, VF_ERR_INVALID_ARG, VF_ERR_CUDA, VF_ERR_IO, VF_ERR_PARSE, VF_ERR_STATE = range(6)
 VF_CAM_MEI, VF_CAM_PINHOLE = 0, 1

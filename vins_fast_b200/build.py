@@ -53,6 +53,18 @@ def needs_build() -> bool:
         return f.read().strip() != source_hash()
 
 
+def build_timing() -> str:
+    """Measurement aid: a second library with the LK phase counters compiled in (-DVF_LKW_TIMING), selected with VF_LIB=<path>."""
+    out = os.path.join(HERE, "libvinsfast_b200_timing.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-DVF_LKW_TIMING", "-I", os.path.join(ROOT, "include"), "-o", out] + srcs, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building the timing library")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -73,4 +85,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    if "--timing" in sys.argv:
+        print(build_timing())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1092,7 +1092,7 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
 }
 
 vf_status vf_debug_set_lk_kernel(int32_t mode) {
-    if (mode < 0 || mode > 1) return fail(nullptr, VF_ERR_INVALID_ARG, "LK kernel mode must be 0 or 1");
+    if (mode < 0 || mode > 3) return fail(nullptr, VF_ERR_INVALID_ARG, "LK kernel mode must be 0 .. 3");
     set_lk_kernel_mode(mode);
     return VF_OK;
 }

@@ -91,8 +91,8 @@ void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_p
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream);
 
 // ---- vf_lk_warp.cu: the same passes with one warp per feature ----
-void set_lk_kernel_mode(int mode);        // 0 = one warp per feature (default), 1 = one 4-warp CTA per feature (A/B, parity tests)
-bool lk_use_warp_kernel();
+void set_lk_kernel_mode(int mode);        // 0 = warp-level passes (COOP / BATCH by size), 1 = vf_lk.cu kernels, 2 = BATCH, 3 = COOP (A/B, parity tests)
+bool lk_use_warp_kernel(long long n_features);
 cudaError_t lk_warp_prepare();
 void launch_lk_temporal_warp(const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream);
 void launch_lk_stereo_warp(const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream);

@@ -853,13 +853,13 @@ cudaError_t lk_prepare() {
 }
 
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
-    if (lk_use_warp_kernel()) { launch_lk_temporal_warp(h, parity, cur, prev, stream); return; }
+    if (lk_use_warp_kernel((long long)h.cap * h.n_streams)) { launch_lk_temporal_warp(h, parity, cur, prev, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);   // bit 1 of the parity argument
     launch_kernel(lk_temporal_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, prev);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
-    if (lk_use_warp_kernel()) { launch_lk_stereo_warp(h, parity, cur, dt_host, stream); return; }
+    if (lk_use_warp_kernel((long long)h.cap * h.n_streams)) { launch_lk_stereo_warp(h, parity, cur, dt_host, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);
     launch_kernel(lk_stereo_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, dt_host);
@@ -871,7 +871,7 @@ void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parit
 void launch_lk_op(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status,
                   int* iters, int n, int max_level, int use_initial_flow, cudaStream_t stream) {
     if (n <= 0) return;
-    if (lk_use_warp_kernel()) { launch_lk_op_warp(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow, stream); return; }
+    if (lk_use_warp_kernel(n)) { launch_lk_op_warp(prev, next, prev_pts, next_pts, status, iters, n, max_level, use_initial_flow, stream); return; }
     const int nlv = (max_level < prev.n_levels - 1 ? max_level : prev.n_levels - 1) + 1;
     const bool staged = lk_plan_staged(nlv, n);                                     // bit 1 of the flow flag
     lk_op_kernel<<<n, kLkThreads, lk_smem_bytes(nlv, staged), stream>>>(prev, next, prev_pts, next_pts, status, iters, n, max_level,

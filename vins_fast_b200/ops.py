@@ -59,7 +59,8 @@ def set_response_kernel(mode: int) -> None:
 
 
 def set_lk_kernel(mode: int) -> None:
-    """A/B and parity tests: 0 = one warp per feature (default), 1 = one 4-warp CTA per feature (identical results)."""
+    """A/B and parity tests: 0 = warp-level passes scheduled by launch size (default), 1 = the block-barrier kernels of vf_lk.cu,
+    2 = one warp per feature, 3 = one 4-warp CTA per feature with warp-level passes (identical results)."""
     check(load().vf_debug_set_lk_kernel(int(mode)))
 
 
