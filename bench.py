@@ -574,6 +574,19 @@ def main():
             multi = {"streams_per_gpu": S, "steps": steps_m, "value": world * S * steps_m / (ms_m * 1e-3), "unit": "frames/s",
                      "us_per_frame_per_stream": ms_m * 1e3 / (steps_m * S), "ms_per_step": ms_m / steps_m,
                      "regions_ms": m_dev, "launches_per_step": mb.launches_per_frame}
+            # per-kernel device times of the batched step (CUDA events around every kernel, plain launches, synchronous frames)
+            mb.reset()
+            mb.set_profiling(True)
+            macc, mcnt = {}, 0
+            for k in range(12):
+                mb.enqueue_device(mt(k), base + k * frame_bytes, base + k * frame_bytes + H * W, W, frame_bytes)
+                mb.fetch_counts()
+                if k >= 4:
+                    for name, ms in mb.stage_times_ms().items():
+                        macc[name] = macc.get(name, 0.0) + ms * 1e3
+                    mcnt += 1
+            mb.set_profiling(False)
+            multi["stages_us"] = {k: v / max(mcnt, 1) for k, v in macc.items()}
             mb.close()
 
         # ---------------- BASELINE configs 3, 4 and 5 as measured workloads ----------------
@@ -744,8 +757,18 @@ def main():
     roofline["streaming_kernels"] = {k: {"achieved_GBps": alg_bytes[k] / (kernels[k] * 1e-6) / 1e9,
                                          "frac": alg_bytes[k] / (kernels[k] * 1e-6) / 1e9 / peak}
                                      for k in ("pyrdown_left", "response_nms", "mask_and_max") if kernels.get(k, 0) > 0}
-    if isinstance(ncu.get("lk_stereo_S64"), dict):
-        roofline["batched"] = dict(ncu["lk_stereo_S64"], note="ncu capture of lk_stereo in the 64-stream batch (profiles/r2_lk_issue.json)")
+    if isinstance(ncu.get("lk_stereo_S64"), dict) and multi and multi.get("stages_us", {}).get("lk_stereo", 0) > 0 and multi["streams_per_gpu"] == 64:
+        # the launch that fills the machine: 64 streams x 150 features, one warp per feature (vf_lk_warp.cu).  Warp instructions
+        # per launch from the committed ncu capture of exactly this launch, duration measured live (events, profiling mode).
+        rb = ncu["lk_stereo_S64"]
+        us = multi["stages_us"]["lk_stereo"]
+        a_b = rb["warp_instructions"] / (us * 1e-6) / 1e9
+        roofline["batched"] = {"kernel": "lk_stereo_warp_kernel (64 streams)", "bound": "issue", "kernel_us": us, "achieved": a_b, "peak": issue_peak,
+                               "unit": "Gwarp-inst/s", "frac": a_b / issue_peak, "traffic": rb.get("dram_bytes"),
+                               "warp_instructions_per_launch": rb["warp_instructions"], "issue_active_pct_ncu": rb.get("issue_active_pct"),
+                               "warps_active_pct_ncu": rb.get("warps_active_pct"), "top_stalls_ncu": rb.get("top_stalls"),
+                               "registers_per_thread": rb.get("registers_per_thread"),
+                               "note": "profiles/r2_lk_issue.json + profiles/r2_ncu_lk_batch_summary.txt"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
