@@ -79,9 +79,9 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.idx, self.sm, self.mx, self.reasons, self.stop = gpu_index, [], [], set(), False
-        self.t = None
+        self.t, self.nv = None, None
 
-    def _nvml(self):
+    def _nvml_open(self):
         import pynvml as nv
         nv.nvmlInit()
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -90,12 +90,26 @@ class ClockSampler:
         mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
         names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                  "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-        while not self.stop:
+        self.nv = (nv, h, mx, names)
+
+    def sample(self):
+        """One sample now (also called by the timed loops themselves, from inside a region: a 1.4 ms region is shorter than
+        the polling thread's period)."""
+        if self.nv is None:
+            return
+        nv, h, mx, names = self.nv
+        try:
             self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)); self.mx.append(mx)
             r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             for k, bit in names.items():
                 if r & bit:
                     self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _nvml(self):
+        while not self.stop:
+            self.sample()
             time.sleep(SAMPLE_S)
 
     def _smi(self):
@@ -112,15 +126,18 @@ class ClockSampler:
                 return
 
     def _run(self):
-        try:
+        if self.nv is not None:
             self._nvml()
-        except Exception:
+        else:
             self._smi()
 
     def __enter__(self):
+        try:                      # NVML is opened HERE, synchronously: importing / initialising it takes longer than a short region
+            self._nvml_open()
+        except Exception:
+            self.nv = None
         self.t = threading.Thread(target=self._run, daemon=True)
         self.t.start()
-        time.sleep(0.01)
         return self
 
     def __exit__(self, *a):
@@ -544,7 +561,10 @@ def main():
                     vf.load().vf_batch_trace_get(tb._h, tbuf, 256)
                     if k >= Wm:
                         a = np.array(list(tbuf), np.uint64)[:192].reshape(6, 16, 2)[k % 6, :14]
-                        tacc.append((a - a[:, 0].min()).astype(np.int64))
+                        unused = a[:, 1] == 0                                # kernels this plan does not launch
+                        a = a.astype(np.int64) - int(a[~unused, 0].min())
+                        a[unused] = 0
+                        tacc.append(a)
                 tm = np.mean(tacc, 0) / 1e3
                 timeline = {"kernels": {n: {"start_us": round(float(tm[i, 0]), 2), "end_us": round(float(tm[i, 1]), 2),
                                             "us": round(float(tm[i, 1] - tm[i, 0]), 2)} for i, n in enumerate(tnames)},

@@ -65,7 +65,10 @@ for k in range(n_frames):
     vf.load().vf_batch_trace_get(b._h, tbuf, 256)
     if k >= 3:
         a = np.array(list(tbuf), np.uint64)[:192].reshape(6, 16, 2)[k % 6, :14]
-        tacc.append((a - a[:, 0].min()).astype(np.int64))
+        unused = a[:, 1] == 0                                # kernels this plan does not launch
+        a = a.astype(np.int64) - int(a[~unused, 0].min())
+        a[unused] = 0
+        tacc.append(a)
         ph = np.array(list(tbuf), np.uint64)[224 + 8:224 + 13].astype(np.int64)   # select_tracked's phase stamps (stream 0)
         sel_acc.append(np.diff(ph))
 tm = np.mean(tacc, 0) / 1e3

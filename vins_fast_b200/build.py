@@ -65,6 +65,18 @@ def build_timing() -> str:
     return out
 
 
+def build_variant(name: str, defines: list) -> str:
+    """Measurement aid: libvinsfast_b200_<name>.so built with extra -D flags, selected with VF_LIB=<path> (A/B runs on the GPU box)."""
+    out = os.path.join(HERE, f"libvinsfast_b200_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run([nvcc] + NVCC_FLAGS + list(defines) + ["-I", os.path.join(ROOT, "include"), "-o", out] + srcs, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed building the {name} variant")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -85,6 +97,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:      # python -m vins_fast_b200.build --variant NAME -DX=1 -DY=2
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], [a for a in sys.argv[i + 2:] if a.startswith("-D")]))
+        sys.exit(0)
     if "--timing" in sys.argv:
         print(build_timing())
         sys.exit(0)

@@ -32,7 +32,10 @@
 
 namespace vf {
 
-constexpr int kLkThreads = 128;              // 4 warps: one per SM sub-partition; a second CTA (the other LK kernel of a
+#ifndef VF_LK_THREADS
+#define VF_LK_THREADS 128                    // (A/B aid: 256 threads measured no faster -- the iteration is bound by its dependent chain)
+#endif
+constexpr int kLkThreads = VF_LK_THREADS;    // 4 warps: one per SM sub-partition; a second CTA (the other LK kernel of a
                                              // pipelined frame pair) interleaves with it instead of queueing behind it
 constexpr int kLkWarps = kLkThreads / 32;
 constexpr int kLkItems = 256;                // work items of a pass are numbered 0..255; thread t owns items t, t + kLkThreads, ...
@@ -144,6 +147,67 @@ __device__ __forceinline__ float chain_value(int n, F term) {
 
 extern __shared__ __align__(16) unsigned char lk_smem_raw[];
 __device__ __forceinline__ float* lk_terms_a(LkSmem&, int off) { return reinterpret_cast<float*>(lk_smem_raw + off); }   // LkSmem sits at offset 0
+
+// Cold path of an iteration (the global exactness bound failed, ~8 % of the iterations): spill the terms in OpenCV's
+// accumulation order and run the 10 ordered float chains, one lane per chain.  Returns (ib1, ib2).  Out of line on purpose.
+struct LkTerms { int ex0[kIpt], ey0[kIpt], ex1[kIpt], ey1[kIpt]; };   // by value: an array passed by address would live in local memory
+__device__ __noinline__ float2 lk_spill_chains(LkSmem& sm, const LkTerms tm) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int (&ex0)[kIpt] = tm.ex0; const int (&ey0)[kIpt] = tm.ey0; const int (&ex1)[kIpt] = tm.ex1; const int (&ey1)[kIpt] = tm.ey1;
+#pragma unroll
+    for (int q = 0; q < kIpt; ++q) {
+        const int it = tid + q * kLkThreads;
+        if (it < 168) {
+            const int y = it >> 3, g = (it >> 2) & 1, c = it & 3, slot = y * 2 + g;
+            sm.termsB[(2 * c + 0) * kChainA + slot] = (float)(ex0[q] + ex1[q]);      // v_cvt_f32 of the pmaddwd pair sum
+            sm.termsB[(2 * c + 1) * kChainA + slot] = (float)(ey0[q] + ey1[q]);
+        } else if (it >= 192 && it < 192 + 53) {
+            const int t = 2 * (it - 192);
+            sm.termsB[8 * kChainA + t] = (float)ex0[q]; sm.termsB[9 * kChainA + t] = (float)ey0[q];
+            if (t + 1 < kTail) { sm.termsB[8 * kChainA + t + 1] = (float)ex1[q]; sm.termsB[9 * kChainA + t + 1] = (float)ey1[q]; }
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const float4* src = reinterpret_cast<const float4*>(sm.termsB + min(lane, 9) * kChainA);
+        float acc = 0.f;
+        if (lane < 8) {           // SIMD-lane chains: 42 terms (11 vector loads, zero padded)
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+                const float4 v = src[i];
+                acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+            }
+        } else {                  // scalar tails: 105 terms
+#pragma unroll
+            for (int i = 0; i < kChainA / 4; ++i) {
+                const float4 v = src[i];
+                acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+            }
+        }
+        if (lane < 10) sm.chainB[lane] = acc;
+    }
+    __syncthreads();
+    const float4 k0 = *reinterpret_cast<const float4*>(sm.chainB), k1 = *reinterpret_cast<const float4*>(sm.chainB + 4);
+    const float2 k2 = *reinterpret_cast<const float2*>(sm.chainB + 8);
+    // qb0+qb1 -> (s0,s1,s2,s3); ib1 += (s0+0)+(s2+0); ib2 += (s1+0)+(s3+0)
+    const float s0 = __fadd_rn(k0.x, k1.x), s1 = __fadd_rn(k0.y, k1.y);
+    const float s2 = __fadd_rn(k0.z, k1.z), s3 = __fadd_rn(k0.w, k1.w);
+    return make_float2(__fadd_rn(k2.x, __fadd_rn(s0, s2)), __fadd_rn(k2.y, __fadd_rn(s1, s3)));
+}
+
+// Cold path of an iteration: the window left the staged tile of J, one warp re-stages it around the new origin.  Out of line.
+__device__ __noinline__ void lk_restage_tile(LkSmem& sm, int ja, int level, int jbuf, int jx0, int jy0) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();    // everybody is done with the current tile
+    if (wid == kLkWarps - 2) {
+        uint32_t v[kTileJ / 4];
+        load_row_words<kTileJ / 4>(sm.pyr[ja][level], jx0, jy0 + lane, v);
+        uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
+        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+    __syncthreads();
+}
 
 // One calcOpticalFlowPyrLK for one point, executed cooperatively by the CTA (all threads pass identical
 // arguments and return identical results).  ia / ja select the source and target pyramids in sm.pyr.
@@ -443,15 +507,7 @@ __device__ __noinline__ LkResult lk_track_point_impl(LkSmem& sm, int ia, int ja,
                 }
                 // the window left the staged tile: re-centre it (uniform branch)
                 jx0 = inx - kJMargin; jy0 = iny - kJMargin;
-                __syncthreads();    // everybody is done with the current tile
-                if (wid == kLkWarps - 2) {
-                    uint32_t v[kTileJ / 4];
-                    load_row_words<kTileJ / 4>(LJ, jx0, jy0 + lane, v);
-                    uint4* dst = reinterpret_cast<uint4*>(sm.tileJ[jbuf] + lane * kTileJ);
-                    dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
-                    dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
-                }
-                __syncthreads();
+                lk_restage_tile(sm, ja, level, jbuf, jx0, jy0);
                 lox = max(-kWin, jx0); hix = min(jcols - 1, jx0 + kTileJ - kTileD);
                 loy = max(-kWin, jy0); hiy = min(jrows - 1, jy0 + kTileJ - kTileD);
             }
@@ -501,47 +557,12 @@ __device__ __noinline__ LkResult lk_track_point_impl(LkSmem& sm, int ia, int ja,
                 ib1 = (float)bx; ib2 = (float)by;
                 ++fast;
             } else {
-                // spill the terms in OpenCV's accumulation order and run the 10 ordered float chains, one lane per chain
+                // (cold, out of line: keeps the hot loop compact in the instruction caches)
+                LkTerms tm;
 #pragma unroll
-                for (int q = 0; q < kIpt; ++q) {
-                    const int it = tid + q * kLkThreads;
-                    if (it < 168) {
-                        const int y = it >> 3, g = (it >> 2) & 1, c = it & 3, slot = y * 2 + g;
-                        sm.termsB[(2 * c + 0) * kChainA + slot] = (float)(ex0[q] + ex1[q]);      // v_cvt_f32 of the pmaddwd pair sum
-                        sm.termsB[(2 * c + 1) * kChainA + slot] = (float)(ey0[q] + ey1[q]);
-                    } else if (it >= 192 && it < 192 + 53) {
-                        const int t = 2 * (it - 192);
-                        sm.termsB[8 * kChainA + t] = (float)ex0[q]; sm.termsB[9 * kChainA + t] = (float)ey0[q];
-                        if (t + 1 < kTail) { sm.termsB[8 * kChainA + t + 1] = (float)ex1[q]; sm.termsB[9 * kChainA + t + 1] = (float)ey1[q]; }
-                    }
-                }
-                __syncthreads();
-                if (wid == 0) {
-                    const float4* src = reinterpret_cast<const float4*>(sm.termsB + min(lane, 9) * kChainA);
-                    float acc = 0.f;
-                    if (lane < 8) {           // SIMD-lane chains: 42 terms (11 vector loads, zero padded)
-#pragma unroll
-                        for (int i = 0; i < 11; ++i) {
-                            const float4 v = src[i];
-                            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
-                        }
-                    } else {                  // scalar tails: 105 terms
-#pragma unroll
-                        for (int i = 0; i < kChainA / 4; ++i) {
-                            const float4 v = src[i];
-                            acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
-                        }
-                    }
-                    if (lane < 10) sm.chainB[lane] = acc;
-                }
-                __syncthreads();
-                const float4 k0 = *reinterpret_cast<const float4*>(sm.chainB), k1 = *reinterpret_cast<const float4*>(sm.chainB + 4);
-                const float2 k2 = *reinterpret_cast<const float2*>(sm.chainB + 8);
-                // qb0+qb1 -> (s0,s1,s2,s3); ib1 += (s0+0)+(s2+0); ib2 += (s1+0)+(s3+0)
-                const float s0 = __fadd_rn(k0.x, k1.x), s1 = __fadd_rn(k0.y, k1.y);
-                const float s2 = __fadd_rn(k0.z, k1.z), s3 = __fadd_rn(k0.w, k1.w);
-                ib1 = __fadd_rn(k2.x, __fadd_rn(s0, s2));
-                ib2 = __fadd_rn(k2.y, __fadd_rn(s1, s3));
+                for (int q = 0; q < kIpt; ++q) { tm.ex0[q] = ex0[q]; tm.ey0[q] = ey0[q]; tm.ex1[q] = ex1[q]; tm.ey1[q] = ey1[q]; }
+                const float2 ib = lk_spill_chains(sm, tm);
+                ib1 = ib.x; ib2 = ib.y;
                 LK_TF(8);
             }
             const float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
