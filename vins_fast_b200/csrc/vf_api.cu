@@ -55,11 +55,13 @@ struct vf_batch {
     int S = 0, device = 0;
     cudaStream_t main = nullptr, side_a = nullptr, side_b = nullptr, side_c = nullptr, side_d = nullptr, side_e = nullptr;
     bool own_main = false, serialized = false;
+    bool one_graph_sync = false;           // synchronous frames replay SEQ_FRAME_SYNC (one graph) instead of four
+    bool corner_after_pyr = false;         // ... whose corner stage starts behind the left pyramid instead of beside it
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
     cudaEvent_t ev_input = nullptr;        // device-input ordering: recorded on the caller's stream / handed in by the caller
     cudaEvent_t ev_user_input = nullptr;   // vf_batch_set_input_event: the next frame's uploads wait for it (not owned)
     cudaEvent_t ev_fork = nullptr, ev_right = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr}, ev_img = nullptr,
-                ev_sel = nullptr, ev_un = nullptr, ev_pyrl = nullptr, ev_scat = nullptr,
+                ev_sel = nullptr, ev_un = nullptr, ev_pyrl = nullptr, ev_scat = nullptr, ev_rimg = nullptr, ev_fork2 = nullptr, ev_pyr_sync = nullptr,
                 ev_chain[2] = {nullptr, nullptr};
     uint8_t* stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // unpadded upload targets [camera][parity]: [S][H][stage_pitch]
     int stage_pitch = 0;
@@ -75,7 +77,7 @@ struct vf_batch {
     long frame = 0;
     long known_done = -1;                          // newest frame index a fetch has seen complete (frames complete in order)
     int last_parity = -1;
-    cudaGraphExec_t graph[7][6] = {};
+    cudaGraphExec_t graph[8][6] = {};
     int pyr_launches = 1;   // one per frame % 6 (parity x pyramid ring slot)
     int launches = 0;
     std::string err;
@@ -217,7 +219,7 @@ void destroy_batch(vf_batch* b) {
     if (!b) return;
     DeviceGuard g(b->device);
     sync_all(b);
-    for (int w = 0; w < 7; ++w) for (int p = 0; p < 6; ++p) if (b->graph[w][p]) cudaGraphExecDestroy(b->graph[w][p]);
+    for (int w = 0; w < 8; ++w) for (int p = 0; p < 6; ++p) if (b->graph[w][p]) cudaGraphExecDestroy(b->graph[w][p]);
     for (void* p : b->allocs) cudaFree(p);
     if (b->d) cudaFree(b->d);
     for (int p = 0; p < 3; ++p) {
@@ -234,6 +236,9 @@ void destroy_batch(vf_batch* b) {
     if (b->ev_un) cudaEventDestroy(b->ev_un);
     if (b->ev_pyrl) cudaEventDestroy(b->ev_pyrl);
     if (b->ev_scat) cudaEventDestroy(b->ev_scat);
+    if (b->ev_rimg) cudaEventDestroy(b->ev_rimg);
+    if (b->ev_fork2) cudaEventDestroy(b->ev_fork2);
+    if (b->ev_pyr_sync) cudaEventDestroy(b->ev_pyr_sync);
     for (int p = 0; p < 2; ++p) if (b->ev_chain[p]) cudaEventDestroy(b->ev_chain[p]);
     for (int k = 0; k < 16; ++k) { if (b->st_beg[k]) cudaEventDestroy(b->st_beg[k]); if (b->st_end[k]) cudaEventDestroy(b->st_end[k]); }
     if (b->side_a && !b->serialized) cudaStreamDestroy(b->side_a);
@@ -275,7 +280,11 @@ vf_status reset_state(vf_batch* b) {
 //   SEQ_TAIL       side C, overlapped frames: stereo pass with the left undistortion on a branch (side E) beside it.
 // (A plain launch of one of these kernels costs the host 4-4.5 us -- the batch descriptor travels by value -- a graph
 //  launch 3.5 us whatever it holds.)
-enum { SEQ_CORNER = 0, SEQ_CHAIN = 1, SEQ_REST_SYNC = 2, SEQ_HEAD_SYNC = 3, SEQ_PYR_LEFT = 4, SEQ_PYR_RIGHT = 5, SEQ_TAIL = 6, SEQ_COUNT = 7 };
+//   SEQ_FRAME_SYNC a whole synchronous frame as ONE graph: head, corner stage (side A), right pyramid (side D, behind an
+//                  EXTERNAL wait for the right upload's event) and the rest, joined inside the graph -- no graph boundary
+//                  between lk_temporal and select_tracked.
+enum { SEQ_CORNER = 0, SEQ_CHAIN = 1, SEQ_REST_SYNC = 2, SEQ_HEAD_SYNC = 3, SEQ_PYR_LEFT = 4, SEQ_PYR_RIGHT = 5, SEQ_TAIL = 6, SEQ_FRAME_SYNC = 7,
+       SEQ_COUNT = 8 };
 
 }  // namespace
 namespace vf { bool& pdl_hint() { static thread_local bool on = false; return on; } }
@@ -295,13 +304,45 @@ vf_status issue_sequence(vf_batch* b, int which, int parity_, int cur, int prev,
     const DevBatch& h = b->h;
     const int parity = parity_ | (phase << 4);   // kernels take the frame parity in bit 0 and the trace slot above it
     const double* dev_dt = b->dev_dt + (size_t)phase * b->S;
-    if (which == SEQ_HEAD_SYNC) {
+    if (which == SEQ_FRAME_SYNC) {
+        // fork: the corner stage (reads the staged left image only) and the right pyramid (its upload is outside the graph:
+        // an external event wait) run beside the head of the chain
+        VF_CUDA(b, cudaEventRecord(b->ev_fork2, b->main));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_fork2, 0));
+        vf_status st = issue_sequence(b, SEQ_HEAD_SYNC, parity_, cur, prev, phase);   // records ev_pyr_sync behind the pyramid
+        if (st != VF_OK) return st;
+        // corner stage: beside the head of the chain, or (corner_after_pyr) behind the left pyramid, so that the pyramid -- on
+        // the critical path -- has the SMs to itself; the response then runs beside the temporal LK, which leaves most issue slots free
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_a, b->corner_after_pyr ? b->ev_pyr_sync : b->ev_fork2, 0));
+        if ((st = issue_sequence(b, SEQ_CORNER, parity_, cur, prev, phase)) != VF_OK) return st;
+        VF_CUDA(b, cudaEventRecord(b->ev_scat, b->side_a));
+        {   // the right upload's event is recorded outside the graph: an external wait node (the flag only exists under capture)
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            VF_CUDA(b, cudaStreamIsCapturing(b->side_d, &cs));
+            VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_rimg, cs == cudaStreamCaptureStatusActive ? cudaEventWaitExternal : 0));
+        }
+        if ((st = issue_sequence(b, SEQ_PYR_RIGHT, parity_, cur, prev, phase)) != VF_OK) return st;
+        VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
+        // select_tracked only needs lk_temporal: it follows it directly (programmatic edge); the joins come behind it
+        { StageTimer t(b, ST_SELECT_TRACKED, b->main); PdlScope pdl(b, true); launch_select_tracked(b->d, h, parity, b->main); }
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_scat, 0));
+        { StageTimer t(b, ST_MASK_AND_MAX, b->main); launch_mask_and_max(b->d, h, parity, b->main); }
+        { StageTimer t(b, ST_GFTT_SELECT, b->main); PdlScope pdl(b, true); launch_gftt_select(b->d, h, parity, b->main); }
+        VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
+        VF_CUDA(b, cudaStreamWaitEvent(b->side_e, b->ev_sel, 0));
+        { StageTimer t(b, ST_UNDISTORT_LEFT, b->side_e); launch_undistort_left(b->d, h, parity, dev_dt, b->dev_n[phase % 3], b->side_e); }
+        VF_CUDA(b, cudaEventRecord(b->ev_un, b->side_e));
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
+        { StageTimer t(b, ST_LK_STEREO, b->main); launch_lk_stereo(b->d, h, parity, cur, dev_dt, b->main); }
+        VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_un, 0));
+    } else if (which == SEQ_HEAD_SYNC) {
         {
             StageTimer t(b, ST_PYR_LEFT, b->main);
             PdlScope pdl(b, true);   // the border kernel follows the pyramid kernel
             const Level0Src src = {b->stage[0][parity_], b->stage_pitch, (size_t)b->stage_pitch * h.H};
             b->pyr_launches = launch_pyramid(h.left[cur], h.lvl_stream_stride, b->S, b->main, &src, h.trace, TR_PYR_LEFT + 16 * phase);
         }
+        VF_CUDA(b, cudaEventRecord(b->ev_pyr_sync, b->main));
         { StageTimer t(b, ST_LK_TEMPORAL, b->main); PdlScope pdl(b, true); launch_lk_temporal(b->d, h, parity, cur, prev, b->main); }
     } else if (which == SEQ_PYR_LEFT || which == SEQ_PYR_RIGHT) {
         const int cam = which == SEQ_PYR_RIGHT;
@@ -456,7 +497,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
     };
     const bool use_graph = b->cfg.use_cuda_graph && !b->profiling;
     static const char* const kSeqNames[SEQ_COUNT] = {"vf.corner_stage", "vf.chain", "vf.rest_sync", "vf.head_sync", "vf.pyramid_left",
-                                                     "vf.pyramid_right", "vf.stereo_tail"};
+                                                     "vf.pyramid_right", "vf.stereo_tail", "vf.frame_sync"};
     auto run = [&](int which, cudaStream_t st) -> vf_status {   // one of the captured kernel sequences, as a graph or directly
         NvtxRange r(kSeqNames[which]);
         if (use_graph) {
@@ -515,6 +556,19 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         // selection inside the same graph, the left undistortion on a branch beside it.
         // host order = how soon each piece reaches the GPU: the head of the critical path first (it must be queued before
         // the left upload completes), then the right image (its upload queues behind the left one anyway)
+        // the stereo pass / left undistortion read what the previous frame's wrote (velocity): if that frame was an
+        // overlapped one they ran on other streams -- unless the host has already seen it complete
+        const bool wait_prev = b->frame >= 1 && b->known_done < b->frame - 1;
+        if (b->one_graph_sync && use_graph) {
+            // ONE graph for the whole frame.  The right upload is issued first (it queues behind the left one on the link) so
+            // that its event exists when the graph is launched: the graph's right-pyramid branch waits for it as an external
+            // event, everything else starts with the left image.
+            { vf_status st = issue_right(); if (st != VF_OK) return st; }
+            VF_CUDA(b, cudaEventRecord(b->ev_rimg, b->side_d));
+            VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
+            if (wait_prev) VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 3) & 3], 0));
+            { vf_status st = run(SEQ_FRAME_SYNC, b->main); if (st != VF_OK) return st; }
+        } else {
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_img, 0));
         { vf_status st = run(SEQ_HEAD_SYNC, b->main); if (st != VF_OK) return st; }
         { vf_status st = issue_right(); if (st != VF_OK) return st; }
@@ -525,10 +579,9 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
         VF_CUDA(b, cudaStreamWaitEvent(b->side_d, b->ev_scat, 0));
         VF_CUDA(b, cudaEventRecord(b->ev_right, b->side_d));
         VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_right, 0));
-        // the stereo pass / left undistortion read what the previous frame's wrote (velocity): if that frame was an
-        // overlapped one they ran on other streams -- unless the host has already seen it complete
-        if (b->frame >= 1 && b->known_done < b->frame - 1) VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 3) & 3], 0));
+        if (wait_prev) VF_CUDA(b, cudaStreamWaitEvent(b->main, b->ev_done[(slot + 3) & 3], 0));
         { vf_status st = run(SEQ_REST_SYNC, b->main); if (st != VF_OK) return st; }
+        }
         VF_CUDA(b, cudaGetLastError());
         VF_CUDA(b, cudaEventRecord(b->ev_sel, b->main));
         VF_CUDA(b, cudaEventRecord(b->ev_chain[parity], b->main));
@@ -678,6 +731,9 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRYC(cudaEventCreateWithFlags(&b->ev_un, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_pyrl, cudaEventDisableTiming));
     TRYC(cudaEventCreateWithFlags(&b->ev_scat, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_rimg, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_fork2, cudaEventDisableTiming));
+    TRYC(cudaEventCreateWithFlags(&b->ev_pyr_sync, cudaEventDisableTiming));
     for (int p = 0; p < 2; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_chain[p], cudaEventDisableTiming));
     for (int p = 0; p < 4; ++p) TRYC(cudaEventCreateWithFlags(&b->ev_done[p], cudaEventDisableTiming));
 
@@ -718,8 +774,9 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     for (int p = 0; p < 2; ++p) {   // corner stage, double-buffered: frame k+1's response runs while frame k is on the chain
         TRY(dalloc(b, &h.eig[p], SP)); TRY(dalloc(b, &h.lmflag[p], SP));
         TRY(dalloc(b, &h.cand[p], (size_t)S * h.cand_cap)); TRY(dalloc(b, &h.cand_sorted[p], (size_t)S * h.cand_cap));
-        TRY(dalloc(b, &h.hist[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_start[p], (size_t)S * (h.n_buckets + 8)));
-        TRY(dalloc(b, &h.bucket_fill[p], (size_t)S * h.n_buckets)); TRY(dalloc(b, &h.bucket_nz[p], (size_t)S * h.n_buckets));
+        // every bucket has kHistRep counters / cursors / start offsets (vf_common.cuh)
+        TRY(dalloc(b, &h.hist[p], (size_t)S * h.n_buckets * kHistRep)); TRY(dalloc(b, &h.bucket_start[p], (size_t)S * (h.n_buckets * kHistRep + 8)));
+        TRY(dalloc(b, &h.bucket_fill[p], (size_t)S * h.n_buckets * kHistRep)); TRY(dalloc(b, &h.bucket_nz[p], (size_t)S * h.n_buckets));
         TRY(dalloc(b, &h.ccnt[p], (size_t)S * C_COUNT));
     }
     // result records, feature counts and frame intervals live in mapped pinned host memory: the kernels write / read them
@@ -738,6 +795,9 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     TRYC(cudaMalloc(&b->d, sizeof(DevBatch)));
     TRYC(cudaMemcpy(b->d, &h, sizeof(DevBatch), cudaMemcpyHostToDevice));
 
+    // synchronous frames as one graph (VF_SYNC_ONE_GRAPH=0: the four-graph plan, for A/B runs)
+    b->one_graph_sync = !(getenv("VF_SYNC_ONE_GRAPH") != nullptr && atoi(getenv("VF_SYNC_ONE_GRAPH")) == 0) && !b->serialized;
+    b->corner_after_pyr = getenv("VF_CORNER_AFTER_PYR") != nullptr && atoi(getenv("VF_CORNER_AFTER_PYR")) != 0;
     TRYC(select_tracked_prepare(cap));
     TRYC(lk_prepare());
     TRYC(corners_prepare());

@@ -50,9 +50,9 @@ struct DevBatch {
     unsigned long long* cand[2];     // [parity][S][cand_cap] local maxima, key = float_key(eig) << 32 | raster index (unordered);
                                      //               reused as sort scratch by gftt_select once scattered
     unsigned long long* cand_sorted[2]; // [parity][S][cand_cap] same keys grouped by bucket, strongest bucket first
-    unsigned int* hist[2];           // [parity][S][n_buckets]
-    unsigned int* bucket_start[2];   // [parity][S][n_buckets + 8] (one entry past the end + padding that keeps every stream 16-byte aligned) start of bucket d in cand_sorted, d = n_buckets-1-bucket (descending)
-    unsigned int* bucket_fill[2];    // [parity][S][n_buckets] scatter cursors (indexed by d)
+    unsigned int* hist[2];           // [parity][S][n_buckets][kHistRep] candidate counts; a candidate uses the copy its pixel selects (vf_common.cuh: hist_slot)
+    unsigned int* bucket_start[2];   // [parity][S][n_buckets * kHistRep + 8] (one entry past the end + padding that keeps every stream 16-byte aligned) start of (bucket d, copy) in cand_sorted at index 8 d + 7 - copy, d = n_buckets-1-bucket (descending): bucket d spans [8 d], [8 (d + 1)])
+    unsigned int* bucket_fill[2];    // [parity][S][n_buckets][kHistRep] scatter cursors (indexed like hist)
     int* bucket_nz[2];               // [parity][S][n_buckets] the non-empty d, ascending (counter C_N_NZ_BUCKETS)
     int* ccnt[2];                    // [parity][S][C_COUNT] the corner stage's own counters (C_N_LOCALMAX, C_N_NZ_BUCKETS)
     uint8_t* mask;                   // [S][H][W] SetFeatureExtractorMask

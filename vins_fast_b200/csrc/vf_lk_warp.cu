@@ -51,6 +51,9 @@ constexpr int kChains = 15;                  // 3 matrix entries x (4 SIMD-lane 
 constexpr int kProd = kWinPx + 3;            // floats per product plane (row-major 21x21)
 constexpr int kPP = 24;                      // pitch of the weighted-pixel plane P (23 x 23 values)
 constexpr int kCoopWarps = 4;
+#ifndef VF_LKW_MIN_BLOCKS
+#define VF_LKW_MIN_BLOCKS 3                  // BATCH: resident 4-warp CTAs per SM the register budget is sized for
+#endif
 
 struct alignas(16) LkLevel {                 // what the prologue of one level leaves for the iterations
     uint8_t tileI[kTileI * kTileI + 16];     // 24x24 source pixels around the window (+16: word fetches of the last row)
@@ -313,6 +316,45 @@ __device__ __forceinline__ void stage_tile_j(uint8_t* tile, const LevelRef& L, i
     dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
 }
 
+// Cold path of an iteration (the exactness bound failed): OpenCV's 10 ordered float chains over the spilled terms, one lane per
+// chain.  Chains 2c + comp (c = 0..3) take the pmaddwd pair sums of columns (8g + c, 8g + c + 4), g = 0, 1, row by row; chains
+// 8 / 9 the scalar tail (columns 16..20).  Returns (ib1, ib2) in every lane.  Out of line on purpose.
+__device__ __noinline__ float2 lkw_ordered_chains(const int* termX, const int* termY) {
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    {
+        const int q = min(lane, 9);
+        const int* T = (q & 1) ? termY : termX;
+        if (q < 8) {
+            const int c = q >> 1;
+#pragma unroll 3
+            for (int y = 0; y < kWin; ++y) {
+                acc = __fadd_rn(acc, (float)(T[y * kWin + c] + T[y * kWin + c + 4]));            // v_cvt_f32 of the pair sum
+                acc = __fadd_rn(acc, (float)(T[y * kWin + 8 + c] + T[y * kWin + 12 + c]));
+            }
+        } else {
+#pragma unroll 3
+            for (int y = 0; y < kWin; ++y)
+#pragma unroll
+                for (int x = 16; x < kWin; ++x) acc = __fadd_rn(acc, (float)T[y * kWin + x]);
+        }
+    }
+    // qb0 + qb1 -> (s0, s1, s2, s3); ib1 += (s0 + 0) + (s2 + 0); ib2 += (s1 + 0) + (s3 + 0)
+    const float k0x = __shfl_sync(0xffffffffu, acc, 0), k0y = __shfl_sync(0xffffffffu, acc, 1);
+    const float k0z = __shfl_sync(0xffffffffu, acc, 2), k0w = __shfl_sync(0xffffffffu, acc, 3);
+    const float k1x = __shfl_sync(0xffffffffu, acc, 4), k1y = __shfl_sync(0xffffffffu, acc, 5);
+    const float k1z = __shfl_sync(0xffffffffu, acc, 6), k1w = __shfl_sync(0xffffffffu, acc, 7);
+    const float k2x = __shfl_sync(0xffffffffu, acc, 8), k2y = __shfl_sync(0xffffffffu, acc, 9);
+    const float s0 = __fadd_rn(k0x, k1x), s1 = __fadd_rn(k0y, k1y), s2 = __fadd_rn(k0z, k1z), s3 = __fadd_rn(k0w, k1w);
+    return make_float2(__fadd_rn(k2x, __fadd_rn(s0, s2)), __fadd_rn(k2y, __fadd_rn(s1, s3)));
+}
+// Cold path of an iteration: the window left the staged tile, re-stage it around the new origin.  Out of line.
+__device__ __noinline__ void lkw_restage_tile(uint8_t* tile, const LevelRef& L, int x0, int y0) {
+    __syncwarp();
+    stage_tile_j(tile, L, x0, y0);
+    __syncwarp();
+}
+
 // ---- the iterations of one level, one warp (all lanes hold identical scalars) ----
 // LN: the next (finer) level of the target pyramid, for the speculative tile fetch; unused at level 0.
 __device__ __forceinline__ void lk_iterate(IterState& st, const LkLevel& B, LkWork& wk, const Segs& sg, const LevelRef& LJ, const LevelRef& LN,
@@ -390,9 +432,7 @@ __device__ __forceinline__ void lk_iterate(IterState& st, const LkLevel& B, LkWo
                 break;
             }
             jx0 = inx - kJMargin; jy0 = iny - kJMargin;          // the window left the staged tile: re-centre it (uniform branch)
-            __syncwarp();
-            stage_tile_j(wk.tileJ[st.jbuf], LJ, jx0, jy0);
-            __syncwarp();
+            lkw_restage_tile(wk.tileJ[st.jbuf], LJ, jx0, jy0);
             lox = max(-kWin, jx0); hix = min(jcols - 1, jx0 + kTileJ - kTileD);
             loy = max(-kWin, jy0); hiy = min(jrows - 1, jy0 + kTileJ - kTileD);
         }
@@ -440,33 +480,8 @@ __device__ __forceinline__ void lk_iterate(IterState& st, const LkLevel& B, LkWo
                     }
                 }
             __syncwarp();
-            float acc = 0.f;
-            {
-                const int q = min(lane, 9);
-                const int* T = (q & 1) ? termY : termX;
-                if (q < 8) {
-                    const int c = q >> 1;
-#pragma unroll 3
-                    for (int y = 0; y < kWin; ++y) {
-                        acc = __fadd_rn(acc, (float)(T[y * kWin + c] + T[y * kWin + c + 4]));            // v_cvt_f32 of the pair sum
-                        acc = __fadd_rn(acc, (float)(T[y * kWin + 8 + c] + T[y * kWin + 12 + c]));
-                    }
-                } else {
-#pragma unroll 3
-                    for (int y = 0; y < kWin; ++y)
-#pragma unroll
-                        for (int x = 16; x < kWin; ++x) acc = __fadd_rn(acc, (float)T[y * kWin + x]);
-                }
-            }
-            // qb0 + qb1 -> (s0, s1, s2, s3); ib1 += (s0 + 0) + (s2 + 0); ib2 += (s1 + 0) + (s3 + 0)
-            const float k0x = __shfl_sync(0xffffffffu, acc, 0), k0y = __shfl_sync(0xffffffffu, acc, 1);
-            const float k0z = __shfl_sync(0xffffffffu, acc, 2), k0w = __shfl_sync(0xffffffffu, acc, 3);
-            const float k1x = __shfl_sync(0xffffffffu, acc, 4), k1y = __shfl_sync(0xffffffffu, acc, 5);
-            const float k1z = __shfl_sync(0xffffffffu, acc, 6), k1w = __shfl_sync(0xffffffffu, acc, 7);
-            const float k2x = __shfl_sync(0xffffffffu, acc, 8), k2y = __shfl_sync(0xffffffffu, acc, 9);
-            const float s0 = __fadd_rn(k0x, k1x), s1 = __fadd_rn(k0y, k1y), s2 = __fadd_rn(k0z, k1z), s3 = __fadd_rn(k0w, k1w);
-            ib1 = __fadd_rn(k2x, __fadd_rn(s0, s2));
-            ib2 = __fadd_rn(k2y, __fadd_rn(s1, s3));
+            const float2 ib = lkw_ordered_chains(termX, termY);      // cold, out of line (keeps the loop compact in the L0 I-cache)
+            ib1 = ib.x; ib2 = ib.y;
         }
         const float b1 = __fmul_rn(ib1, FLT_SCALE), b2 = __fmul_rn(ib2, FLT_SCALE);
         const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
@@ -630,7 +645,7 @@ struct Pass {
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), feature_tracker.cpp:37-67 ----
 template <bool COOP>
-__global__ void __launch_bounds__(128) lk_temporal_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
+__global__ void __launch_bounds__(128, COOP ? 1 : VF_LKW_MIN_BLOCKS) lk_temporal_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
     pdl_wait(); pdl_release();
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;
     __shared__ LevelRef pyr[2][kMaxLevels];
@@ -671,7 +686,7 @@ __global__ void __launch_bounds__(128) lk_temporal_warp_kernel(const __grid_cons
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then RemoveDistortion +
 //      ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
 template <bool COOP>
-__global__ void __launch_bounds__(128) lk_stereo_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
+__global__ void __launch_bounds__(128, COOP ? 1 : VF_LKW_MIN_BLOCKS) lk_stereo_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
     pdl_wait(); pdl_release();
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;
     __shared__ LevelRef pyr[2][kMaxLevels];
