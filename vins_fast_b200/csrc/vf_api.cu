@@ -797,7 +797,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
 
     // synchronous frames as one graph (VF_SYNC_ONE_GRAPH=0: the four-graph plan, for A/B runs)
     b->one_graph_sync = !(getenv("VF_SYNC_ONE_GRAPH") != nullptr && atoi(getenv("VF_SYNC_ONE_GRAPH")) == 0) && !b->serialized;
-    b->corner_after_pyr = getenv("VF_CORNER_AFTER_PYR") != nullptr && atoi(getenv("VF_CORNER_AFTER_PYR")) != 0;
+    b->corner_after_pyr = !(getenv("VF_CORNER_AFTER_PYR") != nullptr && atoi(getenv("VF_CORNER_AFTER_PYR")) == 0);   // =0: beside the pyramid (A/B)
     TRYC(select_tracked_prepare(cap));
     TRYC(lk_prepare());
     TRYC(corners_prepare());

@@ -51,6 +51,14 @@ constexpr int kChains = 15;                  // 3 matrix entries x (4 SIMD-lane 
 constexpr int kProd = kWinPx + 3;            // floats per product plane (row-major 21x21)
 constexpr int kPP = 24;                      // pitch of the weighted-pixel plane P (23 x 23 values)
 constexpr int kCoopWarps = 4;
+#ifndef VF_LKW_BATCH_WARPS
+#define VF_LKW_BATCH_WARPS 4                // BATCH: warps (= features) per CTA
+#endif
+#ifdef VF_LKW_MAXNREG                        // A/B aid: cap the registers directly (e.g. 144 with 2-warp CTAs: 14 warps per SM)
+#define VF_LKW_BOUNDS(COOP) __maxnreg__(VF_LKW_MAXNREG)
+#else
+#define VF_LKW_BOUNDS(COOP) __launch_bounds__(COOP ? 128 : 32 * VF_LKW_BATCH_WARPS, COOP ? 1 : VF_LKW_MIN_BLOCKS)
+#endif
 #ifndef VF_LKW_MIN_BLOCKS
 #define VF_LKW_MIN_BLOCKS 3                  // BATCH: resident 4-warp CTAs per SM the register budget is sized for
 #endif
@@ -645,7 +653,7 @@ struct Pass {
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), feature_tracker.cpp:37-67 ----
 template <bool COOP>
-__global__ void __launch_bounds__(128, COOP ? 1 : VF_LKW_MIN_BLOCKS) lk_temporal_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
+__global__ void VF_LKW_BOUNDS(COOP) lk_temporal_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
     pdl_wait(); pdl_release();
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;
     __shared__ LevelRef pyr[2][kMaxLevels];
@@ -686,7 +694,7 @@ __global__ void __launch_bounds__(128, COOP ? 1 : VF_LKW_MIN_BLOCKS) lk_temporal
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then RemoveDistortion +
 //      ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
 template <bool COOP>
-__global__ void __launch_bounds__(128, COOP ? 1 : VF_LKW_MIN_BLOCKS) lk_stereo_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
+__global__ void VF_LKW_BOUNDS(COOP) lk_stereo_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
     pdl_wait(); pdl_release();
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;
     __shared__ LevelRef pyr[2][kMaxLevels];
@@ -753,7 +761,7 @@ __global__ void __launch_bounds__(128) lk_op_warp_kernel(PyrView prev, PyrView n
     }
 }
 
-constexpr int kBatchWarps = 4;     // features per CTA in BATCH scheduling
+constexpr int kBatchWarps = VF_LKW_BATCH_WARPS;     // features per CTA in BATCH scheduling
 size_t smem_batch() { return (sizeof(LkLevel) + sizeof(LkWork)) * kBatchWarps; }
 size_t smem_coop(int n_levels) { return sizeof(LkLevel) * (size_t)(n_levels > 1 ? n_levels : 1) + sizeof(LkWork) * kCoopWarps; }
 
