@@ -431,6 +431,28 @@ def main():
             wall_ms.append(max_over_ranks(wall))
         return dev_ms, wall_ms
 
+    def isolated_stage_times(cfg_, n_streams, feed, n_frames_, skip):
+        """Per-kernel device times with every kernel ALONE on the GPU: a batch created with VF_SERIALIZE=1 puts all stages of a
+        frame on one stream, profiling mode brackets every kernel with CUDA events on that stream (plain launches, no graph).
+        What the frame plans overlap (pyramid beside response, stereo beside undistortion) would otherwise stretch the
+        event-to-event spans; these are the launch durations the roofline fractions are computed from."""
+        os.environ["VF_SERIALIZE"] = "1"
+        try:
+            sb = vf.Batch(cfg_, n_streams)
+        finally:
+            del os.environ["VF_SERIALIZE"]
+        sb.set_profiling(True)
+        acc_, cnt_ = {}, 0
+        for k in range(n_frames_):
+            feed(sb, k)
+            if k >= skip:
+                for nm, ms in sb.stage_times_ms().items():
+                    acc_[nm] = acc_.get(nm, 0.0) + ms * 1e3
+                cnt_ += 1
+        sb.set_profiling(False)
+        sb.close()
+        return {k: v / max(cnt_, 1) for k, v in acc_.items()}
+
     K, Wm, R = args.steps, args.warmup, args.repeats
     cam0, cam1 = workload_cameras("c1")
     # D distinct frames (> L2 in total), visited forward then backward (0..D-1, D-2..0, ...): consecutive steps always
@@ -525,6 +547,7 @@ def main():
 
         # ---------------- per-kernel times (CUDA events on the launching streams) ----------------
         stages_us, n_prof, iters_t, iters_s, feats, fast_it = {}, 0, 0, 0, 0, 0
+        stages_in_frame_us = {}
         if "stages" in legs:
             from vins_fast_b200 import _lib as L
             batch.reset()
@@ -541,7 +564,8 @@ def main():
                     iters_t += int((it_t & 0xffff).sum()); iters_s += int((it_s & 0xffff).sum()); feats += len(it_s)
                     fast_it += int((it_t >> 16).sum()) + int((it_s >> 16).sum())
             batch.set_profiling(False)
-            stages_us = {k: v / max(n_prof, 1) * 1e3 for k, v in acc.items()}
+            stages_in_frame_us = {k: v / max(n_prof, 1) * 1e3 for k, v in acc.items()}   # event-to-event, stages overlapping as in a frame
+            stages_us = isolated_stage_times(cfg, 1, lambda sb, k: sb.track_ptrs(times[k], ptr_l[k], W, ptr_r[k], W), min(n_frames, Wm + 40), Wm)
 
         # ---------------- kernel timeline of a synchronous frame on the GPU's own nanosecond timer ----------------
         # (every kernel stamps its first start / last end when tracing is on: no event overhead, true launch gaps)
@@ -595,19 +619,13 @@ def main():
                      "us_per_frame_per_stream": ms_m * 1e3 / (steps_m * S), "ms_per_step": ms_m / steps_m,
                      "regions_ms": m_dev, "launches_per_step": mb.launches_per_frame}
             # per-kernel device times of the batched step (CUDA events around every kernel, plain launches, synchronous frames)
-            mb.reset()
-            mb.set_profiling(True)
-            macc, mcnt = {}, 0
-            for k in range(12):
-                mb.enqueue_device(mt(k), base + k * frame_bytes, base + k * frame_bytes + H * W, W, frame_bytes)
-                mb.fetch_counts()
-                if k >= 4:
-                    for name, ms in mb.stage_times_ms().items():
-                        macc[name] = macc.get(name, 0.0) + ms * 1e3
-                    mcnt += 1
-            mb.set_profiling(False)
-            multi["stages_us"] = {k: v / max(mcnt, 1) for k, v in macc.items()}
             mb.close()
+
+            def feed_multi(sb, k):
+                sb.enqueue_device(mt(k), base + k * frame_bytes, base + k * frame_bytes + H * W, W, frame_bytes)
+                sb.fetch_counts()
+            multi["stages_us"] = isolated_stage_times(vf.make_config(W, H, MAX_CNT, MIN_DIST, FLOW_BACK, cam0, cam1, lk_max_level=LEVEL, device=local),
+                                                      S, feed_multi, 12, 4)
 
         # ---------------- BASELINE configs 3, 4 and 5 as measured workloads ----------------
         workloads = {}
@@ -647,17 +665,7 @@ def main():
                         wb.track_ptrs(k / 20.0, pl[k], w, pr[k], w)
                 s_dev, s_wall = regions(wst, 3, sync_steps)
                 s_ms = [max(a, b) for a, b in zip(s_dev, s_wall)]
-                wb.reset()
-                wb.set_profiling(True)
-                acc, cnt = {}, 0
-                for k in range(min(n_tot, warm + 8)):
-                    wb.track_ptrs(k / 20.0, pl[k], w, pr[k], w)
-                    if k >= warm:
-                        for nm, ms in wb.stage_times_ms().items():
-                            acc[nm] = acc.get(nm, 0.0) + ms * 1e3
-                        cnt += 1
-                wb.set_profiling(False)
-            st_us = {k: v / max(cnt, 1) for k, v in acc.items()}
+            st_us = isolated_stage_times(wcfg, 1, lambda sb, k: sb.track_ptrs(k / 20.0, pl[k], w, pr[k], w), min(n_tot, warm + 8), warm)
             npx = w * h
             s_l = sum(4.0 ** -l for l in range(lvl + 1))
             # SURVEY 8(d) compulsory bytes: pyramid read N + write N (S_L - 1); response read N + write 4 N response + N flags;
@@ -804,7 +812,10 @@ def main():
         "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                    "samples": clocks["samples"], "rejected": bool(bad)},
         "gpu_launches": launches, "launches_per_frame": batch.launches_per_frame, "host_issue_us_per_frame": host_issue,
-        "stages_us": stages_us, "timeline": timeline, "roofline": roofline, "multi_stream": multi, "workloads": workloads,
+        "stages_us": stages_us, "stages_note": "per-kernel launch durations, every kernel alone on the GPU (VF_SERIALIZE batch, CUDA events around each plain launch: includes "
+                                               "~5 us of event / launch latency per stage, the timeline has the bare kernel spans); "
+                                               "stages_in_frame_us = the same events with the frame's stages overlapping as they do in a synchronous frame",
+        "stages_in_frame_us": stages_in_frame_us, "timeline": timeline, "roofline": roofline, "multi_stream": multi, "workloads": workloads,
         "lk": {"iterations_per_frame": (iters_t + iters_s) / max(n_prof, 1),
                "exact_integer_path_fraction": fast_it / max(iters_t + iters_s, 1)},
     }
