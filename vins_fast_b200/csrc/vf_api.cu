@@ -57,6 +57,7 @@ struct vf_batch {
     bool own_main = false, serialized = false;
     bool one_graph_sync = false;           // synchronous frames replay SEQ_FRAME_SYNC (one graph) instead of four
     bool corner_after_pyr = false;         // ... whose corner stage starts behind the left pyramid instead of beside it
+    bool chain_direct = false;             // overlapped frames issue the chain's four kernels directly instead of replaying a graph
     double host_wait_us = 0, host_issue_us = 0;   // host time spent waiting for frame k-2 / issuing frame k (cumulative)
     cudaEvent_t ev_input = nullptr;        // device-input ordering: recorded on the caller's stream / handed in by the caller
     cudaEvent_t ev_user_input = nullptr;   // vf_batch_set_input_event: the next frame's uploads wait for it (not owned)
@@ -500,7 +501,7 @@ vf_status enqueue_frame(vf_batch* b, const double* times, const uint8_t* const* 
                                                      "vf.pyramid_right", "vf.stereo_tail", "vf.frame_sync"};
     auto run = [&](int which, cudaStream_t st) -> vf_status {   // one of the captured kernel sequences, as a graph or directly
         NvtxRange r(kSeqNames[which]);
-        if (use_graph) {
+        if (use_graph && !(which == SEQ_CHAIN && b->chain_direct)) {
             if (!b->graph[which][phase]) {
                 vf_status r = build_graph(b, phase, which);
                 if (r != VF_OK) return r;
@@ -798,6 +799,9 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     // synchronous frames as one graph (VF_SYNC_ONE_GRAPH=0: the four-graph plan, for A/B runs)
     b->one_graph_sync = !(getenv("VF_SYNC_ONE_GRAPH") != nullptr && atoi(getenv("VF_SYNC_ONE_GRAPH")) == 0) && !b->serialized;
     b->corner_after_pyr = !(getenv("VF_CORNER_AFTER_PYR") != nullptr && atoi(getenv("VF_CORNER_AFTER_PYR")) == 0);   // =0: beside the pyramid (A/B)
+    // A graph that follows another graph in the same stream starts 5-9 us after it ends; a kernel that follows a kernel ~1 us.
+    // The chain is the one sequence whose predecessor in its stream (the previous frame's chain) sits on the critical path.
+    b->chain_direct = getenv("VF_CHAIN_DIRECT") != nullptr && atoi(getenv("VF_CHAIN_DIRECT")) != 0;
     TRYC(select_tracked_prepare(cap));
     TRYC(lk_prepare());
     TRYC(corners_prepare());

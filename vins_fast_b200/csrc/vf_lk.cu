@@ -677,8 +677,7 @@ __device__ __forceinline__ void lk_timing_flush(LkSmem& sm) {
 }
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), :37-67 ----
-__global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
-    pdl_wait(); pdl_release();
+__device__ __forceinline__ void lk_temporal_body(const DevBatch& b, int parity_arg, int cur, int prev) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
@@ -739,8 +738,7 @@ __global__ void __launch_bounds__(kLkThreads) lk_temporal_kernel(const __grid_co
 
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then
 //      RemoveDistortion + ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
-__global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
-    pdl_wait(); pdl_release();
+__device__ __forceinline__ void lk_stereo_body(const DevBatch& b, int parity_arg, int cur, const double* __restrict__ dt_host) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;   // frame parity; trace slot (frame % 6)
     LkSmem& sm = *reinterpret_cast<LkSmem*>(lk_smem_raw);
     __shared__ int stat[2];
@@ -797,6 +795,17 @@ __global__ void __launch_bounds__(kLkThreads) lk_stereo_kernel(const __grid_cons
 #endif
     }
     lk_timing_flush(sm);
+}
+
+// ONE entry point for both pairs of LK calls (bit 2 of parity_arg: 0 = temporal, 1 = stereo).  A device function is linked into
+// every kernel that calls it, so two kernels would each carry their own 80 KB copy of the pass -- and in overlapped frames the
+// temporal launch of frame k+1 and the stereo launch of frame k share every SM: two copies competed for the 32 KB of L1.5
+// instruction cache (`no_instruction` was already the second stall reason of either kernel alone).  One kernel, one copy.
+__global__ void __launch_bounds__(kLkThreads) lk_pair_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev,
+                                                             const double* __restrict__ dt_host) {
+    pdl_wait(); pdl_release();
+    if (parity_arg & 4) lk_stereo_body(b, parity_arg & ~4, cur, dt_host);
+    else lk_temporal_body(b, parity_arg, cur, prev);
 }
 
 // ---- left camera: RemoveDistortion + ComputeKpsVelocity (:103-104, :310-363) and the left half of the record.
@@ -858,16 +867,13 @@ void launch_undistort(const CamParams& cam, const float2* uv, float2* out, int n
 // The LK kernels keep all per-level state of a pass in (dynamic) shared memory: opt in above 48 KB once per device.
 cudaError_t lk_prepare() {
     const int bytes = (int)lk_smem_bytes(kMaxLevels, true);
-    cudaError_t e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(lk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     if ((e = lk_warp_prepare()) != cudaSuccess) return e;
     // same carveout as every other kernel of the library (see corners_prepare)
-    if ((e = cudaFuncSetAttribute(lk_temporal_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(lk_stereo_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(lk_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(undistort_left_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(undistort_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout);
@@ -877,13 +883,14 @@ void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, 
     if (lk_use_warp_kernel((long long)h.cap * h.n_streams)) { launch_lk_temporal_warp(h, parity, cur, prev, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);   // bit 1 of the parity argument
-    launch_kernel(lk_temporal_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, prev);
+    launch_kernel(lk_pair_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, prev,
+                  (const double*)nullptr);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
     if (lk_use_warp_kernel((long long)h.cap * h.n_streams)) { launch_lk_stereo_warp(h, parity, cur, dt_host, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);
-    launch_kernel(lk_stereo_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0), cur, dt_host);
+    launch_kernel(lk_pair_kernel, grid, dim3(kLkThreads), lk_smem_bytes(h.n_levels, staged), stream, h, parity | (staged ? 2 : 0) | 4, cur, 0, dt_host);
 }
 void launch_undistort_left(const DevBatch* d_batch, const DevBatch& h, int parity, const double* dt_host, int* n_host, cudaStream_t stream) {
     dim3 grid((h.cap + 127) / 128, h.n_streams);

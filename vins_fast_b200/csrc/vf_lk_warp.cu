@@ -653,11 +653,8 @@ struct Pass {
 
 // ---- temporal: prev -> cur (maxLevel L) then cur -> prev (maxLevel 1, initial flow), feature_tracker.cpp:37-67 ----
 template <bool COOP>
-__global__ void VF_LKW_BOUNDS(COOP) lk_temporal_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev) {
-    pdl_wait(); pdl_release();
+__device__ __forceinline__ void lk_temporal_warp_body(const DevBatch& b, int parity_arg, int cur, int prev, LevelRef (*pyr)[kMaxLevels], WarpPass& result) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;
-    __shared__ LevelRef pyr[2][kMaxLevels];
-    __shared__ WarpPass result;
     TraceScope trace(b.trace, TR_LK_TEMPORAL + 16 * tphase);
     const int s = blockIdx.y, i = Pass<COOP>::feature(), cap = b.cap;
     const int n_prev = b.counters[parity ^ 1][s * C_COUNT + C_N_TOTAL];
@@ -694,11 +691,9 @@ __global__ void VF_LKW_BOUNDS(COOP) lk_temporal_warp_kernel(const __grid_constan
 // ---- stereo: left -> right then right -> left (both maxLevel L), status (:112-135), then RemoveDistortion +
 //      ComputeKpsVelocity for the right camera and the right half of the featureFrame record ----
 template <bool COOP>
-__global__ void VF_LKW_BOUNDS(COOP) lk_stereo_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, const double* __restrict__ dt_host) {
-    pdl_wait(); pdl_release();
+__device__ __forceinline__ void lk_stereo_warp_body(const DevBatch& b, int parity_arg, int cur, const double* __restrict__ dt_host, LevelRef (*pyr)[kMaxLevels],
+                                                    WarpPass& result) {
     const int parity = parity_arg & 1, tphase = parity_arg >> 4;
-    __shared__ LevelRef pyr[2][kMaxLevels];
-    __shared__ WarpPass result;
     TraceScope trace(b.trace, TR_LK_STEREO + 16 * tphase);
     const int s = blockIdx.y, i = Pass<COOP>::feature(), cap = b.cap;
     const int n = b.counters[parity][s * C_COUNT + C_N_TOTAL];
@@ -742,6 +737,19 @@ __global__ void VF_LKW_BOUNDS(COOP) lk_stereo_warp_kernel(const __grid_constant_
     }
 }
 
+// ONE entry point per scheduling for both pairs of LK calls (bit 2 of parity_arg: 0 = temporal, 1 = stereo): the passes are
+// __noinline__ functions, linked into every kernel that calls them, and in overlapped frames the temporal launch of frame k+1
+// shares the SMs with the stereo launch of frame k -- two kernels meant two 65 KB copies of the same code fighting for the
+// instruction caches (vf_lk.cu: lk_pair_kernel).
+template <bool COOP>
+__global__ void VF_LKW_BOUNDS(COOP) lk_pair_warp_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev, const double* __restrict__ dt_host) {
+    pdl_wait(); pdl_release();
+    __shared__ LevelRef pyr[2][kMaxLevels];
+    __shared__ WarpPass result;
+    if (parity_arg & 4) lk_stereo_warp_body<COOP>(b, parity_arg & ~4, cur, dt_host, pyr, result);
+    else lk_temporal_warp_body<COOP>(b, parity_arg, cur, prev, pyr, result);
+}
+
 // ---- stand-alone calcOpticalFlowPyrLK (vf_op_lk) ----
 template <bool COOP>
 __global__ void __launch_bounds__(128) lk_op_warp_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts,
@@ -782,8 +790,7 @@ cudaError_t lk_warp_prepare() {
 #define VF_PREP(kernel, bytes)                                                                                            \
     if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;  \
     if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
-    VF_PREP(lk_temporal_warp_kernel<true>, coop) VF_PREP(lk_temporal_warp_kernel<false>, batch)
-    VF_PREP(lk_stereo_warp_kernel<true>, coop) VF_PREP(lk_stereo_warp_kernel<false>, batch)
+    VF_PREP(lk_pair_warp_kernel<true>, coop) VF_PREP(lk_pair_warp_kernel<false>, batch)
     VF_PREP(lk_op_warp_kernel<true>, coop) VF_PREP(lk_op_warp_kernel<false>, batch)
 #undef VF_PREP
     return cudaSuccess;
@@ -791,18 +798,18 @@ cudaError_t lk_warp_prepare() {
 
 void launch_lk_temporal_warp(const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
     if (pick_coop((long long)h.cap * h.n_streams)) {
-        launch_kernel(lk_temporal_warp_kernel<true>, dim3(h.cap, h.n_streams), dim3(32 * kCoopWarps), smem_coop(h.n_levels), stream, h, parity, cur, prev);
+        launch_kernel(lk_pair_warp_kernel<true>, dim3(h.cap, h.n_streams), dim3(32 * kCoopWarps), smem_coop(h.n_levels), stream, h, parity, cur, prev, (const double*)nullptr);
     } else {
         dim3 grid((h.cap + kBatchWarps - 1) / kBatchWarps, h.n_streams);
-        launch_kernel(lk_temporal_warp_kernel<false>, grid, dim3(32 * kBatchWarps), smem_batch(), stream, h, parity, cur, prev);
+        launch_kernel(lk_pair_warp_kernel<false>, grid, dim3(32 * kBatchWarps), smem_batch(), stream, h, parity, cur, prev, (const double*)nullptr);
     }
 }
 void launch_lk_stereo_warp(const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
     if (pick_coop((long long)h.cap * h.n_streams)) {
-        launch_kernel(lk_stereo_warp_kernel<true>, dim3(h.cap, h.n_streams), dim3(32 * kCoopWarps), smem_coop(h.n_levels), stream, h, parity, cur, dt_host);
+        launch_kernel(lk_pair_warp_kernel<true>, dim3(h.cap, h.n_streams), dim3(32 * kCoopWarps), smem_coop(h.n_levels), stream, h, parity | 4, cur, 0, dt_host);
     } else {
         dim3 grid((h.cap + kBatchWarps - 1) / kBatchWarps, h.n_streams);
-        launch_kernel(lk_stereo_warp_kernel<false>, grid, dim3(32 * kBatchWarps), smem_batch(), stream, h, parity, cur, dt_host);
+        launch_kernel(lk_pair_warp_kernel<false>, grid, dim3(32 * kBatchWarps), smem_batch(), stream, h, parity | 4, cur, 0, dt_host);
     }
 }
 void launch_lk_op_warp(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status, int* iters, int n,
