@@ -55,12 +55,14 @@ typedef struct {
     int32_t min_dist;             /* MIN_DIST                                                        */
     int32_t flow_back;            /* OPTICAL_FLOW_BACK                                               */
     int32_t lk_max_level;         /* default 3   (maxLevel of the forward and stereo LK calls)       */
-    int32_t lk_win;               /* 21 only: the reference passes the literal cv::Size(21, 21) at all four call sites
-                                   * (feature_tracker.cpp:42,51,119,127) and has no key for it.  The LK kernels reproduce
-                                   * OpenCV's float summation ORDER for that width (two 8-wide SIMD groups + a 5-column scalar
-                                   * tail per row, lkpyramid.cpp), which is what makes positions bit-identical; another width
-                                   * is another accumulation order and another tile plan, so it is a compile-time constant
-                                   * (csrc/vf_common.cuh: kWin) and any other value returns VF_ERR_INVALID_ARG             */
+    int32_t lk_win;               /* default 21; any odd width in [5, 31].  The reference passes the literal cv::Size(21, 21) at all
+                                   * four call sites (feature_tracker.cpp:42,51,119,127) and has no key for it.  OpenCV's float
+                                   * summation ORDER -- which the LK kernels reproduce to stay bit-identical -- is a function of
+                                   * the window width (8-wide SIMD groups over the first (win / 8) * 8 columns + a scalar tail per
+                                   * row, lkpyramid.cpp): width 21 runs the tuned kernels built around its chain layout
+                                   * (csrc/vf_lk.cu, vf_lk_warp.cu), every other width the run-time-width kernels of
+                                   * csrc/vf_lk_generic.cu (same results as OpenCV for that width, less tuned).  Even widths and
+                                   * widths outside [5, 31] return VF_ERR_INVALID_ARG                                          */
     double quality_level;         /* default 0.01                                                    */
     vf_camera cam[2];             /* [0] left, [1] right  (ReadIntrinsicParameter order, :301-308)   */
     int32_t device;               /* CUDA device ordinal, -1 = current device                        */
@@ -202,6 +204,10 @@ vf_status vf_op_scharr(const uint8_t* img, int32_t w, int32_t h, int32_t device,
 vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t h, const float* prev_pts,
                    float* next_pts, uint8_t* status, int32_t n, int32_t max_level, int32_t use_initial_flow,
                    int32_t device, int32_t* iters_out);
+/* The same call with winSize (win, win), win odd in [5, 31] (the pyramid's early stop follows the window too). */
+vf_status vf_op_lk_win(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t h, const float* prev_pts,
+                       float* next_pts, uint8_t* status, int32_t n, int32_t max_level, int32_t win,
+                       int32_t use_initial_flow, int32_t device, int32_t* iters_out);
 /* Which corner-response kernel the library launches (process-wide; parity tests only): 0 = by frame size (default),
  * 1 = tiles (small frames), 2 = strips (large frames / batches).  Both give identical results. */
 vf_status vf_debug_set_response_kernel(int32_t mode);

@@ -62,9 +62,11 @@ public:
     FeatureTracker(const FeatureTracker&) = delete;
     FeatureTracker& operator=(const FeatureTracker&) = delete;
 
-    /// CUDA device ordinal (-1 = current) and LK pyramid depth (the reference's literal 3); call before the first frame
+    /// CUDA device ordinal (-1 = current), LK pyramid depth (the reference's literal 3) and LK window width (its literal
+    /// cv::Size(21, 21), feature_tracker.cpp:42,51,119,127; any odd width 5..31); call before the first frame
     void SetDevice(int device) { cfg_.device = device; Release(); }
     void SetLkMaxLevel(int level) { cfg_.lk_max_level = level; Release(); }
+    void SetLkWindow(int win) { cfg_.lk_win = win; Release(); }
 
     /// Read camera intrinsic param: index 0 = left, 1 = right (feature_tracker.cpp:301-308)
     void ReadIntrinsicParameter(const std::vector<std::string>& calib_file_path) {

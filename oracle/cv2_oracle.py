@@ -95,12 +95,13 @@ class Cv2FeatureTracker:
     `calls` counts the frames, so bench.py can report "cv2 calls only" beside the inclusive figure.
     """
 
-    LK_WIN = (21, 21)
+    LK_WIN = (21, 21)            # the reference's literal cv::Size(21, 21) (feature_tracker.cpp:42,51,119,127)
 
     def __init__(self, cam0: Camera, cam1: Camera, max_cnt: int = 150, min_dist: int = 30,
-                 flow_back: int = 1, lk_max_level: int = 3, quality: float = 0.01, keep_debug: bool = True):
+                 flow_back: int = 1, lk_max_level: int = 3, quality: float = 0.01, keep_debug: bool = True, lk_win: int = 21):
         if cv2 is None:
             raise RuntimeError("cv2 is not importable; use oracle.c_oracle instead")
+        self.LK_WIN = (int(lk_win), int(lk_win))     # the north star keeps the window size as a parameter
         self.cams = [cam0, cam1]
         self.MAX_CNT, self.MIN_DIST, self.FLOW_BACK = int(max_cnt), int(min_dist), int(flow_back)
         self.lk_max_level, self.quality = int(lk_max_level), float(quality)

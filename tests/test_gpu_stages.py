@@ -151,6 +151,48 @@ def test_lk_high_contrast_takes_the_ordered_chains(lib, oracle, lk_kernel):
     assert np.array_equal(q.view(np.uint32), rq.view(np.uint32)), np.abs(q - rq).max()
 
 
+@pytest.mark.parametrize("win", [5, 7, 9, 11, 13, 15, 17, 19, 23, 25, 27, 29, 31])
+def test_lk_other_window_sizes_bit_exact(lib, oracle, euroc_frames, win):
+    """calcOpticalFlowPyrLK with winSize != (21, 21) (csrc/vf_lk_generic.cu): forward at 0 / 3 / 5 requested levels (the
+    pyramid's early stop follows the window), reverse with an initial flow, points outside the image included --
+    positions, status and iteration counts bit-equal to the oracle for that width."""
+    from vins_fast_b200 import ops
+    _, l0, r0 = euroc_frames[0]
+    _, l1, _ = euroc_frames[1]
+    pts = np.concatenate([_lk_points(l0, 300, win), np.array([[-40, 50], [760, 470], [0.2, 0.3], [751, 479], [-3, 200]], np.float32)])
+    for a, b, level in ((l0, l1, 3), (l0, r0, 0), (_crop(l0, 200, 260), _crop(l1, 200, 260), 5)):
+        q, st, it = ops.lk(a, b, pts, level, return_iters=True, win=win)
+        rq, rst, rit = oracle.lk(oracle.Pyramid(a, level, win), oracle.Pyramid(b, level, win), pts, level, win, return_iters=True)
+        assert np.array_equal(st, rst), level
+        assert np.array_equal(it, rit), level
+        assert np.array_equal(q.view(np.uint32), rq.view(np.uint32)), (level, np.abs(q - rq).max())
+    fwd, _ = ops.lk(l0, l1, pts, 3, win=win)
+    rev, rst = ops.lk(l1, l0, fwd, 1, init=pts, win=win)
+    orev, orst = oracle.lk(oracle.Pyramid(l1, 1, win), oracle.Pyramid(l0, 1, win), fwd, 1, win, init=pts)
+    assert np.array_equal(rst, orst) and np.array_equal(rev.view(np.uint32), orev.view(np.uint32))
+
+
+@pytest.mark.parametrize("win", [7, 15, 31])
+def test_lk_other_window_sizes_ordered_chains_and_textureless(lib, oracle, win):
+    """The high-contrast checker of the 21x21 test (sums beyond 2^24: ordered float chains in the layout of this width) and a
+    flat image (minEig below threshold)."""
+    from vins_fast_b200 import ops
+    yy, xx = np.mgrid[0:240, 0:320]
+    a = (((xx // 5 + yy // 5) & 1) * 255).astype(np.uint8)
+    b = np.roll(a, (1, 2), (0, 1))
+    b[::2] = (b[::2].astype(np.int32) * 3 // 4).astype(np.uint8)
+    pts = _lk_points(a, 300, 5)
+    q, st, it = ops.lk(a, b, pts, 3, return_iters=True, win=win)
+    rq, rst, rit = oracle.lk(oracle.Pyramid(a, 3, win), oracle.Pyramid(b, 3, win), pts, 3, win, return_iters=True)
+    assert np.array_equal(st, rst) and np.array_equal(it, rit)
+    assert np.array_equal(q.view(np.uint32), rq.view(np.uint32)), np.abs(q - rq).max()
+    flat = np.full((120, 160), 77, np.uint8)
+    p2 = np.array([[50, 50], [80.5, 60.25]], np.float32)
+    q, st = ops.lk(flat, flat, p2, 3, win=win)
+    rq, rst = oracle.lk(oracle.Pyramid(flat, 3, win), oracle.Pyramid(flat, 3, win), p2, 3, win)
+    assert np.array_equal(st, rst) and st.sum() == 0 and np.array_equal(q.view(np.uint32), rq.view(np.uint32))
+
+
 @pytest.fixture(params=[1, 2], ids=["tiles", "strips"])
 def response_kernel(request, lib):
     """Both corner-response kernels (the library picks by frame size) must give the same bits."""

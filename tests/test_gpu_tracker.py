@@ -14,17 +14,18 @@ from oracle.camera import EUROC_CAM0, EUROC_CAM1, pinhole_for
 pytestmark = pytest.mark.gpu
 
 
-def _tracker(w, h, max_cnt, min_dist, flow_back, cam0, cam1, level=3, graph=True):
+def _tracker(w, h, max_cnt, min_dist, flow_back, cam0, cam1, level=3, graph=True, win=21):
     import vins_fast_b200 as v
     cfg = v.make_config(w, h, max_cnt, min_dist, flow_back, cam0.__dict__, cam1.__dict__, lk_max_level=level,
                         use_cuda_graph=graph)
+    cfg.lk_win = win
     return v.FeatureTracker(cfg)
 
 
-def _run_pair(oracle, frames, w, h, max_cnt, min_dist, flow_back, cam0, cam1, level=3, graph=True, check_debug=False):
+def _run_pair(oracle, frames, w, h, max_cnt, min_dist, flow_back, cam0, cam1, level=3, graph=True, check_debug=False, win=21):
     from vins_fast_b200 import _lib
-    gpu = _tracker(w, h, max_cnt, min_dist, flow_back, cam0, cam1, level, graph)
-    ref = oracle.CFeatureTracker(cam0, cam1, w, h, max_cnt, min_dist, flow_back, level, 21, 0.01, 0)
+    gpu = _tracker(w, h, max_cnt, min_dist, flow_back, cam0, cam1, level, graph, win)
+    ref = oracle.CFeatureTracker(cam0, cam1, w, h, max_cnt, min_dist, flow_back, level, win, 0.01, 0)
     total = 0
     for k, (t, l, r) in enumerate(frames):
         g = oracle.records_to_frame(gpu.track(t, l, r))
@@ -57,6 +58,39 @@ def test_euroc_no_graph_and_debug_getters(lib, oracle, euroc_frames):
 
 def test_flow_back_off(lib, oracle, euroc_frames):
     _run_pair(oracle, euroc_frames[:8], 752, 480, 150, 30, 0, EUROC_CAM0, EUROC_CAM1)
+
+
+@pytest.mark.parametrize("win,level,flow_back", [(15, 3, 1), (31, 3, 1), (9, 2, 0), (27, 4, 1)])
+def test_euroc_sequence_with_other_lk_windows(lib, oracle, euroc_frames, win, level, flow_back):
+    """`lk_win` is a parameter (north star); the reference's literal is 21.  Every other odd width 5..31 runs the
+    run-time-width kernels of csrc/vf_lk_generic.cu: the whole TrackImage stays bit-identical to the oracle with that window
+    (and the oracle to cv2 with that window: tests/test_oracle_golden.py)."""
+    n = _run_pair(oracle, euroc_frames[:10], 752, 480, 150, 30, flow_back, EUROC_CAM0, EUROC_CAM1, level=level, win=win)
+    assert n > 10 * 120
+
+
+def test_other_lk_window_batch_and_golden_sequences(lib, oracle):
+    """Window 15 / 31 against the committed cv2 fixture directly (GPU vs OpenCV, no oracle in between), through a batch of two
+    streams so that the stream index of the run-time-width kernels is exercised as well."""
+    import os
+    import vins_fast_b200 as v
+    from vins_fast_b200.synth import StereoSequence
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lk_windows_cv2_4_13.npz"))
+    for name in ("win15", "win31"):
+        w, h, max_cnt, min_dist, flow_back, level, n_frames, seed, win = (int(x) for x in g[f"{name}_params"])
+        cam = pinhole_for(w, h)
+        cfg = v.make_config(w, h, max_cnt, min_dist, flow_back, cam.__dict__, cam.__dict__, lk_max_level=level)
+        cfg.lk_win = win
+        batch = v.Batch(cfg, 2)
+        seq = StereoSequence(seed, w, h)
+        for k in range(n_frames):
+            t, l, r = seq.frame(k)
+            recs = batch.track(t, np.stack([l, l]), np.stack([r, r]))
+            for s in range(2):
+                f = oracle.records_to_frame(recs[s])
+                for key, val in f.items():
+                    ref = g[f"{name}_f{k}_{key}"]
+                    assert val.shape == ref.shape and val.tobytes() == ref.astype(val.dtype).tobytes(), (name, k, s, key)
 
 
 @pytest.mark.parametrize("mode", [1, 2], ids=["fused", "tma"])
@@ -162,7 +196,7 @@ def test_error_codes(lib):
     import vins_fast_b200 as v
     from vins_fast_b200 import _lib
     cfg = v.make_config(752, 480, 150, 30)
-    cfg.lk_win = 15
+    cfg.lk_win = 16                                                        # even / outside [5, 31]: no such OpenCV window here
     with pytest.raises(v.VfError) as e:
         v.FeatureTracker(cfg)._ensure()
     assert e.value.status == _lib.VF_ERR_INVALID_ARG

@@ -56,7 +56,7 @@ def test_argument_validation_needs_no_gpu(lib):
     assert lib.vf_tracker_create(None, C.byref(h)) == _lib.VF_ERR_INVALID_ARG and b"null" in lib.vf_last_global_error()
     cfg = _lib.VfConfig()
     lib.vf_config_default(C.byref(cfg))
-    for field, bad in (("lk_win", 15), ("max_cnt", 0), ("min_dist", -1), ("width", 10), ("quality_level", 0.0), ("lk_max_level", 9)):
+    for field, bad in (("lk_win", 14), ("lk_win", 33), ("lk_win", 3), ("max_cnt", 0), ("min_dist", -1), ("width", 10), ("quality_level", 0.0), ("lk_max_level", 9)):
         c2 = _lib.VfConfig.from_buffer_copy(cfg)
         setattr(c2, field, bad)
         assert lib.vf_tracker_create(C.byref(c2), C.byref(h)) == _lib.VF_ERR_INVALID_ARG, field

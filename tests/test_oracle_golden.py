@@ -114,6 +114,46 @@ def test_lk_golden(oracle, stages, crops, pair):
     assert np.array_equal(_bits(rev), _bits(stages[f"lk_{pair}_rev_pts"]))
 
 
+@pytest.fixture(scope="module")
+def lk_windows():
+    return np.load(os.path.join(GOLD, "lk_windows_cv2_4_13.npz"))
+
+
+def test_lk_golden_other_window_sizes(oracle, lk_windows, crops):
+    """`lk_win` other than the reference's literal 21: OpenCV's accumulation order is a function of the window width, so each
+    width pins its own chain layout of the C oracle (tests/golden/make_golden_lk_windows.py, cv2 4.13)."""
+    a, b, _ = crops
+    g = lk_windows
+    assert _sha(a) == str(g["crop_sha_a"]) and _sha(b) == str(g["crop_sha_b"])
+    pts = g["pts"]
+    for win in (int(w) for w in g["windows"]):
+        for level in (0, 3):
+            nxt, st = oracle.lk(oracle.Pyramid(a, level, win), oracle.Pyramid(b, level, win), pts, level, win)
+            assert np.array_equal(st, g[f"w{win}_l{level}_st"]), (win, level)
+            assert np.array_equal(_bits(nxt), _bits(g[f"w{win}_l{level}_pts"])), (win, level)
+        rev, rst = oracle.lk(oracle.Pyramid(b, 1, win), oracle.Pyramid(a, 1, win), nxt, 1, win, init=pts)
+        assert np.array_equal(rst, g[f"w{win}_rev_st"]), win
+        assert np.array_equal(_bits(rev), _bits(g[f"w{win}_rev_pts"])), win
+
+
+@pytest.mark.parametrize("name", ["win15", "win31"])
+def test_track_image_golden_other_window_sizes(oracle, lk_windows, name):
+    from vins_fast_b200.synth import StereoSequence
+    g = lk_windows
+    w, h, max_cnt, min_dist, flow_back, level, n_frames, seed, win = (int(v) for v in g[f"{name}_params"])
+    cam = pinhole_for(w, h)
+    seq = StereoSequence(seed, w, h)
+    tr = oracle.CFeatureTracker(cam, cam, w, h, max_cnt, min_dist, flow_back, level, win)
+    for k in range(n_frames):
+        t, l, r = seq.frame(k)
+        f = tr.track_image(t, l, r)
+        for key, v in f.items():
+            ref = g[f"{name}_f{k}_{key}"]
+            assert v.shape == ref.shape, f"frame {k} {key}"
+            assert v.tobytes() == ref.astype(v.dtype).tobytes(), f"frame {k} {key}"
+        assert len(f["ids"]) > max_cnt // 2
+
+
 @pytest.mark.parametrize("n", [17, 150, 400])
 def test_std_sort_permutation_golden(stages, n):
     from oracle.cv2_oracle import stdsort_perm

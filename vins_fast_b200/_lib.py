@@ -58,7 +58,7 @@ EXPORTS = [
     "vf_batch_set_profiling", "vf_batch_stage_count", "vf_batch_stage_name", "vf_batch_stage_times", "vf_batch_trace_get",
     "vf_tracker_debug_get",
     "vf_debug_set_response_kernel", "vf_debug_set_pyramid_kernel", "vf_debug_set_lk_kernel",
-    "vf_op_build_pyramid", "vf_op_scharr", "vf_op_lk", "vf_op_min_eigen", "vf_op_good_features", "vf_op_set_mask",
+    "vf_op_build_pyramid", "vf_op_scharr", "vf_op_lk", "vf_op_lk_win", "vf_op_min_eigen", "vf_op_good_features", "vf_op_set_mask",
     "vf_op_undistort", "vf_op_triangulate_one_point", "vf_op_triangulate_pts", "vf_op_outliers_rejection",
     "vf_host_alloc", "vf_host_free", "vf_device_count",
 ]
@@ -120,6 +120,7 @@ def load() -> C.CDLL:
         "vf_op_build_pyramid": (I32, [P, I32, I32, I32, I32, P, P, P, P]),
         "vf_op_scharr": (I32, [P, I32, I32, I32, P]),
         "vf_op_lk": (I32, [P, P, I32, I32, P, P, P, I32, I32, I32, I32, P]),
+        "vf_op_lk_win": (I32, [P, P, I32, I32, P, P, P, I32, I32, I32, I32, I32, P]),
         "vf_debug_set_response_kernel": (I32, [I32]),
         "vf_debug_set_pyramid_kernel": (I32, [I32]),
         "vf_debug_set_lk_kernel": (I32, [I32]),

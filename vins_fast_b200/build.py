@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libvinsfast_b200.so")
 
-SOURCES = ["vf_api.cu", "vf_pyramid.cu", "vf_pyramid_tma.cu", "vf_lk.cu", "vf_lk_warp.cu", "vf_corners.cu", "vf_select.cu", "vf_geometry.cu", "vf_yaml.cpp"]
+SOURCES = ["vf_api.cu", "vf_pyramid.cu", "vf_pyramid_tma.cu", "vf_lk.cu", "vf_lk_warp.cu", "vf_lk_generic.cu", "vf_corners.cu", "vf_select.cu", "vf_geometry.cu", "vf_yaml.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # parity: no FMA contraction anywhere (critical expressions also use _rn intrinsics)

@@ -188,7 +188,8 @@ vf_status validate_config(const vf_config* c, int n_streams) {
         return fail(nullptr, VF_ERR_INVALID_ARG, "image size must be within [64, 16384] in both dimensions");
     if (c->max_cnt < 1 || c->max_cnt > 4096) return fail(nullptr, VF_ERR_INVALID_ARG, "max_cnt must be in [1, 4096]");
     if (c->min_dist < 0 || c->min_dist > 1024) return fail(nullptr, VF_ERR_INVALID_ARG, "min_dist must be in [0, 1024]");
-    if (c->lk_win != 21) return fail(nullptr, VF_ERR_INVALID_ARG, "lk_win must be 21 (the reference's cv::Size(21,21))");
+    if (!lk_window_supported(c->lk_win))
+        return fail(nullptr, VF_ERR_INVALID_ARG, "lk_win must be odd and in [5, 31] (the reference's cv::Size(21, 21) is the default)");
     if (c->lk_max_level < 0 || c->lk_max_level >= kMaxLevels)
         return fail(nullptr, VF_ERR_INVALID_ARG, "lk_max_level must be in [0, 7]");
     if (!(c->quality_level > 0.0 && c->quality_level <= 1.0))
@@ -742,7 +743,7 @@ vf_status vf_batch_create(const vf_config* cfg, int32_t n_streams, vf_batch** ou
     memset(&h, 0, sizeof(h));
     const int S = n_streams, W = cfg->width, H = cfg->height, cap = cfg->max_cnt;
     h.n_streams = S; h.W = W; h.H = H; h.cap = cap; h.min_dist = cfg->min_dist; h.flow_back = cfg->flow_back ? 1 : 0;
-    h.lk_max_level = cfg->lk_max_level; h.quality = cfg->quality_level;
+    h.lk_max_level = cfg->lk_max_level; h.lk_win = cfg->lk_win; h.quality = cfg->quality_level;
     h.n_levels = effective_levels(W, H, cfg->lk_max_level, cfg->lk_win);
     h.bucket_bits = ((size_t)W * H <= (1u << 20)) ? 13 : kMaxBucketBits;
     h.n_buckets = 1 << h.bucket_bits;
@@ -1032,9 +1033,9 @@ struct TempPyr {
     ~TempPyr() { for (void* p : allocs) cudaFree(p); }
 };
 
-vf_status temp_pyramid(TempPyr& tp, const uint8_t* img, int w, int h, int max_level, cudaStream_t st) {
+vf_status temp_pyramid(TempPyr& tp, const uint8_t* img, int w, int h, int max_level, cudaStream_t st, int win = kWin) {
     memset(&tp.pv, 0, sizeof(tp.pv));
-    const int n = effective_levels(w, h, max_level, kWin);
+    const int n = effective_levels(w, h, max_level, win);
     tp.pv.n_levels = n;
     int lw = w, lh = h;
     for (int l = 0; l < n; ++l) {
@@ -1123,18 +1124,21 @@ vf_status vf_op_scharr(const uint8_t* img, int32_t w, int32_t h, int32_t device,
     return VF_OK;
 }
 
-vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t h, const float* prev_pts, float* next_pts,
-                   uint8_t* status, int32_t n, int32_t max_level, int32_t use_initial_flow, int32_t device, int32_t* iters_out) {
+vf_status vf_op_lk_win(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t h, const float* prev_pts, float* next_pts,
+                       uint8_t* status, int32_t n, int32_t max_level, int32_t win, int32_t use_initial_flow, int32_t device,
+                       int32_t* iters_out) {
     if (!prev || !next || (n > 0 && (!prev_pts || !next_pts || !status))) return fail(nullptr, VF_ERR_INVALID_ARG, "null argument");
     if (w < 1 || h < 1 || n < 0 || max_level < 0 || max_level >= kMaxLevels) return fail(nullptr, VF_ERR_INVALID_ARG, "bad size / level");
+    if (!lk_window_supported(win)) return fail(nullptr, VF_ERR_INVALID_ARG, "win must be odd and in [5, 31]");
+    if (win != kWin && (w <= win || h <= win)) return fail(nullptr, VF_ERR_INVALID_ARG, "the image must be larger than the window");
     if (n == 0) return VF_OK;   // calcOpticalFlowPyrLK with no points returns empty outputs
     GuardHolder gh;
     vf_status st = op_device(device, &gh.g);
     if (st != VF_OK) return st;
     TempPyr a, c;
-    st = temp_pyramid(a, prev, w, h, max_level, 0);
+    st = temp_pyramid(a, prev, w, h, max_level, 0, win);
     if (st != VF_OK) return st;
-    st = temp_pyramid(c, next, w, h, max_level, 0);
+    st = temp_pyramid(c, next, w, h, max_level, 0, win);
     if (st != VF_OK) return st;
     float2 *dp = nullptr, *dn = nullptr;
     uint8_t* ds = nullptr;
@@ -1147,12 +1151,18 @@ vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t 
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(dn, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
     VF_CUDA((vf_batch*)nullptr, lk_prepare());
     VF_CUDA((vf_batch*)nullptr, pyramid_prepare());
-    launch_lk_op(a.pv, c.pv, dp, dn, ds, di, n, max_level, use_initial_flow, 0);
+    if (win == kWin) launch_lk_op(a.pv, c.pv, dp, dn, ds, di, n, max_level, use_initial_flow, 0);
+    else launch_lk_op_generic(a.pv, c.pv, dp, dn, ds, di, n, max_level, use_initial_flow, win, 0);
     VF_CUDA((vf_batch*)nullptr, cudaGetLastError());
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(next_pts, dn, sizeof(float2) * n, cudaMemcpyDeviceToHost));
     VF_CUDA((vf_batch*)nullptr, cudaMemcpy(status, ds, n, cudaMemcpyDeviceToHost));
     if (iters_out) VF_CUDA((vf_batch*)nullptr, cudaMemcpy(iters_out, di, sizeof(int) * n, cudaMemcpyDeviceToHost));
     return VF_OK;
+}
+
+vf_status vf_op_lk(const uint8_t* prev, const uint8_t* next, int32_t w, int32_t h, const float* prev_pts, float* next_pts,
+                   uint8_t* status, int32_t n, int32_t max_level, int32_t use_initial_flow, int32_t device, int32_t* iters_out) {
+    return vf_op_lk_win(prev, next, w, h, prev_pts, next_pts, status, n, max_level, kWin, use_initial_flow, device, iters_out);
 }
 
 vf_status vf_debug_set_lk_kernel(int32_t mode) {

@@ -11,6 +11,7 @@ namespace vf {
 // Per-stream arrays are laid out [S][cap] (or [S][H][W]); "parity" double-buffers what one frame hands to the next.
 struct DevBatch {
     int n_streams, W, H, cap, min_dist, flow_back, lk_max_level, n_levels;
+    int lk_win;                      // LK window width (odd, 5..31); 21 = the reference's literal, served by the tuned kernels
     int bucket_bits, n_buckets;      // candidate bucketing resolution (vf_common.cuh: bucket_of)
     size_t cand_cap;                 // per-stream capacity of cand / cand_sorted (power of two >= W*H)
     double quality;
@@ -98,6 +99,14 @@ void launch_lk_temporal_warp(const DevBatch& h, int parity, int cur, int prev, c
 void launch_lk_stereo_warp(const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream);
 void launch_lk_op_warp(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status, int* iters, int n,
                        int max_level, int use_initial_flow, cudaStream_t stream);
+
+// ---- vf_lk_generic.cu: the same four calls for a window width given at run time (lk_win != 21) ----
+bool lk_window_supported(int win);        // odd widths 5..31
+cudaError_t lk_generic_prepare();
+void launch_lk_temporal_generic(const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream);
+void launch_lk_stereo_generic(const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream);
+void launch_lk_op_generic(const PyrView& prev, const PyrView& next, const float2* prev_pts, float2* next_pts, uint8_t* status, int* iters,
+                          int n, int max_level, int use_initial_flow, int win, cudaStream_t stream);
 
 // ---- vf_corners.cu ----
 void set_response_kernel_mode(int mode);   // 0 auto, 1 tiles, 2 strips (parity tests)

@@ -872,6 +872,7 @@ cudaError_t lk_prepare() {
     e = cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     if ((e = lk_warp_prepare()) != cudaSuccess) return e;
+    if ((e = lk_generic_prepare()) != cudaSuccess) return e;
     // same carveout as every other kernel of the library (see corners_prepare)
     if ((e = cudaFuncSetAttribute(lk_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(lk_op_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveout)) != cudaSuccess) return e;
@@ -880,6 +881,7 @@ cudaError_t lk_prepare() {
 }
 
 void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, int prev, cudaStream_t stream) {
+    if (h.lk_win != kWin) { launch_lk_temporal_generic(h, parity, cur, prev, stream); return; }   // vf_lk_generic.cu
     if (lk_use_warp_kernel((long long)h.cap * h.n_streams)) { launch_lk_temporal_warp(h, parity, cur, prev, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);   // bit 1 of the parity argument
@@ -887,6 +889,7 @@ void launch_lk_temporal(const DevBatch* d_batch, const DevBatch& h, int parity, 
                   (const double*)nullptr);
 }
 void launch_lk_stereo(const DevBatch* d_batch, const DevBatch& h, int parity, int cur, const double* dt_host, cudaStream_t stream) {
+    if (h.lk_win != kWin) { launch_lk_stereo_generic(h, parity, cur, dt_host, stream); return; }
     if (lk_use_warp_kernel((long long)h.cap * h.n_streams)) { launch_lk_stereo_warp(h, parity, cur, dt_host, stream); return; }
     dim3 grid(h.cap, h.n_streams);
     const bool staged = lk_plan_staged(h.n_levels, (long long)h.cap * h.n_streams);

@@ -37,9 +37,9 @@ def scharr(img, device: int = -1) -> np.ndarray:
     return out
 
 
-def lk(prev, nxt, prev_pts, max_level: int = 3, init=None, device: int = -1, return_iters: bool = False):
-    """cv::calcOpticalFlowPyrLK(prev, next, prev_pts, init, winSize=(21,21), maxLevel, criteria 30/0.01,
-    flags = USE_INITIAL_FLOW if init is given) -> (next_pts, status)."""
+def lk(prev, nxt, prev_pts, max_level: int = 3, init=None, device: int = -1, return_iters: bool = False, win: int = 21):
+    """cv::calcOpticalFlowPyrLK(prev, next, prev_pts, init, winSize=(win,win), maxLevel, criteria 30/0.01,
+    flags = USE_INITIAL_FLOW if init is given) -> (next_pts, status).  win: odd, 5..31 (21 = the reference's)."""
     a, b = np.ascontiguousarray(_img(prev)), np.ascontiguousarray(_img(nxt))
     assert a.shape == b.shape
     h, w = a.shape
@@ -48,8 +48,8 @@ def lk(prev, nxt, prev_pts, max_level: int = 3, init=None, device: int = -1, ret
     q = np.zeros((n, 2), np.float32) if init is None else np.ascontiguousarray(init, np.float32).reshape(-1, 2).copy()
     st = np.zeros(n, np.uint8)
     it = np.zeros(n, np.int32)
-    check(load().vf_op_lk(a.ctypes.data, b.ctypes.data, w, h, p.ctypes.data, q.ctypes.data, st.ctypes.data, n, max_level,
-                          0 if init is None else 1, device, it.ctypes.data))
+    check(load().vf_op_lk_win(a.ctypes.data, b.ctypes.data, w, h, p.ctypes.data, q.ctypes.data, st.ctypes.data, n, max_level,
+                              int(win), 0 if init is None else 1, device, it.ctypes.data))
     return (q, st, it) if return_iters else (q, st)
 
 
