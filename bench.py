@@ -43,7 +43,7 @@ WORKLOAD = ("configs[1]: EuRoC-shape 752x480 synthetic stereo, cam0/cam1 MEI, ma
 L2_BYTES = 126 * 1024 * 1024
 N_DISTINCT = 224          # distinct stereo frames resident in HBM: 224 * 722 KB = 154 MiB > 126 MiB L2
 N_SM, N_SCHED = 148, 4    # B200: 148 SMs x 4 warp schedulers, one warp instruction per scheduler and clock
-ALL_LEGS = "value,e2e,pipelined,stages,timeline,multi,c3,c4,c5,parity,cpu"
+ALL_LEGS = "value,e2e,pipelined,stages,timeline,multi,c3,c4,c5,win,parity,cpu"
 
 
 def workload_config(n_streams_per_gpu: int = 1) -> dict:
@@ -369,6 +369,9 @@ def main():
     ap.add_argument("--multi-streams", type=int, default=64, help="streams per GPU for the extra multi-stream line (0 = skip)")
     ap.add_argument("--legs", default=ALL_LEGS, help="comma list of the legs to run (profiling runs pick one)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-affinity", default="auto", choices=["auto", "off"],
+                    help="auto: run this rank on the CPUs NVML names as local to its GPU (vins_fast_b200/affinity.py)")
+    ap.add_argument("--dist-backend", default="nccl", choices=["nccl", "gloo"], help="barrier / max-over-ranks plumbing (A/B runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -386,6 +389,11 @@ def main():
         run_reference(args, rank, world)
         return
 
+    affinity = {"bound": False, "why": "--cpu-affinity off"}
+    if args.cpu_affinity == "auto":          # before CUDA comes up, so that the driver's own threads inherit it
+        from vins_fast_b200.affinity import bind_to_gpu
+        affinity = bind_to_gpu(local)
+
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -393,7 +401,10 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if args.dist_backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
 
     import vins_fast_b200 as vf
     from vins_fast_b200 import build as vf_build
@@ -410,7 +421,7 @@ def main():
     def max_over_ranks(ms: float) -> float:
         if world == 1:
             return ms
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms], device="cuda" if args.dist_backend == "nccl" else "cpu", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -684,6 +695,42 @@ def main():
                             "d2h_bytes_per_step": wl["max_cnt"] * 60 + 4},
                     "features_last_frame": nf, "stages_us": st_us, "streaming_kernels": streaming}
 
+        def window_workload(win, steps):
+            """The headline configuration with another LK window width (`lk_win`; csrc/vf_lk_generic.cu): same frames, same
+            two legs (device-resident overlapped frames; host-synchronous call from pinned images)."""
+            wcfg = vf.make_config(W, H, MAX_CNT, MIN_DIST, FLOW_BACK, cam0, cam1, lk_max_level=LEVEL, device=local)
+            wcfg.lk_win = win
+            wb = vf.Batch(wcfg, 1)
+            wst = torch.cuda.ExternalStream(wb.cuda_stream, device=dev)
+            warm = 5
+            with torch.cuda.stream(wst):
+                def dev_steps(first, count):
+                    for k in range(first, first + count):
+                        o = base + fidx[k] * frame_bytes
+                        wb.enqueue_device(times[k], o, o + H * W, W, frame_bytes)
+                    return wb.fetch_counts()
+                dev_steps(0, warm)
+                d_ms, _ = regions(wst, 3, lambda r: dev_steps(warm + r * steps, steps))
+                nf = int(wb.fetch_counts()[0])
+                wb.reset()
+                for k in range(warm):
+                    wb.track_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
+
+                def sync_steps(r):
+                    for k in range(warm + r * steps, warm + (r + 1) * steps):
+                        wb.track_ptrs(times[k], ptr_l[k], W, ptr_r[k], W)
+                s_dev, s_wall = regions(wst, 3, sync_steps)
+            wb.close()
+            st_us = isolated_stage_times(wcfg, 1, lambda sb, k: sb.track_ptrs(times[k], ptr_l[k], W, ptr_r[k], W), warm + 8, warm)
+            dm, sm = med(d_ms), med([max(a, b) for a, b in zip(s_dev, s_wall)])
+            return {"lk_win": win, "lk_kernels_us": {k: st_us.get(k) for k in ("lk_temporal", "lk_stereo")}, "steps": steps, "regions": 3, "value": world * steps / (dm * 1e-3), "unit": "frames/s",
+                    "us_per_frame": dm / steps * 1e3, "e2e": {"value": world * steps / (sm * 1e-3), "us_per_frame": sm / steps * 1e3},
+                    "features_last_frame": nf}
+
+        if "win" in legs:
+            steps_w = max(1, min(K, (n_frames - 5) // 3, 100))
+            workloads["lk_windows"] = {"note": "headline configuration with lk_win 15 / 31 instead of the reference's 21 (run-time-width LK kernels)",
+                                       "w15": window_workload(15, steps_w), "w31": window_workload(31, steps_w)}
         if "c3" in legs:
             workloads["c3"] = other_workload("c3", 72, min(K, 100), 1000 + rank)
         if "c5" in legs:
@@ -805,6 +852,7 @@ def main():
         "config": workload_config(),
         "run": {"repeats": R, "value_regions_ms": v_dev, "value_min_us_per_frame": min(v_dev) / K * 1e3,
                 "value_max_us_per_frame": max(v_dev) / K * 1e3, "features_last_frame": n_last, "cuda_graph": bool(cfg.use_cuda_graph),
+                "cpu_affinity": affinity, "dist_backend": args.dist_backend if world > 1 else None,
                 "create_ms": create_ms, "first_frames_us": [round(v, 1) for v in first_frames_us[:8]],
                 "value_mode": "frames enqueued asynchronously (vf_batch_enqueue_device), records of every frame downloaded; the "
                               "stereo pass of frame k overlaps the temporal chain of frame k+1; each region = exactly K steps timed "

@@ -13,9 +13,9 @@
 //   * the exact-integer shortcut of the 21x21 kernels (vf_lk.cu): b1 only adds x-terms and b2 only y-terms, so if the sum of
 //     the |terms| of each stays below 2^24 every partial sum of every chain is an exactly representable integer and the
 //     ordered chains equal the integer sums.
-// One 128-thread CTA per feature, level after level, all tiles in 21 KB of static shared memory; pixels are fetched with
-// index reflection, so the kernels do not depend on how much of a level's border is filled (the 21x21 kernels' aligned word
-// fetches need 26 of the 28 filled border pixels; a 31x31 window would need 32).  The tuned kernels of vf_lk.cu /
+// One 256-thread CTA per feature, level after level, all tiles in 25 KB of static shared memory; tiles that reach beyond the
+// filled part of a level's border are fetched with index reflection (the 21x21 kernels' aligned word fetches need 26 of the 28
+// filled border pixels; a 31x31 window can reach 36), the others with aligned words like theirs.  The tuned kernels of vf_lk.cu /
 // vf_lk_warp.cu stay the path for the reference's own width; this one trades their per-level pipelining for generality.
 // Checked against the C oracle for every odd width 5..31 (tests/test_gpu_stages.py, tests/test_gpu_tracker.py), and the oracle
 // against cv2 for the same widths (tests/golden/lk_windows_cv2_4_13.npz).
@@ -28,24 +28,29 @@ namespace vf {
 namespace {
 
 constexpr int kGenWinMax = 31;
-constexpr int kGenThreads = 128;
+constexpr int kGenThreads = 256;                                // two warps per SM sub-partition: a 31-wide window is 2.2 x the pixels of a 21-wide one
 constexpr int kGenWarps = kGenThreads / 32;
 constexpr int kGenMargin = 4;                                   // staged J tile = (win + 1) taps + this margin on every side
-constexpr int kGenTI = kGenWinMax + 3;                          // I tile: window + bilinear tap + Scharr ring
+constexpr int kGenTI = kGenWinMax + 3;                          // I tile: window + bilinear tap + Scharr ring (pitch: next multiple of 4)
 constexpr int kGenTD = kGenWinMax + 1;                          // derivative tile: window + bilinear tap
-constexpr int kGenTJ = kGenWinMax + 1 + 2 * kGenMargin;
+constexpr int kGenTJ = kGenWinMax + 1 + 2 * kGenMargin;         // J tile (pitch: next multiple of 4)
 constexpr int kGenPx = kGenWinMax * kGenWinMax;
-constexpr int kGenIpt = 5;                                      // work items per thread: pair items + tail items <= 589 (win 31)
+constexpr int kGenIpt = 3;                                      // work items per thread: pair items + tail items <= 589 (win 31)
+// staged terms of A: per matrix entry four SIMD-lane chains of win * (simd_w / 4) terms and one tail chain of win * tail
+// terms, each padded to a multiple of four -- largest at win 31: 3 * (4 * 188 + 220)
+constexpr int kGenScratch = 3 * (4 * 188 + 220);
+static_assert(kGenScratch >= 2 * (4 * 96 + 220), "the staged terms of b (2 x (4 x win * (simd_w / 8) + win * tail), padded) must fit the scratch area");
 
 struct GenSmem {
     LevelRef pyr[2][kMaxLevels];
-    alignas(16) uint8_t tileI[kGenTI * kGenTI + 4];
+    alignas(16) uint8_t tileI[((kGenTI + 3) & ~3) * kGenTI];
     alignas(16) short2 dtile[kGenTD * kGenTD];
     alignas(16) short Iw[kGenPx + 3];
     alignas(16) short2 dI[kGenPx + 1];
-    alignas(16) uint8_t tileJ[kGenTJ * kGenTJ];
-    alignas(16) int termX[kGenPx + 1];
-    alignas(16) int termY[kGenPx + 1];
+    alignas(16) uint8_t tileJ[((kGenTJ + 3) & ~3) * kGenTJ];
+    // the terms of A staged in accumulation order (prologue of a level) and, later in the same level, the spilled terms of b
+    // (iterations that leave the exact-integer path): never live at the same time
+    alignas(16) int scratch[kGenScratch];
     alignas(16) int4 part[2][kGenWarps];
     alignas(16) float A[4];                                     // A11, A12, A22, 1 / det
     float2 ib;
@@ -61,10 +66,22 @@ __device__ __forceinline__ int refl_clamp(int i, int n) {
     return min(max(i, 0), n - 1);
 }
 
-__device__ __forceinline__ void gen_stage_tile(uint8_t* dst, int side, const LevelRef& L, int x0, int y0) {
-    for (int e = threadIdx.x; e < side * side; e += kGenThreads) {
-        const int y = e / side, x = e - y * side;
-        dst[e] = __ldg(L.p + (ptrdiff_t)refl_clamp(y0 + y, L.h) * L.pitch + refl_clamp(x0 + x, L.w));
+// side x side pixels of a level from (x0, y0) into a shared-memory tile whose pitch is a multiple of 4.  Where the rows lie inside
+// the level's filled REFLECT_101 border (vf_common.cuh: kPyrPadFill; always, for windows up to 21) they are fetched as aligned
+// 32-bit words and realigned with a funnel shift; otherwise pixel by pixel with index reflection.
+__device__ __forceinline__ void gen_stage_tile(uint8_t* dst, int pitch, int side, const LevelRef& L, int x0, int y0) {
+    const int tid = threadIdx.x, m = x0 & 3, xa = x0 - m, ow = pitch >> 2;
+    if (xa >= -kPyrPadFill && xa + 4 * (ow + 1) <= L.w + kPyrPadFill && y0 >= -kPyrPadFill && y0 + side <= L.h + kPyrPadFill) {
+        for (int y = tid >> 3; y < side; y += kGenThreads / 8)
+            for (int k = tid & 7; k < ow; k += 8) {
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(L.p + (ptrdiff_t)(y0 + y) * L.pitch + xa) + k;   // origin, pitch: 16-byte aligned
+                reinterpret_cast<uint32_t*>(dst + y * pitch)[k] = __funnelshift_r(__ldg(wp), __ldg(wp + 1), 8 * m);
+            }
+    } else {
+        for (int y = tid >> 4; y < side; y += kGenThreads / 16) {
+            const uint8_t* row = L.p + (ptrdiff_t)refl_clamp(y0 + y, L.h) * L.pitch;
+            for (int x = tid & 15; x < side; x += 16) dst[y * pitch + x] = __ldg(row + refl_clamp(x0 + x, L.w));
+        }
     }
 }
 
@@ -74,25 +91,35 @@ __device__ __noinline__ LkResult lk_track_generic(GenSmem& sm, int ia, int ja, f
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float half = __fmul_rn((float)(win - 1), 0.5f);
     const float FLT_SCALE = 1.f / (1 << 20);
-    const int TI = win + 3, TD = win + 1, TJ = win + 1 + 2 * kGenMargin, npx = win * win;
+    const int TIs = win + 3, TD = win + 1, TJs = win + 1 + 2 * kGenMargin;   // tile sides
+    const int TI = (TIs + 3) & ~3, TJ = (TJs + 3) & ~3;                     // tile pitches
     const int simd_w = (win >> 3) << 3, ngrp = simd_w >> 3, tailw = win - simd_w;
     const int n_pair = win * ngrp * 4, n_item = n_pair + win * tailw;
+    const int n_q = (n_item + kGenThreads - 1) / kGenThreads;   // item slots in use (uniform): a 15-wide window needs 1 of the 3
     int status = 1, iters = 0, fast = 0;
     float outx = init_pt.x, outy = init_pt.y;
+    const int Ls = win * (simd_w >> 2), Lsp = (Ls + 3) & ~3, Lt = win * tailw, Ltp = (Lt + 3) & ~3, Lm = 4 * Lsp + Ltp;
+    float* termsA = reinterpret_cast<float*>(sm.scratch);
+    // staged terms of b (iterations off the exact-integer path): per component four SIMD-lane chains of win * (simd_w / 8) pair
+    // sums and one tail chain, in accumulation order
+    const int Lb = win * ngrp, Lbp = (Lb + 3) & ~3, Lbm = 4 * Lbp + Ltp;
+    float* termsB = reinterpret_cast<float*>(sm.scratch);
 
     // Work items of an iteration (level-invariant): pair items = the column pairs (c, c + 4) of every 8-wide group of every
     // row (OpenCV's pmaddwd pair sums), tail items = single pixels of the scalar tail columns.
-    int e0[kGenIpt], e1[kGenIpt], o0[kGenIpt], o1[kGenIpt];
+    int e0[kGenIpt], e1[kGenIpt], o0[kGenIpt], o1[kGenIpt], bs[kGenIpt];   // bs: slot of the item's term in its chain of b
 #pragma unroll
     for (int q = 0; q < kGenIpt; ++q) {
         const int it = tid + q * kGenThreads;
-        e0[q] = -1; e1[q] = -1;
+        e0[q] = -1; e1[q] = -1; bs[q] = 0;
         if (it < n_pair) {
             const int y = it / (4 * ngrp), r = it - y * (4 * ngrp);
             e0[q] = y * win + 8 * (r >> 2) + (r & 3); e1[q] = e0[q] + 4;
+            bs[q] = (r & 3) * Lbp + y * ngrp + (r >> 2);
         } else if (it < n_item) {
             const int t = it - n_pair, y = t / tailw;
             e0[q] = y * win + simd_w + (t - y * tailw);
+            bs[q] = 4 * Lbp + t;
         }
         o0[q] = e0[q] < 0 ? 0 : (e0[q] / win) * TJ + (e0[q] - (e0[q] / win) * win);
         o1[q] = e1[q] < 0 ? 0 : (e1[q] / win) * TJ + (e1[q] - (e1[q] / win) * win);
@@ -118,13 +145,21 @@ __device__ __noinline__ LkResult lk_track_generic(GenSmem& sm, int ia, int ja, f
         int w00, w01, w10, w11;
         bilinear_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
 
-        // ---- source side of the level: I tile, Scharr taps, interpolated patches ----
+        // ---- source side of the level: I tile, Scharr taps, interpolated patches.  The J tile around the start estimate goes
+        //      out in the same batch of loads (one global round trip per level instead of two) ----
+        int jx0 = __float2int_rd(__fsub_rn(nx, half)) - kGenMargin, jy0 = __float2int_rd(__fsub_rn(ny, half)) - kGenMargin;
         __syncthreads();                                        // the previous level / pass may still read the tiles
-        gen_stage_tile(sm.tileI, TI, LI, ipx - 1, ipy - 1);
+        gen_stage_tile(sm.tileI, TI, TIs, LI, ipx - 1, ipy - 1);
+        gen_stage_tile(sm.tileJ, TJ, TJs, LJ, jx0, jy0);
+        if (tid < 15) {                                         // +0 in the padding slots of the 15 chains of A (an exact identity)
+            const int m = tid / 5, c = tid - 5 * m;
+            float* ch = termsA + m * Lm + (c < 4 ? c * Lsp : 4 * Lsp);
+            for (int i = (c < 4 ? Ls : Lt); i < (c < 4 ? Lsp : Ltp); ++i) ch[i] = 0.f;
+        }
         __syncthreads();
-        for (int e = tid; e < TD * TD; e += kGenThreads) {
-            const int ty = e / TD, tx = e - ty * TD;
-            const int x = ipx + tx, y = ipy + ty;
+        for (int ty = tid >> 4; ty < TD; ty += kGenThreads / 16)
+        for (int tx = tid & 15; tx < TD; tx += 16) {
+            const int e = ty * TD + tx, x = ipx + tx, y = ipy + ty;
             const bool inside = (unsigned)x < (unsigned)LI.w && (unsigned)y < (unsigned)LI.h;
             const uint8_t* p = sm.tileI + (ty + 1) * TI + (tx + 1);
             const int a0 = p[-TI - 1], a1 = p[-TI], a2 = p[-TI + 1], a3 = p[-1], a4 = p[1], a5 = p[TI - 1], a6 = p[TI], a7 = p[TI + 1];
@@ -133,29 +168,34 @@ __device__ __noinline__ LkResult lk_track_generic(GenSmem& sm, int ia, int ja, f
             sm.dtile[e] = make_short2((short)(inside ? t0p - t0m : 0), (short)(inside ? (t1m + t1p) * 3 + t1c * 10 : 0));
         }
         __syncthreads();
-        for (int e = tid; e < npx; e += kGenThreads) {
-            const int y = e / win, x = e - y * win;
+        for (int y = tid >> 4; y < win; y += kGenThreads / 16)
+        for (int x = tid & 15; x < win; x += 16) {
+            const int e = y * win + x;
             const uint8_t* s = sm.tileI + (y + 1) * TI + (x + 1);
             const short2* dt = sm.dtile + y * TD + x;
             const short2 d00 = dt[0], d01 = dt[1], d10 = dt[TD], d11 = dt[TD + 1];
             sm.Iw[e] = (short)VF_DESCALE(s[0] * w00 + s[1] * w01 + s[TI] * w10 + s[TI + 1] * w11, 9);
-            sm.dI[e] = make_short2((short)VF_DESCALE(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14),
-                                   (short)VF_DESCALE(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14));
+            const int ixv = VF_DESCALE(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14);
+            const int iyv = VF_DESCALE(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14);
+            sm.dI[e] = make_short2((short)ixv, (short)iyv);
+            // the three products in the slot of their chain: |Ix|, |Iy| <= 4080, so each is an exact float
+            float* ta = termsA + (x < simd_w ? (x & 3) * Lsp + y * (simd_w >> 2) + (x >> 2) : 4 * Lsp + y * tailw + (x - simd_w));
+            ta[0] = (float)(ixv * ixv); ta[Lm] = (float)(ixv * iyv); ta[2 * Lm] = (float)(iyv * iyv);
         }
         __syncthreads();
         // ---- the 15 ordered float chains of A, one lane per chain: per matrix entry four SIMD lanes (lane l sees columns
-        //      l, l + 4, ... < simd_w of every row in turn) and the scalar tail (columns simd_w .. win - 1 of every row);
-        //      |Ix|, |Iy| <= 4080, so every product is an exact float whichever way it is formed ----
+        //      l, l + 4, ... < simd_w of every row in turn) and the scalar tail (columns simd_w .. win - 1 of every row), read
+        //      back in that order with 16-byte loads ----
         if (wid == 0) {
             const int ch = min(lane, 14), m = ch / 5, c = ch - 5 * m;
-            const int x_begin = c < 4 ? c : simd_w, x_end = c < 4 ? simd_w : win, x_step = c < 4 ? 4 : 1;
+            const float4* src = reinterpret_cast<const float4*>(termsA + m * Lm + (c < 4 ? c * Lsp : 4 * Lsp));
+            const int n4 = (c < 4 ? Lsp : Ltp) >> 2;
             float acc = 0.f;
-            for (int y = 0; y < win; ++y)
-                for (int x = x_begin; x < x_end; x += x_step) {
-                    const short2 d = sm.dI[y * win + x];
-                    const int fa = m < 2 ? d.x : d.y, fb = m == 0 ? d.x : d.y;
-                    acc = __fadd_rn(acc, (float)(fa * fb));
-                }
+#pragma unroll 4
+            for (int i = 0; i < n4; ++i) {
+                const float4 v = src[i];
+                acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
+            }
             float r[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -186,11 +226,10 @@ __device__ __noinline__ LkResult lk_track_generic(GenSmem& sm, int ia, int ja, f
         short2 g0[kGenIpt], g1[kGenIpt];
 #pragma unroll
         for (int q = 0; q < kGenIpt; ++q) {
+            if (q >= n_q) break;
             I0[q] = sm.Iw[max(e0[q], 0)]; I1[q] = sm.Iw[max(e1[q], 0)];
             g0[q] = e0[q] >= 0 ? sm.dI[e0[q]] : make_short2(0, 0); g1[q] = e1[q] >= 0 ? sm.dI[e1[q]] : make_short2(0, 0);
         }
-        int jx0 = 0, jy0 = 0;
-        bool tile_ready = false;
         int pbuf = 0;
         float pdx = 0.f, pdy = 0.f;
 #pragma unroll 1
@@ -200,12 +239,11 @@ __device__ __noinline__ LkResult lk_track_generic(GenSmem& sm, int ia, int ja, f
                 if (level == 0) status = 0;
                 break;
             }
-            if (!tile_ready || inx < jx0 || iny < jy0 || inx + TD > jx0 + TJ || iny + TD > jy0 + TJ) {
+            if (inx < jx0 || iny < jy0 || inx + TD > jx0 + TJs || iny + TD > jy0 + TJs) {
                 jx0 = inx - kGenMargin; jy0 = iny - kGenMargin;     // (re-)centre the staged tile on the window (uniform branch)
                 __syncthreads();
-                gen_stage_tile(sm.tileJ, TJ, LJ, jx0, jy0);
+                gen_stage_tile(sm.tileJ, TJ, TJs, LJ, jx0, jy0);
                 __syncthreads();
-                tile_ready = true;
             }
             ++iters;
             bilinear_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
@@ -217,6 +255,7 @@ __device__ __noinline__ LkResult lk_track_generic(GenSmem& sm, int ia, int ja, f
             unsigned int abx = 0, aby = 0;
 #pragma unroll
             for (int q = 0; q < kGenIpt; ++q) {
+                if (q >= n_q) break;
                 const uint8_t* p0 = jt + o0[q];
                 const uint8_t* p1 = jt + o1[q];
                 const int d0 = VF_DESCALE(p0[0] * w00 + p0[1] * w01 + p0[TJ] * w10 + p0[TJ + 1] * w11, 9) - I0[q];
@@ -244,34 +283,38 @@ __device__ __noinline__ LkResult lk_track_generic(GenSmem& sm, int ia, int ja, f
                 ib1 = (float)bx; ib2 = (float)by;               // every partial sum of every chain is an exact integer
                 ++fast;
             } else {
-                // ordered chains: lanes 0..7 = the eight SIMD lane accumulators (qb0 / qb1 of lkpyramid.cpp: column offset
-                // m = lane >> 1 with its partner m + 4, component lane & 1), lanes 8, 9 = the scalar tails of b1 / b2
+                // ordered chains, one lane per chain: per component the four SIMD lane accumulators (qb0 / qb1 of lkpyramid.cpp:
+                // column offset c of an 8-wide group with its partner c + 4, one pmaddwd pair sum per group and row) and the scalar
+                // tail.  Every thread converts its items' terms (v_cvt_f32 of the exact int32 pair sum; a tail item's partner is
+                // zero) and parks them in accumulation order; the lanes read them back with 16-byte loads.
 #pragma unroll
                 for (int q = 0; q < kGenIpt; ++q) {
-                    if (e0[q] >= 0) { sm.termX[e0[q]] = ex0[q]; sm.termY[e0[q]] = ey0[q]; }
-                    if (e1[q] >= 0) { sm.termX[e1[q]] = ex1[q]; sm.termY[e1[q]] = ey1[q]; }
+                    if (q >= n_q) break;
+                    if (e0[q] >= 0) { termsB[bs[q]] = (float)(ex0[q] + ex1[q]); termsB[Lbm + bs[q]] = (float)(ey0[q] + ey1[q]); }
+                }
+                if (tid < 10) {                                 // +0 in the padding slots (the area also holds the terms of A)
+                    const int comp = tid / 5, c = tid - 5 * comp;
+                    float* ch = termsB + comp * Lbm + (c < 4 ? c * Lbp : 4 * Lbp);
+                    for (int i = (c < 4 ? Lb : Lt); i < (c < 4 ? Lbp : Ltp); ++i) ch[i] = 0.f;
                 }
                 __syncthreads();
                 if (wid == 0) {
-                    const int ch = min(lane, 9);
-                    const int* T = (ch & 1) ? sm.termY : sm.termX;
+                    const int ch = min(lane, 9), comp = ch / 5, c = ch - 5 * comp;
+                    const float4* src = reinterpret_cast<const float4*>(termsB + comp * Lbm + (c < 4 ? c * Lbp : 4 * Lbp));
+                    const int n4 = (c < 4 ? Lbp : Ltp) >> 2;
                     float acc = 0.f;
-                    if (ch < 8) {
-                        const int m = ch >> 1;
-                        for (int y = 0; y < win; ++y)
-                            for (int g = 0; g < ngrp; ++g)
-                                acc = __fadd_rn(acc, (float)(T[y * win + 8 * g + m] + T[y * win + 8 * g + m + 4]));
-                    } else {
-                        for (int y = 0; y < win; ++y)
-                            for (int x = simd_w; x < win; ++x) acc = __fadd_rn(acc, (float)T[y * win + x]);
+#pragma unroll 4
+                    for (int i = 0; i < n4; ++i) {
+                        const float4 v = src[i];
+                        acc = __fadd_rn(acc, v.x); acc = __fadd_rn(acc, v.y); acc = __fadd_rn(acc, v.z); acc = __fadd_rn(acc, v.w);
                     }
                     // s_k = qb0[k] + qb1[k]; ib += v_reduce_sum({s0, s2, 0, 0}) resp. {s1, s3, 0, 0}
                     float r[2];
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const float m0 = __shfl_sync(0xffffffffu, acc, 0 + k), m1 = __shfl_sync(0xffffffffu, acc, 2 + k);
-                        const float m2 = __shfl_sync(0xffffffffu, acc, 4 + k), m3 = __shfl_sync(0xffffffffu, acc, 6 + k);
-                        const float tl = __shfl_sync(0xffffffffu, acc, 8 + k);
+                        const float m0 = __shfl_sync(0xffffffffu, acc, 5 * k + 0), m1 = __shfl_sync(0xffffffffu, acc, 5 * k + 1);
+                        const float m2 = __shfl_sync(0xffffffffu, acc, 5 * k + 2), m3 = __shfl_sync(0xffffffffu, acc, 5 * k + 3);
+                        const float tl = __shfl_sync(0xffffffffu, acc, 5 * k + 4);
                         const float s0 = __fadd_rn(m0, m2), s2 = __fadd_rn(m1, m3);
                         r[k] = __fadd_rn(tl, __fadd_rn(__fadd_rn(s0, 0.f), __fadd_rn(s2, 0.f)));
                     }
