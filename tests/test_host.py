@@ -140,6 +140,11 @@ def test_estimator_yaml(lib, tmp_path):
     cfg = v.load_config_yaml(str(est))
     assert (cfg.width, cfg.height, cfg.max_cnt, cfg.min_dist, cfg.flow_back, cfg.lk_max_level) == (752, 480, 150, 30, 1, 3)
     assert cfg.cam[0].xi == EUROC_CAM0.xi and cfg.cam[1].fx == EUROC_CAM1.fx       # cam0_calib / cam1_calib next to the file
+    assert (cfg.lk_win, cfg.quality_level) == (21, 0.01)                            # the reference's literals when the keys are absent
+    keyed = tmp_path / "est_keys.yaml"                                              # north star: pyramid levels and window size are parameters
+    keyed.write_text(est.read_text() + "lk_max_level: 4\nlk_win: 15\nquality_level: 0.02\n")
+    cfg2 = v.load_config_yaml(str(keyed))
+    assert (cfg2.lk_max_level, cfg2.lk_win, cfg2.quality_level) == (4, 15, 0.02)
     buf = C.create_string_buffer(64)
     assert lib.vf_yaml_get(str(est).encode(), b"max_cnt", buf, 64) == _lib.VF_OK and buf.value == b"150"
     assert lib.vf_yaml_get(str(est).encode(), b"cam0_calib", buf, 64) == _lib.VF_OK and buf.value == b"cam0_mei.yaml"
@@ -400,3 +405,15 @@ def test_input_side_pgm_euroc_listing_and_stereo_sync(tmp_path):
     for got, (t, l, r, _) in zip(pairs, expect):
         assert abs(float(got[1]) - t) < 1e-6 and int(got[2]) == int(l.sum()) and int(got[3]) == int(r.sum())
     assert "thrown 2 0" in res.stdout          # the left image whose partner was lost + the unpaired extra one
+
+
+def test_cpu_affinity_helper_degrades_without_nvml():
+    """bench.py runs every rank on the CPUs next to its GPU (vins_fast_b200/affinity.py); without NVML / a GPU the helper
+    reports why it did nothing and leaves the process where it is."""
+    import os
+    from vins_fast_b200.affinity import bind_to_gpu, gpu_cpu_set
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu(0)
+    assert set(info) >= {"bound"} and (info["bound"] or "why" in info)
+    if not gpu_cpu_set(0):
+        assert info["bound"] is False and os.sched_getaffinity(0) == before
