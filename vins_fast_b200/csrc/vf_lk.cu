@@ -71,6 +71,7 @@ struct LkSmem {
     alignas(16) float termsB[10 * kChainA];   // terms of b in accumulation order (chain-major, zero padded), spilled
                                               // only when the global exactness bound fails
     alignas(16) float chainB[12];
+    alignas(16) int4 part2[kLkWarps][5];  // per-warp (sum x, sum y, sum |x|, sum |y|) of the four SIMD column chains and of the tail (lk_chain_sums)
     int found[2];
     int termsA_off;                       // byte offset (from the start of this struct) of the staged terms of A,
                                           // [level][kChainsA * kChainA] behind the level blocks, or 0: the chains then form their
@@ -193,6 +194,51 @@ __device__ __noinline__ float2 lk_spill_chains(LkSmem& sm, const LkTerms tm) {
     const float s0 = __fadd_rn(k0.x, k1.x), s1 = __fadd_rn(k0.y, k1.y);
     const float s2 = __fadd_rn(k0.z, k1.z), s3 = __fadd_rn(k0.w, k1.w);
     return make_float2(__fadd_rn(k2.x, __fadd_rn(s0, s2)), __fadd_rn(k2.y, __fadd_rn(s1, s3)));
+}
+
+// Second exactness test of an iteration whose global bound failed, CHAIN BY CHAIN.  A chain of OpenCV's sums of b adds
+// integer terms t_1 .. t_n (pmaddwd pair sums for the eight SIMD-lane chains, single products for the two scalar tails) into a
+// float that starts at +0.  If sum |t_i| < 2^24 over the terms of THAT chain, every term and every partial sum is an integer of
+// magnitude below 2^24, hence a float, hence every addition of the chain is exact and the chain's value is the integer sum --
+// whatever the other chains do.  A chain holds a tenth (SIMD lanes: 42 pair sums) to a quarter (tails: 105 products) of the
+// window's terms, so this test still passes when the whole window's sum is several times 2^24: on the benchmark sequence most
+// of the iterations the global bound turns away (they are what the slowest features of a launch spend their time in).
+// The ten chain values are then combined with the very float additions of lkpyramid.cpp (those need not be exact).
+// Pair items belong to the chain of their column offset c = item & 3 = lane & 3 (items are numbered tid, tid + 128), tail items
+// to the tails.  .z = 0 if a chain fails its bound: the caller then runs the ordered chains (lk_spill_chains).
+struct LkChainIn { int px, py; unsigned int apx, apy; int tx, ty; unsigned int atx, aty; };
+__device__ __noinline__ float4 lk_chain_sums(LkSmem& sm, const LkChainIn in) {   // (ib1, ib2, passed, -): by value, see LkTerms
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int cx = in.px, cy = in.py;
+    unsigned int ax = in.apx, ay = in.apy;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {                 // lanes of equal column offset: 8 per warp
+        cx += __shfl_xor_sync(0xffffffffu, cx, o); cy += __shfl_xor_sync(0xffffffffu, cy, o);
+        ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o);
+    }
+    const int tx = __reduce_add_sync(0xffffffffu, in.tx), ty = __reduce_add_sync(0xffffffffu, in.ty);
+    const unsigned int atx = __reduce_add_sync(0xffffffffu, in.atx), aty = __reduce_add_sync(0xffffffffu, in.aty);
+    if (lane < 4) sm.part2[wid][lane] = make_int4(cx, cy, (int)ax, (int)ay);
+    if (lane == 4) sm.part2[wid][4] = make_int4(tx, ty, (int)atx, (int)aty);
+    __syncthreads();
+    int sx[5], sy[5];
+    unsigned int worst = 0u;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        unsigned int abx = 0u, aby = 0u;
+        sx[c] = 0; sy[c] = 0;
+#pragma unroll
+        for (int w = 0; w < kLkWarps; ++w) {
+            const int4 q = sm.part2[w][c];
+            sx[c] += q.x; sy[c] += q.y; abx += (unsigned int)q.z; aby += (unsigned int)q.w;   // <= 105 * 2^25: no wrap
+        }
+        worst = max(worst, max(abx, aby));
+    }
+    if (worst >= (unsigned int)kExact) return make_float4(0.f, 0.f, 0.f, 0.f);
+    // qb0 + qb1 -> (s0, s1, s2, s3); ib1 += s0 + s2; ib2 += s1 + s3  (as lk_spill_chains)
+    const float s0 = __fadd_rn((float)sx[0], (float)sx[2]), s2 = __fadd_rn((float)sx[1], (float)sx[3]);
+    const float s1 = __fadd_rn((float)sy[0], (float)sy[2]), s3 = __fadd_rn((float)sy[1], (float)sy[3]);
+    return make_float4(__fadd_rn((float)sx[4], __fadd_rn(s0, s2)), __fadd_rn((float)sy[4], __fadd_rn(s1, s3)), 1.f, 0.f);
 }
 
 // Cold path of an iteration: the window left the staged tile of J, one warp re-stages it around the new origin.  Out of line.
@@ -517,7 +563,8 @@ __device__ __noinline__ LkResult lk_track_point_impl(LkSmem& sm, int ia, int ja,
             const uint8_t* jt = tj + (iny - jy0) * kTileJ + (inx - jx0);
             // exact int32 products (idle items own zero gradients); pair items form OpenCV's pmaddwd pair sums, tail items keep
             // single terms.  tx / ty: what this thread adds to b1 / b2; abx / aby: its sum |term| per
-            // component, clamped so that the totals over all contributing items stay below 2^32
+            // component, clamped so that the totals over all contributing items stay below 2^32.  (The products stay in
+            // registers for the cold paths below: forming them again there measured slower, frame span 104.6 -> 108.7 us.)
             int ex0[kIpt], ey0[kIpt], ex1[kIpt], ey1[kIpt];
             int tx = 0, ty = 0, abx = 0, aby = 0;
 #pragma unroll
@@ -557,11 +604,27 @@ __device__ __noinline__ LkResult lk_track_point_impl(LkSmem& sm, int ia, int ja,
                 ib1 = (float)bx; ib2 = (float)by;
                 ++fast;
             } else {
-                // (cold, out of line: keeps the hot loop compact in the instruction caches)
-                LkTerms tm;
+                // (cold, out of line: keeps the hot loop compact in the instruction caches)  First the exactness test chain by
+                // chain; the ordered chains only if one of the ten fails it.
+                LkChainIn ci = {0, 0, 0u, 0u, 0, 0, 0u, 0u};
 #pragma unroll
-                for (int q = 0; q < kIpt; ++q) { tm.ex0[q] = ex0[q]; tm.ey0[q] = ey0[q]; tm.ex1[q] = ex1[q]; tm.ey1[q] = ey1[q]; }
-                const float2 ib = lk_spill_chains(sm, tm);
+                for (int q = 0; q < kIpt; ++q) {
+                    const int sx_ = ex0[q] + ex1[q], sy_ = ey0[q] + ey1[q];
+                    if (is_pair[q]) { ci.px += sx_; ci.py += sy_; ci.apx += (unsigned int)abs(sx_); ci.apy += (unsigned int)abs(sy_); }
+                    else {
+                        ci.tx += sx_; ci.ty += sy_;
+                        ci.atx += (unsigned int)(abs(ex0[q]) + abs(ex1[q])); ci.aty += (unsigned int)(abs(ey0[q]) + abs(ey1[q]));
+                    }
+                }
+                const float4 cs = lk_chain_sums(sm, ci);
+                float2 ib = make_float2(cs.x, cs.y);
+                if (cs.z != 0.f) ++fast;
+                else {
+                    LkTerms tm;
+#pragma unroll
+                    for (int q = 0; q < kIpt; ++q) { tm.ex0[q] = ex0[q]; tm.ey0[q] = ey0[q]; tm.ex1[q] = ex1[q]; tm.ey1[q] = ey1[q]; }
+                    ib = lk_spill_chains(sm, tm);
+                }
                 ib1 = ib.x; ib2 = ib.y;
                 LK_TF(8);
             }
@@ -801,7 +864,12 @@ __device__ __forceinline__ void lk_stereo_body(const DevBatch& b, int parity_arg
 // every kernel that calls it, so two kernels would each carry their own 80 KB copy of the pass -- and in overlapped frames the
 // temporal launch of frame k+1 and the stereo launch of frame k share every SM: two copies competed for the 32 KB of L1.5
 // instruction cache (`no_instruction` was already the second stall reason of either kernel alone).  One kernel, one copy.
-__global__ void __launch_bounds__(kLkThreads) lk_pair_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev,
+#ifdef VF_LK_MINB     // A/B aid: resident CTAs per SM the register budget is sized for (5 caps the kernel at 96 registers, 1 lifts every cap)
+#define VF_LK_BOUNDS __launch_bounds__(kLkThreads, VF_LK_MINB)
+#else
+#define VF_LK_BOUNDS __launch_bounds__(kLkThreads)
+#endif
+__global__ void VF_LK_BOUNDS lk_pair_kernel(const __grid_constant__ DevBatch b, int parity_arg, int cur, int prev,
                                                              const double* __restrict__ dt_host) {
     pdl_wait(); pdl_release();
     if (parity_arg & 4) lk_stereo_body(b, parity_arg & ~4, cur, dt_host);
