@@ -21,9 +21,11 @@ for arg in sys.argv[1:]:
     hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     names = rows[hdr]
     col = {n: i for i, n in enumerate(names)}
-    for r in rows[hdr + 2:]:
-        if len(r) < len(names) or (rx and not re.search(rx, r[col["Kernel Name"]])):
-            continue
+    # several launches may match (lk_pair_kernel is both the temporal and the stereo pair of calls): the one that executed the
+    # most warp instructions is taken (the stereo pair: two passes over all levels)
+    cand = [r for r in rows[hdr + 2:] if len(r) >= len(names) and (not rx or re.search(rx, r[col["Kernel Name"]]))]
+    cand.sort(key=lambda r: -float(r[col["smsp__inst_executed.sum"]].replace(",", "")))
+    for r in cand[:1]:
         f = lambda n: float(r[col[n]].replace(",", ""))
         unit = rows[hdr + 1]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
