@@ -51,7 +51,7 @@ def workload_config(n_streams_per_gpu: int = 1) -> dict:
     return {"workload": WORKLOAD, "width": W, "height": H, "max_cnt": MAX_CNT, "min_dist": MIN_DIST, "flow_back": FLOW_BACK,
             "lk_max_level": LEVEL, "lk_win": 21, "cameras": "EuRoC cam0/cam1 MEI (vins/config/euroc/cam{0,1}_mei.yaml)",
             "streams_per_gpu": n_streams_per_gpu, "distinct_frames": N_DISTINCT,
-            "sequence": "vins_fast_b200.synth.StereoSequence(seed = stream index), frames visited forward / backward",
+            "sequence": "vins_fast_b200.synth.StereoSequence(seed 0) on every rank -- equal work per GPU; --sequence-seeds rank: one seed per rank -- frames visited forward / backward",
             "l2": f"inputs larger than L2: {N_DISTINCT} distinct stereo frames = {N_DISTINCT * 2 * H * W / 2**20:.0f} MiB "
                   f"(L2 = 126 MiB); a frame is re-read only after all the others went through"}
 
@@ -371,6 +371,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-affinity", default="auto", choices=["auto", "off"],
                     help="auto: run this rank on the CPUs NVML names as local to its GPU (vins_fast_b200/affinity.py)")
+    ap.add_argument("--sequence-seeds", default="same", choices=["same", "rank"],
+                    help="same: every rank runs seed 0 (equal work per GPU); rank: one synthetic sequence per rank")
     ap.add_argument("--dist-backend", default="nccl", choices=["nccl", "gloo"], help="barrier / max-over-ranks plumbing (A/B runs)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -469,7 +471,13 @@ def main():
     # D distinct frames (> L2 in total), visited forward then backward (0..D-1, D-2..0, ...): consecutive steps always
     # see neighbouring frames of the sequence, and every frame is re-read only after all the others went through L2.
     D = N_DISTINCT
-    frames = make_frames(rank, D)                                # one independent sequence per rank
+    # Every rank tracks its own stream; by default all of them are fed the SAME synthetic sequence (seed 0), so that the work per
+    # GPU is equal at every N -- what weak scaling is about.  The cost of a frame depends on the sequence (seeds 0..7 of this
+    # workload: 67.5 .. 73.7 us per overlapped frame on one GPU, per-seed runs in DESIGN.md 7), and with one seed per rank the
+    # MAX over ranks reports that spread as a scaling loss (round-2 lines before this change: 0.89 at 8 GPUs).
+    # --sequence-seeds rank restores one seed per rank; config 4 (c4_sharded) always runs 64 distinct sequences.
+    seq_seed = int(os.environ["VF_BENCH_SEED"]) if "VF_BENCH_SEED" in os.environ else (rank if args.sequence_seeds == "rank" else 0)
+    frames = make_frames(seq_seed, D)
     frame_bytes = 2 * H * W
     d_frames = torch.from_numpy(frames).cuda()                   # inputs resident in HBM
     p_frames = torch.from_numpy(frames).pin_memory()             # pinned host copies for the e2e legs
@@ -732,9 +740,9 @@ def main():
             workloads["lk_windows"] = {"note": "headline configuration with lk_win 15 / 31 instead of the reference's 21 (run-time-width LK kernels)",
                                        "w15": window_workload(15, steps_w), "w31": window_workload(31, steps_w)}
         if "c3" in legs:
-            workloads["c3"] = other_workload("c3", 72, min(K, 100), 1000 + rank)
+            workloads["c3"] = other_workload("c3", 72, min(K, 100), 1000 + (rank if args.sequence_seeds == "rank" else 0))
         if "c5" in legs:
-            workloads["c5"] = other_workload("c5", 8, min(K, 40), 2000 + rank)
+            workloads["c5"] = other_workload("c5", 8, min(K, 40), 2000 + (rank if args.sequence_seeds == "rank" else 0))
         if "c4" in legs:
             # BASELINE config 4 as specified: 64 independent sequences (seed = global stream index) partitioned over the ranks
             # (stream s -> rank s mod world), the rank's share batched in ONE vf_batch; aggregate frames/s over all ranks.
