@@ -292,6 +292,36 @@ def test_pipelined_enqueue_fetch_lagged(lib, oracle, euroc_frames):
     batch.close()
 
 
+@pytest.mark.parametrize("win", [15, 31])
+def test_other_lk_window_overlapped_plan(lib, oracle, euroc_frames, win):
+    """The run-time-width LK kernels under the OVERLAPPED frame plan (vf_batch_enqueue + vf_batch_fetch_lagged: the stereo pass
+    of frame k beside the chain of frame k + 1), three streams in the batch: every stream bit-identical to the oracle."""
+    import vins_fast_b200 as v
+    cfg = v.make_config(752, 480, 150, 30, 1, EUROC_CAM0.__dict__, EUROC_CAM1.__dict__)
+    cfg.lk_win = win
+    S = 3
+    batch = v.Batch(cfg, S)
+    refs = [oracle.CFeatureTracker(EUROC_CAM0, EUROC_CAM1, 752, 480, 150, 30, 1, 3, win) for _ in range(S)]
+    frames = euroc_frames[:8]
+    want, keep = [], []
+    for k in range(len(frames)):
+        # stream s sees the sequence shifted by s frames: three different streams out of one fixture
+        imgs = [frames[(k + s) % len(frames)] for s in range(S)]
+        want.append([refs[s].track_image(frames[k][0], imgs[s][1], imgs[s][2]) for s in range(S)])
+        pl = (C.c_void_p * S)(*[im[1].ctypes.data for im in imgs])
+        pr = (C.c_void_p * S)(*[im[2].ctypes.data for im in imgs])
+        keep.append((pl, pr))
+        batch.enqueue_ptrs(frames[k][0], pl, 752, pr, 752)
+        if k >= 1:
+            got = batch.fetch(1)
+            for s in range(S):
+                assert_frames_equal(oracle.records_to_frame(got[s]), want[k - 1][s], f"win {win} lagged frame {k - 1} stream {s}")
+    got = batch.fetch(0)
+    for s in range(S):
+        assert_frames_equal(oracle.records_to_frame(got[s]), want[-1][s], f"win {win} last frame stream {s}")
+    batch.close()
+
+
 def test_mixed_synchronous_and_overlapped_frames(lib, oracle, euroc_frames):
     """The synchronous call and the overlapped enqueue use different stream plans for the same kernels; a sequence may
     switch between them at any frame and must still reproduce the oracle frame after frame (also without CUDA graphs)."""
