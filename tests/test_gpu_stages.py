@@ -172,6 +172,35 @@ def test_lk_other_window_sizes_bit_exact(lib, oracle, euroc_frames, win):
     assert np.array_equal(rst, orst) and np.array_equal(rev.view(np.uint32), orev.view(np.uint32))
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_lk_random_windows_levels_shapes(lib, oracle, seed):
+    """Random odd window 5..31 (21 included: the tuned kernels), level count, image size and point set (inside, on and outside
+    the border), forward and reverse with an initial flow -- the same generator the oracle is checked with against live cv2
+    (tests/test_oracle_golden.py::test_oracle_vs_live_cv2_lk_random_windows)."""
+    from vins_fast_b200 import ops
+    from vins_fast_b200.synth import StereoSequence
+    rng = np.random.default_rng(1000 + seed)
+    win = int(rng.choice(np.arange(5, 33, 2)))
+    level = int(rng.integers(0, 6))
+    h, w = int(rng.integers(70, 260)), int(rng.integers(70, 330))
+    seq = StereoSequence(30 + seed, 352, 288)
+    _, a, c = seq.frame(int(rng.integers(0, 5)))
+    _, b, _ = seq.frame(6)
+    y0, x0 = int(rng.integers(0, 288 - h)), int(rng.integers(0, 352 - w))
+    a, b, c = (np.ascontiguousarray(x[y0:y0 + h, x0:x0 + w]) for x in (a, b, c))
+    pts = np.stack([rng.uniform(-win, w + win, 120), rng.uniform(-win, h + win, 120)], 1).astype(np.float32)
+    for x, y in ((a, b), (a, c)):
+        q, st, it = ops.lk(x, y, pts, level, return_iters=True, win=win)
+        rq, rst, rit = oracle.lk(oracle.Pyramid(x, level, win), oracle.Pyramid(y, level, win), pts, level, win, return_iters=True)
+        assert np.array_equal(st, rst) and np.array_equal(it, rit), (win, level, h, w)
+        assert np.array_equal(q.view(np.uint32), rq.view(np.uint32)), (win, level, h, w)
+        lv = min(1, level)
+        init = (pts + rng.uniform(-2, 2, pts.shape)).astype(np.float32)
+        r2, s2 = ops.lk(y, x, q, lv, init=init, win=win)
+        o2, os2 = oracle.lk(oracle.Pyramid(y, lv, win), oracle.Pyramid(x, lv, win), q, lv, win, init=init)
+        assert np.array_equal(s2, os2) and np.array_equal(r2.view(np.uint32), o2.view(np.uint32)), (win, level, h, w)
+
+
 @pytest.mark.parametrize("win", [7, 15, 31])
 def test_lk_other_window_sizes_ordered_chains_and_textureless(lib, oracle, win):
     """The high-contrast checker of the 21x21 test (sums beyond 2^24: ordered float chains in the layout of this width) and a

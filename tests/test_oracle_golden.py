@@ -252,6 +252,38 @@ def test_oracle_vs_live_cv2_stages(oracle, shape, level):
 
 
 @pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+@pytest.mark.parametrize("seed", range(10))
+def test_oracle_vs_live_cv2_lk_random_windows(oracle, seed):
+    """calcOpticalFlowPyrLK with a random odd window 5..31, random level count, image size, point set (inside, on and outside
+    the border) and optionally an initial flow: the C oracle against the live OpenCV routine, bit for bit (positions of lost
+    points included).  Pins the width-dependent chain layouts beyond the committed fixture."""
+    from vins_fast_b200.synth import StereoSequence
+    rng = np.random.default_rng(1000 + seed)
+    win = int(rng.choice(np.arange(5, 33, 2)))
+    level = int(rng.integers(0, 6))
+    h, w = int(rng.integers(70, 260)), int(rng.integers(70, 330))
+    seq = StereoSequence(30 + seed, 352, 288)
+    _, a, c = seq.frame(int(rng.integers(0, 5)))
+    _, b, _ = seq.frame(6)
+    y0, x0 = int(rng.integers(0, 288 - h)), int(rng.integers(0, 352 - w))
+    a, b, c = (np.ascontiguousarray(x[y0:y0 + h, x0:x0 + w]) for x in (a, b, c))
+    pts = np.stack([rng.uniform(-win, w + win, 120), rng.uniform(-win, h + win, 120)], 1).astype(np.float32)
+    for x, y in ((a, b), (a, c)):
+        nxt, st, _ = cv2.calcOpticalFlowPyrLK(x, y, pts.reshape(-1, 1, 2), None, winSize=(win, win), maxLevel=level)
+        q, s = oracle.lk(oracle.Pyramid(x, level, win), oracle.Pyramid(y, level, win), pts, level, win)
+        assert np.array_equal(s, st.reshape(-1)), (win, level, h, w)
+        assert np.array_equal(_bits(q), _bits(nxt.reshape(-1, 2))), (win, level, h, w)
+        lv = min(1, level)
+        init = (pts + rng.uniform(-2, 2, pts.shape)).astype(np.float32)
+        rev, rst, _ = cv2.calcOpticalFlowPyrLK(y, x, nxt.copy(), init.reshape(-1, 1, 2).copy(), winSize=(win, win), maxLevel=lv,
+                                               criteria=(cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01),
+                                               flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        r2, s2 = oracle.lk(oracle.Pyramid(y, lv, win), oracle.Pyramid(x, lv, win), nxt.reshape(-1, 2), lv, win, init=init)
+        assert np.array_equal(s2, rst.reshape(-1)), (win, level, h, w)
+        assert np.array_equal(_bits(r2), _bits(rev.reshape(-1, 2))), (win, level, h, w)
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
 def test_oracle_vs_live_cv2_track_image(oracle):
     from oracle.cv2_oracle import Cv2FeatureTracker
     from vins_fast_b200.synth import StereoSequence
